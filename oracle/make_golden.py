@@ -1,0 +1,126 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container, where the reference is
+mounted read-only at /root/reference; the GPU box has no such mount, so the
+vectors are committed.  Usage::
+
+    python oracle/make_golden.py            # corr fixtures (+ e2e if host model importable)
+
+What is recorded
+  corr_*.npz   inputs (fmap1, fmap2, coords_k) and the reference outputs of
+               ``FF_RAFT_Core/corr.py`` CorrBlock: the 4 pyramid levels and the
+               lookup result for each coords_k.
+  ffraft_e2e.npz  inputs + ``FF_RAFT_FUSION`` test-mode outputs (flow_lo, flow_up)
+               for weights filled by ``tests/weights.py`` (deterministic by key name,
+               so no 30 MB state_dict needs to be committed).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/core/models/ff-raft"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _ref_corr():
+    sys.path.insert(0, REF)
+    from FF_RAFT_Core.corr import CorrBlock  # noqa: E402  (the reference's own class)
+    from FF_RAFT_Core.utils.utils import coords_grid  # noqa: E402
+    return CorrBlock, coords_grid
+
+
+def coords_cases(rng: np.random.Generator, grid: np.ndarray) -> dict[str, np.ndarray]:
+    """Coordinate sets covering the edge cases SURVEY §8c T2 names."""
+    b, _, h, w = grid.shape
+    n = lambda s: rng.standard_normal(grid.shape).astype(np.float32) * np.float32(s)
+    cases = {
+        "grid": grid.copy(),                                   # exact integers (iteration 0)
+        "half": grid + np.float32(0.5),                        # exact half-integers
+        "s1": grid + n(1.0),
+        "s3": grid + n(3.0),
+        "s20": grid + n(20.0),                                 # ~40% out-of-bounds taps
+        "far": grid + n(200.0),                                # almost everything outside
+        "edge": grid * np.float32(0) + np.float32(-0.25),      # hugging the top-left corner
+    }
+    e2 = grid.copy()
+    e2[:, 0] = np.float32(w - 1) + np.float32(0.75)
+    e2[:, 1] = np.float32(h - 1) - np.float32(0.125)
+    cases["edge_br"] = e2
+    return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in cases.items()}
+
+
+def make_corr(name: str, b: int, d: int, h: int, w: int, seed: int, scale: float = 4.4, keep=None):
+    CorrBlock, coords_grid = _ref_corr()
+    rng = np.random.default_rng(seed)
+    f1 = (rng.standard_normal((b, d, h, w)) * scale).astype(np.float32)
+    f2 = (rng.standard_normal((b, d, h, w)) * scale).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        blk = CorrBlock(torch.from_numpy(f1), torch.from_numpy(f2), num_levels=4, radius=4)
+        grid = coords_grid(b, h, w, device="cpu").numpy()
+        cases = coords_cases(rng, grid)
+        if keep is not None:
+            cases = {k: v for k, v in cases.items() if k in keep}
+        out = {"fmap1": f1, "fmap2": f2}
+        for i, lvl in enumerate(blk.corr_pyramid):
+            out[f"level{i}"] = lvl.numpy()[:, 0]
+        for k, c in cases.items():
+            out[f"coords_{k}"] = c
+            out[f"lookup_{k}"] = blk(torch.from_numpy(c)).numpy()
+    path = os.path.join(GOLD, f"corr_{name}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items() if k.startswith(("level", "lookup_grid"))})
+
+
+def make_e2e():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, REF)
+    from weights import fill_state_dict, synthetic_pair  # tests/weights.py
+    from common import yaml_parser  # reference
+    from FF_RAFT_Core.ff_raft import FF_RAFT_FUSION  # reference
+
+    cfg = yaml_parser(os.path.join(REF, "config/experiment/ffraft_chairs_orb.yaml"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = FF_RAFT_FUSION(use_fusion="parallel", fusion_channels=cfg.MODEL.FUSION_CHANNEL,
+                               raft_small=False, dropout=0.0, alternate_corr=False,
+                               abandon_fnet=False, fuse_cnet=True, cfg=cfg)
+        sd = model.state_dict()
+        fill_state_dict(sd, seed=1234)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        out = {}
+        for tag, (b, hh, ww, iters) in {"a": (1, 128, 192, 12), "b": (2, 136, 160, 4)}.items():
+            im1, im2, m1, m2 = synthetic_pair(b, hh, ww, seed=1234 + b)
+            with torch.no_grad():
+                lo, up = model(im1, im2, m1, m2, raft_iters=iters, test_mode=True)
+            out[f"{tag}_shape"] = np.array([b, hh, ww, iters])
+            out[f"{tag}_flow_lo"] = lo.numpy()
+            out[f"{tag}_flow_up"] = up.numpy()
+            print(tag, "flow_up mean |f| =", float(up.abs().mean()), "max", float(up.abs().max()))
+    out["state_keys"] = np.array(sorted(sd.keys()))
+    path = os.path.join(GOLD, "ffraft_e2e.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", choices=["corr", "e2e"], default=None)
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    if a.only in (None, "corr"):
+        make_corr("b1_d32_16x24", b=1, d=32, h=16, w=24, seed=11)
+        make_corr("b2_d16_17x21", b=2, d=16, h=17, w=21, seed=12, keep=("grid", "s3", "s20"))      # odd dims: floor pooling
+        make_corr("b1_d256_16x16", b=1, d=256, h=16, w=16, seed=13, keep=("grid", "s1"))    # the real D
+    if a.only in (None, "e2e"):
+        make_e2e()
