@@ -1,0 +1,87 @@
+"""ctypes binding of libffcorr.so (the C ABI declared in include/ffcorr.h).
+
+There is NO CPU fallback and no alternative backend: if the shared library is missing the
+import of any operator fails loudly with the build command.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libffcorr.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+PREC_FP16, PREC_FP32, PREC_BF16X3, PREC_TF32 = 0, 1, 2, 3
+PRECISIONS = {"fp16": PREC_FP16, "fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "tf32": PREC_TF32}
+MAX_LEVELS = 8
+
+_lock = threading.Lock()
+_lib = None
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_PROTOS = {
+    # name: (restype, argtypes)
+    "ffcorr_version": (_i, []),
+    "ffcorr_last_error": (ctypes.c_char_p, []),
+    "ffcorr_device_info": (_i, [ctypes.POINTER(_i)] * 3),
+    "ffcorr_volume_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
+    "ffcorr_volume_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "ffcorr_pyramid_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
+    "ffcorr_lookup_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_lookup_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_pyramid_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
+    "ffcorr_volume_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_pwc81_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]),
+    "ffcorr_pwc81_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+}
+SYMBOLS = tuple(_PROTOS)
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libffcorr.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", CSRC, "-j8"], stdout=out, stderr=None if verbose else subprocess.STDOUT)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: the CUDA extension is the only backend of this package "
+                        f"(no CPU or PyTorch fallback). Build it with `make -C {CSRC}` or "
+                        f"`python -c 'import __graft_entry__ as g; g.build()'`."
+                    )
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _PROTOS.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ffcorr_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr_array(tensors) -> ctypes.Array:
+    arr = (_vp * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,189 @@
+"""CorrBlock: drop-in for ``FF_RAFT_Core/corr.py:12-60`` backed by libffcorr (sm_100a).
+
+Same surface as the reference: ``CorrBlock(fmap1, fmap2, num_levels=4, radius=4)`` builds the
+all-pairs volume and its average-pool pyramid once (reference ``corr.py:13-27``), and
+``block(coords)`` returns the ``[B, num_levels*(2r+1)^2, h, w]`` fp32 window lookup
+(``corr.py:29-50``).  ``num_levels``, ``radius`` and ``corr_pyramid`` are attributes as in the
+reference (``corr.py:14-16``); ``corr_pyramid[i]`` is ``[B*h*w, 1, h>>i, w>>i]``.
+
+Differences, all deliberate:
+  * CUDA only.  A CPU tensor raises ``NotImplementedError`` (there is no fallback path).
+  * the contraction runs on tcgen05 tensor cores with fp16-rounded operands and fp32
+    accumulation by default (the reference uses TF32 cuBLAS, ``common.py:25-27``);
+    ``precision="fp32" | "bf16x3" | "tf32"`` select the other operand modes.
+  * one kernel per call instead of ~60 (lookup) / 4 (pyramid) / 2 (volume).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+
+__all__ = ["CorrBlock", "coords_grid", "correlation_volume", "correlation_pyramid", "lookup"]
+
+DEFAULT_PRECISION = "fp16"
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise NotImplementedError(
+            f"{name} is on {t.device}: the B200 correlation path has no CPU implementation"
+        )
+
+
+def coords_grid(batch: int, ht: int, wd: int, device) -> torch.Tensor:
+    """``utils/utils.py:74-77``: [B, 2, ht, wd], channel 0 = x, channel 1 = y."""
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+def _level_shapes(b: int, h: int, w: int, num_levels: int):
+    return [(b * h * w, 1, h >> i, w >> i) for i in range(num_levels)]
+
+
+# ------------------------------------------------------------------------------------
+# raw (non-differentiable) launches
+# ------------------------------------------------------------------------------------
+def _volume_pyramid_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, precision: int) -> List[torch.Tensor]:
+    b, d, h, w = fmap1.shape
+    if (h >> (num_levels - 1)) < 1 or (w >> (num_levels - 1)) < 1:
+        raise ValueError(f"{h}x{w} feature map is too small for {num_levels} pyramid levels")
+    L = _lib.lib()
+    levels = [torch.empty(s, device=fmap1.device, dtype=torch.float32) for s in _level_shapes(b, h, w, num_levels)]
+    ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
+    ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
+    stream = _lib.current_stream()
+    _lib.check(L.ffcorr_volume_f32(fmap1.data_ptr(), fmap2.data_ptr(), levels[0].data_ptr(), b, d, h, w, precision,
+                                   ws.data_ptr() if ws_bytes else None, ws_bytes, stream), "ffcorr_volume_f32")
+    _lib.check(L.ffcorr_pyramid_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream), "ffcorr_pyramid_f32")
+    # `ws` may be freed here: the caching allocator is stream-ordered on the current stream.
+    return levels
+
+
+def _lookup_raw(levels, level_ptrs, coords: torch.Tensor, radius: int) -> torch.Tensor:
+    b, _, h, w = coords.shape
+    k = 2 * radius + 1
+    out = torch.empty((b, len(levels) * k * k, h, w), device=coords.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ffcorr_lookup_f32(level_ptrs, len(levels), coords.data_ptr(), out.data_ptr(), b, h, w, radius,
+                                            _lib.current_stream()), "ffcorr_lookup_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------
+# autograd wrappers (reference: ATen autograd of corr.py:26,45,58; coords never need a
+# gradient because the caller detaches them, raft.py:216-217)
+# ------------------------------------------------------------------------------------
+class _VolumePyramid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, num_levels, precision):
+        levels = _volume_pyramid_raw(fmap1, fmap2, num_levels, precision)
+        ctx.save_for_backward(fmap1, fmap2)
+        ctx.num_levels = num_levels
+        return tuple(levels)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        fmap1, fmap2 = ctx.saved_tensors
+        b, d, h, w = fmap1.shape
+        L = _lib.lib()
+        shapes = _level_shapes(b, h, w, ctx.num_levels)
+        g = []
+        for i, (gi, s) in enumerate(zip(grads, shapes)):
+            if gi is None:
+                g.append(torch.zeros(s, device=fmap1.device, dtype=torch.float32))
+            else:
+                gi = gi.contiguous().float()
+                g.append(gi.clone() if i < ctx.num_levels - 1 else gi)  # finer levels are updated in place
+        stream = _lib.current_stream()
+        _lib.check(L.ffcorr_pyramid_bwd_f32(_lib.ptr_array(g), ctx.num_levels, b * h * w, h, w, stream),
+                   "ffcorr_pyramid_bwd_f32")
+        g1 = torch.empty_like(fmap1) if ctx.needs_input_grad[0] else None
+        g2 = torch.empty_like(fmap2) if ctx.needs_input_grad[1] else None
+        _lib.check(L.ffcorr_volume_bwd_f32(g[0].data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(),
+                                           g1.data_ptr() if g1 is not None else None,
+                                           g2.data_ptr() if g2 is not None else None, b, d, h, w, stream),
+                   "ffcorr_volume_bwd_f32")
+        return g1, g2, None, None
+
+
+class _Lookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, radius, *levels):
+        out = _lookup_raw(levels, _lib.ptr_array(levels), coords, radius)
+        ctx.save_for_backward(coords)
+        ctx.radius = radius
+        ctx.shapes = [tuple(l.shape) for l in levels]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (coords,) = ctx.saved_tensors
+        b, _, h, w = coords.shape
+        gout = gout.contiguous().float()
+        glv = [torch.zeros(s, device=coords.device, dtype=torch.float32) for s in ctx.shapes]
+        _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), len(glv), coords.data_ptr(), gout.data_ptr(),
+                                                    b, h, w, ctx.radius, _lib.current_stream()), "ffcorr_lookup_bwd_f32")
+        return (None, None, *glv)
+
+
+def _prep(fmap: torch.Tensor, name: str) -> torch.Tensor:
+    _require_cuda(fmap, name)
+    if fmap.dim() != 4:
+        raise ValueError(f"{name} must be [B, D, h, w], got {tuple(fmap.shape)}")
+    return fmap.float().contiguous()
+
+
+def _precision_code(precision) -> int:
+    if isinstance(precision, int):
+        return precision
+    try:
+        return _lib.PRECISIONS[precision or DEFAULT_PRECISION]
+    except KeyError:
+        raise ValueError(f"unknown precision {precision!r}; one of {sorted(_lib.PRECISIONS)}") from None
+
+
+def correlation_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None) -> List[torch.Tensor]:
+    """Volume + pyramid (``corr.py:18-27``), differentiable w.r.t. both feature maps."""
+    fmap1, fmap2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
+    if fmap1.shape != fmap2.shape:
+        raise ValueError(f"fmap shapes differ: {tuple(fmap1.shape)} vs {tuple(fmap2.shape)}")
+    code = _precision_code(precision)
+    if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+        return list(_VolumePyramid.apply(fmap1, fmap2, num_levels, code))
+    return _volume_pyramid_raw(fmap1, fmap2, num_levels, code)
+
+
+def correlation_volume(fmap1, fmap2, precision=None) -> torch.Tensor:
+    """``CorrBlock.corr`` (``corr.py:52-60``): [B, h, w, 1, h, w]."""
+    b, _, h, w = fmap1.shape
+    return correlation_pyramid(fmap1, fmap2, 1, precision)[0].view(b, h, w, 1, h, w)
+
+
+def lookup(levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None) -> torch.Tensor:
+    _require_cuda(coords, "coords")
+    coords = coords.float().contiguous()
+    if torch.is_grad_enabled() and any(l.requires_grad for l in levels):
+        return _Lookup.apply(coords, radius, *levels)
+    return _lookup_raw(levels, level_ptrs if level_ptrs is not None else _lib.ptr_array(levels), coords, radius)
+
+
+class CorrBlock:
+    def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4, precision: Optional[str] = None):
+        self.num_levels = num_levels
+        self.radius = radius
+        self.corr_pyramid = correlation_pyramid(fmap1, fmap2, num_levels, precision)
+        self._ptrs = _lib.ptr_array(self.corr_pyramid)
+        self._shape = (fmap1.shape[0], fmap1.shape[2], fmap1.shape[3])
+
+    def __call__(self, coords: torch.Tensor) -> torch.Tensor:
+        b, two, h, w = coords.shape
+        if (b, h, w) != self._shape or two != 2:
+            raise ValueError(f"coords {tuple(coords.shape)} does not match the volume built for B,h,w={self._shape}")
+        return lookup(self.corr_pyramid, coords, self.radius, self._ptrs)
+
+    @staticmethod
+    def corr(fmap1, fmap2, precision: Optional[str] = None):
+        return correlation_volume(fmap1, fmap2, precision)

@@ -1,0 +1,51 @@
+// Shared helpers for libffcorr (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ffcorr.h"
+
+namespace ffcorr {
+
+// thread-local last-error buffer (api.cu)
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return FFCORR_OK;
+}
+
+#define FFCORR_REQUIRE(cond, code, ...)          \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::ffcorr::set_error(__VA_ARGS__);    \
+            return (code);                       \
+        }                                        \
+    } while (0)
+
+#define FFCORR_CUDA(expr)                                                        \
+    do {                                                                         \
+        cudaError_t e_ = (expr);                                                 \
+        if (e_ != cudaSuccess) {                                                 \
+            ::ffcorr::set_error("%s: %s", #expr, cudaGetErrorString(e_));        \
+            return (int)e_;                                                      \
+        }                                                                        \
+    } while (0)
+
+constexpr int kNumSMsB200 = 148;
+
+int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// shared argument validation for the pyramid-shaped entry points (api.cu)
+int check_levels(int num_levels, int h, int w, const char* who);
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace ffcorr

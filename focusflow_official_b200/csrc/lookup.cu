@@ -1,0 +1,319 @@
+// Fused multi-level bilinear window lookup of the correlation pyramid (sm_100a).
+//
+// Replaces, per refinement iteration, the reference's 4x F.grid_sample + ~60 glue
+// kernels (FF_RAFT_Core/corr.py:29-50, utils/utils.py:57-71) with ONE launch.
+//
+// HBM-bound gather: per query and level a (2r+2)^2 window of that query's private
+// [h_i, w_i] correlation map is read once, (2r+1)^2 bilinear samples are written.
+// Algorithmic bytes per query (r = 4, L = 4): 4*100*4 read + 324*4 write + 8 = 2904 B.
+//
+// Work decomposition
+//   unit   = (level, tile of 32 consecutive queries of one batch item), one warp each;
+//   block  = 4 warps = 4 consecutive tiles; blocks are ordered level-major so the
+//            expensive level-0 units are scheduled first and the cheap ones fill the tail.
+//   phase A (lane = query)  : window origin / extent from the first and last tap
+//   phase B (lanes = window): the 32 windows are gathered cooperatively, 32 consecutive
+//            window elements per warp load (3 rows of one private map -> 3-6 sectors),
+//            zero-filled outside the map (grid_sample padding_mode='zeros'), into smem
+//   phase C (lane = query)  : every lane evaluates its own 81 samples from smem and the
+//            warp stores 32 consecutive queries of one output channel = one 128 B line.
+//
+// Numerics: the reference normalises pixel coordinates to [-1, 1] (utils.py:61-62) and
+// ATen un-normalises them again (GridSampler.cuh:26).  That fp32 round trip perturbs
+// every tap differently (up to ~2e-5 px), which is visible at the 1e-5 parity bar, so
+// it is reproduced per tap with explicitly rounded intrinsics (no FMA contraction).
+#include "common.cuh"
+
+namespace ffcorr {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kTile = 32;  // queries per warp
+
+struct LookupParams {
+    const float* lvl[FFCORR_MAX_LEVELS];
+    int lh[FFCORR_MAX_LEVELS];
+    int lw[FFCORR_MAX_LEVELS];
+    const float* coords;  // [B, 2, N]
+    float* out;           // [B, L*K*K, N]
+    int B, N, num_levels;
+    int tiles_per_batch;
+    int blocks_per_batch;
+};
+
+// utils.py:61-62 then GridSampler.cuh:26, every op rounded to fp32 like the reference.
+__device__ __forceinline__ float source_index(float x, float size_m1) {
+    const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, x), size_m1), 1.0f);
+    return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), size_m1);
+}
+
+// |index| beyond this is outside every supported map (h, w <= 16384): all taps are zero.
+constexpr float kWildLimit = 3.0e4f;
+
+template <int R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const LookupParams p) {
+    constexpr int K = 2 * R + 1;
+    constexpr int W2 = K + 2;        // window extent incl. the +-1 floor deviation of the round trip
+    constexpr int WIN = W2 * W2;     // odd -> lane-per-query smem reads are conflict-free
+    constexpr int NLOAD = (WIN + 31) / 32;
+    static_assert(WIN % 2 == 1, "window stride must be odd");
+
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    float* swin = smem + warp * (kTile * WIN);
+
+    // block -> (level, batch, 4 tiles); level-major so level 0 goes first
+    int bid = blockIdx.x;
+    const int per_level = p.B * p.blocks_per_batch;
+    const int level = bid / per_level;
+    bid -= level * per_level;
+    const int b = bid / p.blocks_per_batch;
+    const int tile = (bid - b * p.blocks_per_batch) * kWarpsPerBlock + warp;
+    if (tile >= p.tiles_per_batch) return;  // warp-uniform; no block-level sync below
+
+    const int N = p.N;
+    const int n0 = tile * kTile;
+    const int n = n0 + lane;
+    const bool valid = n < N;
+    const int lh = p.lh[level], lw = p.lw[level];
+    const float* __restrict__ lvl = p.lvl[level];
+    const float inv_scale = __int_as_float((127 - level) << 23);  // 2^-level, exact (corr.py:40)
+
+    // ---------------- phase A: per-query window origin ----------------
+    float cx = 0.f, cy = 0.f;
+    if (valid) {
+        const float* c = p.coords + (size_t)b * 2 * N + n;
+        cx = __ldg(c) * inv_scale;
+        cy = __ldg(c + N) * inv_scale;
+    }
+    const float sx = (float)(lw - 1), sy = (float)(lh - 1);
+    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
+    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
+    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
+    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
+    const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
+                      !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
+    int x_lo = 0, y_lo = 0, ncols = 0, nrows = 0;
+    if (valid && !wild) {
+        x_lo = (int)floorf(ixf);
+        y_lo = (int)floorf(iyf);
+        ncols = min((int)floorf(ixl) + 2 - x_lo, W2);
+        nrows = min((int)floorf(iyl) + 2 - y_lo, W2);
+    }
+    const int pack_xy = (int)(((unsigned)x_lo & 0xFFFFu) | ((unsigned)y_lo << 16));
+    const int pack_rc = nrows | (ncols << 8);
+
+    // ---------------- phase B: cooperative gather into smem ----------------
+    int er[NLOAD], ec[NLOAD];
+#pragma unroll
+    for (int j = 0; j < NLOAD; ++j) {
+        const int e = lane + 32 * j;
+        er[j] = e / W2;
+        ec[j] = e - er[j] * W2;
+    }
+    const int64_t map_elems = (int64_t)lh * lw;
+    const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * map_elems;
+
+    constexpr int QU = 4;  // queries in flight per lane: QU * NLOAD independent loads
+#pragma unroll 1
+    for (int q0 = 0; q0 < kTile; q0 += QU) {
+        float v[QU][NLOAD];
+#pragma unroll
+        for (int u = 0; u < QU; ++u) {
+            const int q = q0 + u;
+            const int xy = __shfl_sync(0xffffffffu, pack_xy, q);
+            const int rc = __shfl_sync(0xffffffffu, pack_rc, q);
+            const int xl = (int)(short)(xy & 0xFFFF);
+            const int yl = xy >> 16;
+            const int nr = rc & 0xFF, nc = rc >> 8;
+            const float* __restrict__ base = tile_base + (int64_t)q * map_elems;
+#pragma unroll
+            for (int j = 0; j < NLOAD; ++j) {
+                const int gy = yl + er[j], gx = xl + ec[j];
+                const bool ok = (er[j] < nr) && (ec[j] < nc) &&
+                                ((unsigned)gy < (unsigned)lh) && ((unsigned)gx < (unsigned)lw);
+                v[u][j] = ok ? __ldg(base + gy * lw + gx) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < QU; ++u) {
+#pragma unroll
+            for (int j = 0; j < NLOAD; ++j) {
+                const int e = lane + 32 * j;
+                if (e < WIN) swin[(q0 + u) * WIN + e] = v[u][j];
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---------------- phase C: lane-per-query evaluation ----------------
+    int rx[K], ry[K];
+    float wx0[K], wx1[K], wy0[K], wy1[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
+        const float fx = floorf(ix);
+        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
+        const float fy = floorf(iy);
+        // corner distances of the ATen CUDA kernel: (ix_se - ix), (ix - ix_nw) with ix_se = ix_nw + 1
+        wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
+        wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+        wy1[a] = wild ? 0.f : __fsub_rn(iy, fy);
+        wy0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+        rx[a] = wild ? 0 : min(max((int)fx - x_lo, 0), W2 - 2);
+        ry[a] = (wild ? 0 : min(max((int)fy - y_lo, 0), W2 - 2)) * W2;
+    }
+
+    const float* sq = swin + lane * WIN;
+    const int CT = p.num_levels * K * K;
+    float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+        for (int bb = 0; bb < K; ++bb) {
+            const float* s = sq + ry[bb] + rx[a];
+            const float v00 = s[0], v01 = s[1], v10 = s[W2], v11 = s[W2 + 1];
+            const float nw = __fmul_rn(wx0[a], wy0[bb]);
+            const float ne = __fmul_rn(wx1[a], wy0[bb]);
+            const float sw = __fmul_rn(wx0[a], wy1[bb]);
+            const float se = __fmul_rn(wx1[a], wy1[bb]);
+            float o = __fmul_rn(v00, nw);
+            o = __fmaf_rn(v01, ne, o);
+            o = __fmaf_rn(v10, sw, o);
+            o = __fmaf_rn(v11, se, o);
+            if (valid) op[(int64_t)(a * K + bb) * N] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// adjoint w.r.t. the pyramid: one thread per output-gradient element, 4 atomics each.
+// ---------------------------------------------------------------------------------
+struct LookupBwdParams {
+    float* glvl[FFCORR_MAX_LEVELS];
+    int lh[FFCORR_MAX_LEVELS];
+    int lw[FFCORR_MAX_LEVELS];
+    const float* coords;
+    const float* gout;
+    int B, N, num_levels, radius;
+};
+
+__global__ void __launch_bounds__(256) lookup_bwd_kernel(const LookupBwdParams p) {
+    const int K = 2 * p.radius + 1;
+    const int KK = K * K;
+    const int CT = p.num_levels * KK;
+    const int64_t total = (int64_t)p.B * CT * p.N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(idx % p.N);
+        const int64_t t = idx / p.N;
+        const int ch = (int)(t % CT);
+        const int b = (int)(t / CT);
+        const int level = ch / KK;
+        const int k = ch - level * KK;
+        const int a = k / K, bb = k - a * K;
+        const float g = __ldg(p.gout + idx);
+        if (g == 0.0f) continue;
+        const int lh = p.lh[level], lw = p.lw[level];
+        const float inv_scale = __int_as_float((127 - level) << 23);
+        const float cx = __ldg(p.coords + (size_t)b * 2 * p.N + n) * inv_scale;
+        const float cy = __ldg(p.coords + (size_t)b * 2 * p.N + p.N + n) * inv_scale;
+        const float ix = source_index(__fadd_rn(cx, (float)(a - p.radius)), (float)(lw - 1));
+        const float iy = source_index(__fadd_rn(cy, (float)(bb - p.radius)), (float)(lh - 1));
+        if (!(fabsf(ix) < kWildLimit) || !(fabsf(iy) < kWildLimit)) continue;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+        const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+        float* m = p.glvl[level] + ((int64_t)b * p.N + n) * ((int64_t)lh * lw);
+        const bool xa = (unsigned)x0 < (unsigned)lw, xb = (unsigned)(x0 + 1) < (unsigned)lw;
+        const bool ya = (unsigned)y0 < (unsigned)lh, yb = (unsigned)(y0 + 1) < (unsigned)lh;
+        if (ya && xa) atomicAdd(m + y0 * lw + x0, g * (wx0 * wy0));
+        if (ya && xb) atomicAdd(m + y0 * lw + x0 + 1, g * (wx1 * wy0));
+        if (yb && xa) atomicAdd(m + (y0 + 1) * lw + x0, g * (wx0 * wy1));
+        if (yb && xb) atomicAdd(m + (y0 + 1) * lw + x0 + 1, g * (wx1 * wy1));
+    }
+}
+
+template <int R>
+int launch_lookup(const LookupParams& p, cudaStream_t stream) {
+    constexpr int K = 2 * R + 1;
+    constexpr int WIN = (K + 2) * (K + 2);
+    const size_t smem = (size_t)kWarpsPerBlock * kTile * WIN * sizeof(float);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    FFCORR_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_dev = dev;
+    }
+    const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
+    FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup: grid too large (%lld blocks)", (long long)blocks);
+    lookup_kernel<R><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    return check_launch("lookup_kernel");
+}
+
+}  // namespace
+}  // namespace ffcorr
+
+using namespace ffcorr;
+
+extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                                 int B, int h, int w, int radius, void* stream) {
+    FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "lookup: null pointer");
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup: B=%d", B);
+    FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup: radius=%d outside [1,4]", radius);
+    if (int rc = check_levels(num_levels, h, w, "lookup")) return rc;
+    if (B == 0) return FFCORR_OK;
+    LookupParams p{};
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "lookup: lvl[%d] is null", i);
+        p.lvl[i] = lvl[i];
+        p.lh[i] = h >> i;
+        p.lw[i] = w >> i;
+    }
+    p.coords = coords;
+    p.out = out;
+    p.B = B;
+    p.N = h * w;
+    p.num_levels = num_levels;
+    p.tiles_per_batch = ceil_div(p.N, kTile);
+    p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (radius) {
+        case 1: return launch_lookup<1>(p, s);
+        case 2: return launch_lookup<2>(p, s);
+        case 3: return launch_lookup<3>(p, s);
+        default: return launch_lookup<4>(p, s);
+    }
+}
+
+extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, const float* coords,
+                                     const float* grad_out, int B, int h, int w, int radius, void* stream) {
+    FFCORR_REQUIRE(grad_lvl && coords && grad_out, FFCORR_EINVAL, "lookup_bwd: null pointer");
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup_bwd: B=%d", B);
+    FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup_bwd: radius=%d outside [1,4]", radius);
+    if (int rc = check_levels(num_levels, h, w, "lookup_bwd")) return rc;
+    if (B == 0) return FFCORR_OK;
+    LookupBwdParams p{};
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(grad_lvl[i] != nullptr, FFCORR_EINVAL, "lookup_bwd: grad_lvl[%d] is null", i);
+        p.glvl[i] = grad_lvl[i];
+        p.lh[i] = h >> i;
+        p.lw[i] = w >> i;
+    }
+    p.coords = coords;
+    p.gout = grad_out;
+    p.B = B;
+    p.N = h * w;
+    p.num_levels = num_levels;
+    p.radius = radius;
+    const int K = 2 * radius + 1;
+    const int64_t total = (int64_t)B * num_levels * K * K * p.N;
+    const int64_t want = ceil_div64(total, 256);
+    const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
+    lookup_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("lookup_bwd_kernel");
+}

@@ -1,0 +1,643 @@
+// All-pairs correlation volume (level 0 of the pyramid) for sm_100a.
+//
+// Replaces torch.matmul(fmap1^T, fmap2) followed by a separate "/ sqrt(D)" pass
+// (FF_RAFT_Core/corr.py:52-60).  C[b,i,j] = sum_d f1[b,d,i] f2[b,d,j] / sqrt(D).
+//
+// Tensor-core path (default):
+//   1. operand pre-pass: [B, D, N] fp32 (MN-major, as the encoder hands it over) ->
+//      [B, N, Dp] K-major fp16 / bf16-split / fp32(tf32), zero padded along K.
+//      Traffic: 2*B*N*D*(4 + e) bytes, ~2% of the volume write.
+//   2. persistent warp-specialised GEMM, one CTA per SM, tile 128 x 256:
+//        warp 0    TMA producer   (cp.async.bulk.tensor, 128B swizzle, 3-stage mbarrier ring)
+//        warp 1    MMA issuer     (tcgen05.mma cta_group::1, M=128 N=256, fp32 accumulators in
+//                                  TMEM, 2 x 256 columns so tile t+1 overlaps the epilogue of t)
+//        warps 2-5 epilogue       (tcgen05.ld -> scale by 1/sqrt(D) -> swizzled smem -> TMA store,
+//                                  each warp owns its 32 TMEM lanes and its own 4-deep store ring)
+//   The kernel is HBM-WRITE bound, not tensor bound: per tile 128 KB of fp32 leave the SM for
+//   2*128*256*D flop (AI ~ 120 flop/B at D=256 < B200 ridge ~215), so the design spends shared
+//   memory on store buffering rather than on a deep operand pipeline.
+// Exact path: FFCORR_PREC_FP32, a CUDA-core SGEMM (also serves the two backward GEMMs).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace ffcorr {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i gets row (lane base + i), columns c .. c+31
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// GEMM configuration
+// ------------------------------------------------------------------------------------------
+constexpr int BM = 128;              // tile rows (queries i)     == UMMA M == TMEM lanes
+constexpr int BN = 256;              // tile cols (targets j)     == UMMA N == TMEM columns per accumulator
+constexpr int BK_BYTES = 128;        // one 128B swizzle atom along K per stage
+constexpr int UMMA_K_BYTES = 32;     // K extent of one tcgen05.mma: 16 x 16-bit or 8 x tf32
+constexpr int STAGES = 3;
+constexpr int ACC_STAGES = 2;
+constexpr int STORE_COLS = 32;       // fp32 columns per store box (128 B rows)
+constexpr int STORE_BUFS = 4;        // per epilogue warp
+constexpr int EPI_WARPS = 4;
+constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
+
+constexpr int SMEM_A_STAGE = BM * BK_BYTES;   // 16 KB
+constexpr int SMEM_B_STAGE = BN * BK_BYTES;   // 32 KB
+constexpr int SMEM_STORE_BUF = 32 * STORE_COLS * 4;  // 4 KB: 32 rows x 128 B
+constexpr int SMEM_STORE = EPI_WARPS * STORE_BUFS * SMEM_STORE_BUF;  // 64 KB
+constexpr int SMEM_OFF_A = SMEM_STORE;
+constexpr int SMEM_OFF_B = SMEM_OFF_A + STAGES * SMEM_A_STAGE;
+constexpr int SMEM_OFF_BAR = SMEM_OFF_B + STAGES * SMEM_B_STAGE;
+constexpr int SMEM_GEMM_TOTAL = SMEM_OFF_BAR + 128 + 1024;  // + barriers + alignment slack
+static_assert(SMEM_GEMM_TOTAL <= 227 * 1024, "shared memory budget");
+
+// K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;         // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                               // layout: SWIZZLE_128B
+    return d;
+}
+
+struct GemmParams {
+    int N;          // rows == cols of the volume per batch item
+    int B;
+    int num_kb;     // K blocks of 128 bytes
+    int tiles_m, tiles_n;
+    float scale;    // 1/sqrt(D) (exact when D is a power of 4) or 1 when divide != 0
+    float divisor;  // sqrt(D)
+    int use_div;    // 1: fp32 divide like the reference; 0: multiply by the exact reciprocal
+    float* out;     // only used by the non-TMA epilogue (N % 4 != 0)
+};
+
+template <bool TF32, bool TMA_STORE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_c, const GemmParams p, const uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + SMEM_OFF_BAR;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_OFF_BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        if (TMA_STORE) tma_prefetch_desc(&tmap_c);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < ACC_STAGES; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), EPI_WARPS);
+        }
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), ACC_STAGES * BN);  // 512 columns
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_batch = p.tiles_m * p.tiles_n;
+    const int num_tiles = tiles_per_batch * p.B;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int b = t / tiles_per_batch;
+                const int r = t - b * tiles_per_batch;
+                const int m0 = (r / p.tiles_n) * BM;
+                const int n0 = (r % p.tiles_n) * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar(stage), SMEM_A_STAGE + SMEM_B_STAGE);
+                    const int k0 = kb * (TF32 ? BK_BYTES / 4 : BK_BYTES / 2);
+                    tma_load_3d(smem_base + SMEM_OFF_A + stage * SMEM_A_STAGE, &tmap_a, full_bar(stage), k0, m0, b);
+                    tma_load_3d(smem_base + SMEM_OFF_B + stage * SMEM_B_STAGE, &tmap_b, full_bar(stage), k0, n0, b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_base + SMEM_OFF_A + stage * SMEM_A_STAGE);
+                    const uint64_t bdesc = make_smem_desc(smem_base + SMEM_OFF_B + stage * SMEM_B_STAGE);
+#pragma unroll
+                    for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
+                        // advance K inside the swizzle atom: +32 B == +2 in the (addr >> 4) field
+                        umma<TF32>(d_tmem, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                   bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(empty_bar(stage));               // frees the smem stage when the MMAs retire
+                    if (kb == p.num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator ready
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int ew = warp - 2;                      // private store ring
+        uint8_t* my_bufs = smem + (size_t)ew * STORE_BUFS * SMEM_STORE_BUF;
+        const uint32_t my_bufs_u32 = smem_base + (uint32_t)(ew * STORE_BUFS * SMEM_STORE_BUF);
+        int buf = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int b = t / tiles_per_batch;
+            const int r = t - b * tiles_per_batch;
+            const int m0 = (r / p.tiles_n) * BM;
+            const int n0 = (r % p.tiles_n) * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const int row0 = m0 + quarter * 32;
+#pragma unroll 1
+            for (int c = 0; c < BN / STORE_COLS; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + (uint32_t)(c * STORE_COLS), v);
+                tmem_ld_wait();
+                if (c == BN / STORE_COLS - 1) {
+                    // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a = __uint_as_float(v[i]);
+                    f[i] = p.use_div ? __fdiv_rn(a, p.divisor) : a * p.scale;
+                }
+                const int col0 = n0 + c * STORE_COLS;
+                if (TMA_STORE) {
+                    if (row0 < p.N && col0 < p.N) {  // warp-uniform: box entirely outside -> skip
+                        if (lane == 0) tma_store_wait_read<STORE_BUFS - 1>();
+                        __syncwarp();
+                        uint8_t* dst = my_bufs + (size_t)buf * SMEM_STORE_BUF + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 q = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = q;  // 128B swizzle
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&tmap_c, my_bufs_u32 + (uint32_t)(buf * SMEM_STORE_BUF), col0, row0, b);
+                            tma_store_commit();
+                        }
+                        buf = (buf + 1) % STORE_BUFS;
+                    }
+                } else {
+                    const int row = row0 + lane;
+                    if (row < p.N) {
+                        float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.N + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.N) o[i] = f[i];
+                    }
+                }
+            }
+        }
+        if (TMA_STORE && lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ACC_STAGES * BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// operand pre-pass: [B, D, N] fp32 -> [B, N, Dp] K-major in the MMA operand type
+// ------------------------------------------------------------------------------------------
+enum : int { CVT_F16 = 0, CVT_BF16X3_A = 1, CVT_BF16X3_B = 2, CVT_F32 = 3 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256) operand_prepass_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                              void* __restrict__ o1, void* __restrict__ o2,
+                                                              int B, int D, int N, int Dp /* padded K per segment */) {
+    __shared__ float tile[32][33];
+    const int which = blockIdx.z / B;          // 0: fmap1 (A operand), 1: fmap2 (B operand)
+    const int b = blockIdx.z - which * B;
+    const float* __restrict__ in = (which == 0 ? f1 : f2) + (size_t)b * D * N;
+    const int n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d = d0 + ty + 8 * i, n = n0 + tx;
+        tile[ty + 8 * i][tx] = (d < D && n < N) ? __ldg(in + (size_t)d * N + n) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty + 8 * i, d = d0 + tx;
+        if (n >= N) continue;
+        const float x = tile[tx][ty + 8 * i];
+        if (MODE == CVT_F16) {
+            __half* o = reinterpret_cast<__half*>(which == 0 ? o1 : o2) + ((size_t)b * N + n) * Dp;
+            o[d] = __float2half_rn(x);
+        } else if (MODE == CVT_F32) {
+            float* o = reinterpret_cast<float*>(which == 0 ? o1 : o2) + ((size_t)b * N + n) * Dp;
+            o[d] = x;
+        } else {
+            // bf16 hi/lo split; A rows hold [hi | hi | lo], B rows [hi | lo | hi] so that one
+            // K = 3*Dp GEMM computes hi*hi + hi*lo + lo*hi with fp32 accumulation.
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(which == 0 ? o1 : o2) + ((size_t)b * N + n) * (3 * (size_t)Dp);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+            o[d] = hi;
+            o[Dp + d] = (which == 0) ? hi : lo;
+            o[2 * Dp + d] = (which == 0) ? lo : hi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA-core SGEMM with arbitrary operand strides (exact fp32 path + backward GEMMs)
+//   C[m, n] = (sum_k A[m,k] * B[k,n]) / divisor,   batched over blockIdx.z
+// ------------------------------------------------------------------------------------------
+constexpr int SG_T = 64, SG_K = 16;
+
+template <bool A_MCONTIG, bool B_NCONTIG>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C,
+                                                    int M, int Nn, int K, int64_t a_sm, int64_t a_sk, int64_t b_sk, int64_t b_sn,
+                                                    int64_t c_ld, int64_t a_batch, int64_t b_batch, int64_t c_batch, float divisor) {
+    __shared__ float As[SG_K][SG_T + 4];
+    __shared__ float Bs[SG_K][SG_T + 4];
+    A += (int64_t)blockIdx.z * a_batch;
+    Bm += (int64_t)blockIdx.z * b_batch;
+    C += (int64_t)blockIdx.z * c_batch;
+    const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+    const int t = threadIdx.x;
+    const int tx = t & 15, ty = t >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += SG_K) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int m, k;
+            if (A_MCONTIG) { m = t & 63; k = (t >> 6) + 4 * i; } else { k = t & 15; m = (t >> 4) + 16 * i; }
+            const int gm = m0 + m, gk = k0 + k;
+            As[k][m] = (gm < M && gk < K) ? __ldg(A + gm * a_sm + gk * a_sk) : 0.0f;
+            int n, kk;
+            if (B_NCONTIG) { n = t & 63; kk = (t >> 6) + 4 * i; } else { kk = t & 15; n = (t >> 4) + 16 * i; }
+            const int gn = n0 + n, gkb = k0 + kk;
+            Bs[kk][n] = (gn < Nn && gkb < K) ? __ldg(Bm + gkb * b_sk + gn * b_sn) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SG_K; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn < Nn) C[gm * c_ld + gn] = __fdiv_rn(acc[i][j], divisor);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+int encode_3d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+              uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, const char* what) {
+    PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
+    FFCORR_REQUIRE(fn != nullptr, FFCORR_EDEVICE, "cuTensorMapEncodeTiled is not available from the driver");
+    (void)elem_bytes;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FFCORR_REQUIRE(r == CUDA_SUCCESS, FFCORR_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return FFCORR_OK;
+}
+
+struct PrecInfo {
+    int elem_bytes;   // operand element size
+    int k_mult;       // K multiplier (3 for the bf16 split)
+    int k_align;      // per-segment K padding in elements (one 128 B swizzle atom)
+};
+
+bool prec_info(int precision, PrecInfo* pi) {
+    switch (precision) {
+        case FFCORR_PREC_FP16:   *pi = {2, 1, 64}; return true;
+        case FFCORR_PREC_BF16X3: *pi = {2, 3, 64}; return true;
+        case FFCORR_PREC_TF32:   *pi = {4, 1, 32}; return true;
+        default: return false;
+    }
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+    FFCORR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return FFCORR_OK;
+}
+
+int launch_sgemm(bool a_mcontig, bool b_ncontig, const float* A, const float* Bm, float* C, int M, int Nn, int K,
+                 int64_t a_sm, int64_t a_sk, int64_t b_sk, int64_t b_sn, int64_t c_ld, int64_t a_batch, int64_t b_batch,
+                 int64_t c_batch, int batches, float divisor, cudaStream_t s) {
+    dim3 grid(ceil_div(Nn, SG_T), ceil_div(M, SG_T), batches);
+    FFCORR_REQUIRE(grid.y < 65536 && grid.z < 65536, FFCORR_EINVAL, "sgemm: grid too large");
+#define FF_SGEMM(AM, BN_)                                                                                           \
+    sgemm_kernel<AM, BN_><<<grid, 256, 0, s>>>(A, Bm, C, M, Nn, K, a_sm, a_sk, b_sk, b_sn, c_ld, a_batch, b_batch, \
+                                               c_batch, divisor)
+    if (a_mcontig && b_ncontig) FF_SGEMM(true, true);
+    else if (a_mcontig) FF_SGEMM(true, false);
+    else if (b_ncontig) FF_SGEMM(false, true);
+    else FF_SGEMM(false, false);
+#undef FF_SGEMM
+    return check_launch("sgemm_kernel");
+}
+
+}  // namespace
+}  // namespace ffcorr
+
+using namespace ffcorr;
+
+extern "C" size_t ffcorr_volume_workspace_bytes(int B, int D, int h, int w, int precision) {
+    PrecInfo pi;
+    if (!prec_info(precision, &pi) || B <= 0 || D <= 0 || h <= 0 || w <= 0) return 0;
+    const size_t N = (size_t)h * w;
+    const size_t Dp = align_up((size_t)D, pi.k_align);
+    const size_t one = align_up((size_t)B * N * Dp * pi.k_mult * pi.elem_bytes, 256);
+    return 2 * one;
+}
+
+extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
+                                 int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    FFCORR_REQUIRE(fmap1 && fmap2 && lvl0, FFCORR_EINVAL, "volume: null pointer");
+    FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume: bad shape B=%d D=%d h=%d w=%d", B, D, h, w);
+    FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "volume: h*w=%lld too large", (long long)h * w);
+    if (B == 0) return FFCORR_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = h * w;
+    const float sqrt_d = sqrtf((float)D);
+
+    if (precision == FFCORR_PREC_FP32) {
+        // C[i,j] = sum_d f1[d,i] f2[d,j]: A[m=i,k=d] (m contiguous), B[k=d,n=j] (n contiguous)
+        return launch_sgemm(true, true, fmap1, fmap2, lvl0, N, N, D, 1, N, N, 1, N, (int64_t)D * N, (int64_t)D * N,
+                            (int64_t)N * N, B, sqrt_d, s);
+    }
+
+    PrecInfo pi;
+    FFCORR_REQUIRE(prec_info(precision, &pi), FFCORR_EINVAL, "volume: unknown precision %d", precision);
+    const size_t need = ffcorr_volume_workspace_bytes(B, D, h, w, precision);
+    FFCORR_REQUIRE(workspace != nullptr && workspace_bytes >= need, FFCORR_EWORKSPACE,
+                   "volume: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    FFCORR_REQUIRE((uintptr_t)workspace % 256 == 0, FFCORR_EALIGN, "volume: workspace must be 256-byte aligned");
+    FFCORR_REQUIRE((uintptr_t)lvl0 % 16 == 0, FFCORR_EALIGN, "volume: lvl0 must be 16-byte aligned");
+
+    const int Dp = (int)align_up((size_t)D, pi.k_align);
+    const int Kt = Dp * pi.k_mult;  // total K in elements
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    void* opA = ws;
+    void* opB = ws + need / 2;
+
+    // ---- 1. operand pre-pass ----
+    {
+        dim3 grid(ceil_div(N, 32), Dp / 32, 2 * B);
+        FFCORR_REQUIRE(grid.y < 65536 && grid.z < 65536, FFCORR_EINVAL, "volume: pre-pass grid too large");
+        if (precision == FFCORR_PREC_FP16)
+            operand_prepass_kernel<CVT_F16><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp);
+        else if (precision == FFCORR_PREC_TF32)
+            operand_prepass_kernel<CVT_F32><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp);
+        else
+            operand_prepass_kernel<CVT_BF16X3_A><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp);
+        if (int rc = check_launch("operand_prepass_kernel")) return rc;
+    }
+
+    // ---- 2. tensor maps ----
+    CUtensorMap ta, tb, tc;
+    const bool tf32 = precision == FFCORR_PREC_TF32;
+    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                        : (precision == FFCORR_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                         : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    const uint32_t box_k = (uint32_t)(BK_BYTES / pi.elem_bytes);
+    const uint64_t row_bytes = (uint64_t)Kt * pi.elem_bytes;
+    if (int rc = encode_3d(&ta, dt, pi.elem_bytes, opA, Kt, N, B, row_bytes, row_bytes * N, box_k, BM, "A")) return rc;
+    if (int rc = encode_3d(&tb, dt, pi.elem_bytes, opB, Kt, N, B, row_bytes, row_bytes * N, box_k, BN, "B")) return rc;
+    const bool tma_store = (N % 4 == 0);
+    if (tma_store) {
+        if (int rc = encode_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, N, N, B, (uint64_t)N * 4, (uint64_t)N * N * 4,
+                               STORE_COLS, 32, "C"))
+            return rc;
+    } else {
+        tc = ta;  // unused by the kernel
+    }
+
+    // ---- 3. GEMM ----
+    GemmParams p{};
+    p.N = N;
+    p.B = B;
+    p.num_kb = Kt * pi.elem_bytes / BK_BYTES;
+    p.tiles_m = ceil_div(N, BM);
+    p.tiles_n = ceil_div(N, BN);
+    p.divisor = sqrt_d;
+    int e = 0;
+    const float mant = frexpf(sqrt_d, &e);
+    p.use_div = (mant == 0.5f) ? 0 : 1;  // sqrt(D) a power of two -> exact reciprocal multiply
+    p.scale = 1.0f / sqrt_d;
+    p.out = lvl0;
+    // instruction descriptor: D=f32, A/B format, K-major both, N>>3, M>>4
+    const uint32_t fmt = tf32 ? 2u : (precision == FFCORR_PREC_FP16 ? 0u : 1u);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const int64_t num_tiles = (int64_t)p.tiles_m * p.tiles_n * B;
+    FFCORR_REQUIRE(num_tiles < (1ll << 31), FFCORR_EINVAL, "volume: too many tiles");
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+#define FF_GEMM(TF, TS)                                                                                  \
+    do {                                                                                                 \
+        if (int rc = set_smem(volume_gemm_kernel<TF, TS>, SMEM_GEMM_TOTAL)) return rc;                   \
+        volume_gemm_kernel<TF, TS><<<grid, GEMM_THREADS, SMEM_GEMM_TOTAL, s>>>(ta, tb, tc, p, idesc);    \
+    } while (0)
+    if (tf32 && tma_store) FF_GEMM(true, true);
+    else if (tf32) FF_GEMM(true, false);
+    else if (tma_store) FF_GEMM(false, true);
+    else FF_GEMM(false, false);
+#undef FF_GEMM
+    return check_launch("volume_gemm_kernel");
+}
+
+extern "C" int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1, const float* fmap2, float* gfmap1,
+                                     float* gfmap2, int B, int D, int h, int w, void* stream) {
+    FFCORR_REQUIRE(grad_lvl0 && fmap1 && fmap2, FFCORR_EINVAL, "volume_bwd: null pointer");
+    FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume_bwd: bad shape");
+    if (B == 0) return FFCORR_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = h * w;
+    const float sqrt_d = sqrtf((float)D);
+    const int64_t fb = (int64_t)D * N, gb = (int64_t)N * N;
+    if (gfmap1) {
+        // gf1[d,i] = sum_j f2[d,j] g[i,j]: A[m=d,k=j] = f2 (k contiguous), B[k=j,n=i] = g[i*N+j] (k contiguous)
+        if (int rc = launch_sgemm(false, false, fmap2, grad_lvl0, gfmap1, D, N, N, N, 1, 1, N, N, fb, gb, fb, B, sqrt_d, s))
+            return rc;
+    }
+    if (gfmap2) {
+        // gf2[d,j] = sum_i f1[d,i] g[i,j]: A[m=d,k=i] = f1 (k contiguous), B[k=i,n=j] = g (n contiguous)
+        if (int rc = launch_sgemm(false, true, fmap1, grad_lvl0, gfmap2, D, N, N, N, 1, N, 1, N, fb, gb, fb, B, sqrt_d, s))
+            return rc;
+    }
+    return FFCORR_OK;
+}

@@ -1,0 +1,136 @@
+/*
+ * ffcorr.h -- C ABI of libffcorr.so: the B200 (sm_100a) correlation hot path of
+ * FocusFlow (FocusRAFT CorrBlock + FF-PWC 9x9 local cost volume).
+ *
+ * Drop-in boundary.  The reference has no FFI layer: its hot path is two Python
+ * call surfaces over torch / CuPy.  Each entry point below replaces the device
+ * work behind one of them (paths relative to the reference root):
+ *
+ *   ffcorr_volume_f32      core/models/ff-raft/FF_RAFT_Core/corr.py:52-60   CorrBlock.corr
+ *                          (torch.matmul + separate "/ sqrt(D)" kernel)
+ *   ffcorr_pyramid_f32     corr.py:24-27   3x F.avg_pool2d(corr, 2, stride=2)
+ *   ffcorr_lookup_f32      corr.py:29-50   CorrBlock.__call__  +  utils/utils.py:57-71
+ *                          bilinear_sampler (4x F.grid_sample + ~60 glue kernels)
+ *   ffcorr_lookup_bwd_f32  autograd of the above w.r.t. the pyramid (coords are detached
+ *                          by the caller, raft.py:216-217)
+ *   ffcorr_pyramid_bwd_f32 autograd of corr.py:24-27
+ *   ffcorr_volume_bwd_f32  autograd of corr.py:52-60
+ *   ffcorr_pwc81_f32       core/models/ff-pwcnet/PWCNet_Core/correlation.py:278-328
+ *                          _FunctionCorrelation.forward (rearrange x2 + updateOutput)
+ *   ffcorr_pwc81_bwd_f32   correlation.py:331-380 _FunctionCorrelation.backward
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching
+ *     allocator in the shipped host code); the library allocates no device memory;
+ *   - all tensors are dense, contiguous, fp32, in the reference's layouts;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises the host;
+ *   - return value: 0 on success, a negative FFCORR_E* code for argument errors,
+ *     a positive cudaError_t when the CUDA runtime reports one.  Nothing throws.
+ *     ffcorr_last_error() returns a thread-local message for the last failure.
+ *   - re-entrant: no global mutable state besides cached function attributes.
+ */
+#ifndef FFCORR_H_
+#define FFCORR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFCORR_VERSION 100
+
+#define FFCORR_OK            0
+#define FFCORR_EINVAL      (-1)   /* bad shape / null pointer / unsupported argument   */
+#define FFCORR_EWORKSPACE  (-2)   /* workspace missing or too small                     */
+#define FFCORR_EDEVICE     (-3)   /* not an sm_100 device / driver entry point missing  */
+#define FFCORR_EALIGN      (-4)   /* pointer alignment the kernel needs is not met      */
+
+#define FFCORR_MAX_LEVELS    8
+
+/* operand precision of the all-pairs contraction (accumulation is always fp32) */
+#define FFCORR_PREC_FP16     0    /* tcgen05 kind::f16, operands rounded to fp16 (RN): default          */
+#define FFCORR_PREC_FP32     1    /* CUDA-core fp32 FMA: exact path for training / debugging            */
+#define FFCORR_PREC_BF16X3   2    /* tcgen05, bf16 hi/lo split, 3 MMAs per k-step: ~fp32 accuracy       */
+#define FFCORR_PREC_TF32     3    /* tcgen05 kind::tf32 on fp32 operands                                */
+
+int         ffcorr_version(void);
+const char* ffcorr_last_error(void);
+
+/* number of SMs / compute capability of the current device (for tests and the bench) */
+int ffcorr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * All-pairs correlation volume, level 0 of the pyramid.
+ *   fmap1, fmap2 : [B, D, h, w]          (raft.py:191-193 hands them over as fp32 NCHW)
+ *   lvl0         : [B*h*w, h, w]         == reference [B*N, 1, h, w], N = h*w
+ *   lvl0[b*N + i, j] = sum_d fmap1[b,d,i] * fmap2[b,d,j] / sqrt(D)
+ * workspace: ffcorr_volume_workspace_bytes() bytes, 256-byte aligned (operand staging
+ * for the tensor-core paths; may be NULL/0 for FFCORR_PREC_FP32).
+ */
+size_t ffcorr_volume_workspace_bytes(int B, int D, int h, int w, int precision);
+int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0,
+                      int B, int D, int h, int w, int precision,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Average-pool pyramid.  lvl[0] is the input [Q, h, w]; lvl[i] (i >= 1) is written,
+ * [Q, h>>i, w>>i] with floor semantics and the ((a+b)+c+d)/4 summation order of
+ * ATen avg_pool2d, so the result is bit-identical to the reference given the same lvl[0].
+ * `lvl` is a HOST array of num_levels device pointers.
+ */
+int ffcorr_pyramid_f32(float* const* lvl, int num_levels, int64_t Q, int h, int w, void* stream);
+
+/*
+ * Fused multi-level bilinear window lookup (one launch per refinement iteration).
+ *   lvl     : HOST array of num_levels device pointers, lvl[i] = [B*h*w, h>>i, w>>i]
+ *   coords  : [B, 2, h, w]  channel 0 = x, channel 1 = y   (utils.py:74-77)
+ *   out     : [B, num_levels*(2r+1)^2, h, w]; channel = lvl*(2r+1)^2 + a*(2r+1) + b samples
+ *             (x/2^lvl + a - r, y/2^lvl + b - r)            (corr.py:37-43)
+ * Zero padding, align_corners=True and the normalise/un-normalise fp32 round trip of
+ * bilinear_sampler + grid_sample are reproduced tap by tap.  radius in [1, 4].
+ */
+int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                      int B, int h, int w, int radius, void* stream);
+
+/*
+ * Adjoint of the lookup w.r.t. the pyramid.  grad_lvl[i] must be ZEROED by the caller;
+ * contributions are accumulated with atomics (red.global.add.f32).
+ */
+int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, const float* coords,
+                          const float* grad_out, int B, int h, int w, int radius, void* stream);
+
+/*
+ * Adjoint of the pyramid: grad_lvl[i-1] += upsample(grad_lvl[i]) / 4 for i = L-1 .. 1
+ * (in place, so after the call grad_lvl[0] holds d loss / d lvl0).
+ */
+int ffcorr_pyramid_bwd_f32(float* const* grad_lvl, int num_levels, int64_t Q, int h, int w, void* stream);
+
+/*
+ * Adjoint of the volume: gfmap1[b,d,i] = sum_j g[b,i,j] fmap2[b,d,j] / sqrt(D),
+ *                         gfmap2[b,d,j] = sum_i g[b,i,j] fmap1[b,d,i] / sqrt(D).
+ * fp32 CUDA-core path.  Either gradient pointer may be NULL.
+ */
+int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1, const float* fmap2,
+                          float* gfmap1, float* gfmap2, int B, int D, int h, int w, void* stream);
+
+/*
+ * PWC local cost volume, max displacement 4 (81 channels).
+ *   one, two : [B, C, H, W];  out : [B, 81, H, W]
+ *   out[b, (dy+4)*9 + (dx+4), y, x] = (1/C) sum_c one[b,c,y,x] * two[b,c,y+dy,x+dx]   (0 outside)
+ * leaky_slope < 0 writes the raw volume (reference semantics); 0 <= leaky_slope < 1 fuses
+ * the leaky_relu the reference applies right after the call (ff_pwcnet.py:317,325).
+ */
+int ffcorr_pwc81_f32(const float* one, const float* two, float* out,
+                     int B, int C, int H, int W, float leaky_slope, void* stream);
+
+/* gradients of the raw cost volume; either output may be NULL. */
+int ffcorr_pwc81_bwd_f32(const float* one, const float* two, const float* grad_out,
+                         float* grad_one, float* grad_two, int B, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFCORR_H_ */

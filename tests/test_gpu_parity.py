@@ -1,0 +1,376 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).
+
+Every test drives the CUDA kernels through the package's public surface, i.e. through the
+C ABI of libffcorr.so, and compares with the CPU oracle (``oracle/``) or with the golden
+vectors the unmodified reference produced (``tests/golden``).  Tolerances are the ones
+BASELINE.json states: volume <= 1e-3 relative, lookups <= 1e-5 (relative to max |ref|),
+pyramid bit-exact given the same level 0.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import corr_oracle as co
+from oracle import pwc_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "corr_*.npz")))
+DEV = "cuda:0"
+
+
+def ff():
+    import focusflow_official_b200 as m
+
+    return m
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def max_rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ---------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_golden_pyramid_bit_exact(path):
+    g = np.load(path)
+    from focusflow_official_b200 import _lib
+
+    lv = [t(g["level0"][:, None])] + [torch.empty((g[f"level{i}"].shape[0], 1) + g[f"level{i}"].shape[1:], device=DEV)
+                                       for i in range(1, 4)]
+    q, _, h, w = lv[0].shape
+    _lib.check(_lib.lib().ffcorr_pyramid_f32(_lib.ptr_array(lv), 4, q, h, w, _lib.current_stream()), "pyramid")
+    for i in range(1, 4):
+        assert np.array_equal(lv[i][:, 0].cpu().numpy(), g[f"level{i}"]), f"level {i}"
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_golden_lookup(path):
+    g = np.load(path)
+    levels = [t(g[f"level{i}"][:, None]) for i in range(4)]
+    for k in [k[len("coords_"):] for k in g.files if k.startswith("coords_")]:
+        out = ff().lookup(levels, t(g[f"coords_{k}"]), 4).cpu().numpy()
+        ref = g[f"lookup_{k}"]
+        assert out.shape == ref.shape
+        assert max_rel(out, ref) <= 1e-5, (k, max_rel(out, ref))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-6), ("bf16x3", 3e-5), ("fp16", 1e-3), ("tf32", 1e-3)])
+def test_golden_volume(path, prec, tol):
+    g = np.load(path)
+    blk = ff().CorrBlock(t(g["fmap1"]), t(g["fmap2"]), num_levels=4, radius=4, precision=prec)
+    for i in range(4):
+        got = blk.corr_pyramid[i][:, 0].cpu().numpy()
+        assert rel_fro(got, g[f"level{i}"]) <= tol, (prec, i, rel_fro(got, g[f"level{i}"]))
+    assert blk.corr_pyramid[0].shape == (g["level0"].shape[0], 1) + g["level0"].shape[1:]
+
+
+# ---------------------------------------------------------------- volume vs oracle
+@pytest.mark.parametrize("shape", [(1, 256, 46, 62), (2, 256, 17, 21), (1, 64, 16, 130), (3, 40, 9, 13), (1, 256, 24, 32)])
+@pytest.mark.parametrize("prec,tol", [("fp16", 1e-3), ("tf32", 1e-3), ("bf16x3", 3e-5), ("fp32", 2e-6)])
+def test_volume_vs_oracle(shape, prec, tol):
+    b, d, h, w = shape
+    rng = np.random.default_rng(1234)
+    f1 = (rng.standard_normal(shape) * 4.4).astype(np.float32)
+    f2 = (rng.standard_normal(shape) * 4.4).astype(np.float32)
+    ref = co.volume_f64(f1, f2)
+    got = ff().correlation_volume(t(f1), t(f2), precision=prec).cpu().numpy().reshape(ref.shape)
+    err = rel_fro(got, ref)
+    assert err <= tol, (shape, prec, err)
+    # no element may be wildly off (catches tile / swizzle / tail mistakes that a norm hides)
+    assert np.abs(got - ref).max() <= 50 * tol * np.abs(ref).max()
+
+
+def test_volume_is_reference_layout():
+    """corr.py:59: [B, h, w, 1, h, w]; entry [b,y1,x1,0,y2,x2] pairs fmap1(y1,x1) with fmap2(y2,x2)."""
+    b, d, h, w = 2, 32, 8, 12
+    f1 = torch.zeros(b, d, h, w, device=DEV)
+    f2 = torch.zeros(b, d, h, w, device=DEV)
+    f1[1, :, 3, 5] = 1.0
+    f2[1, :, 6, 2] = 2.0
+    v = ff().CorrBlock.corr(f1, f2, precision="fp16")
+    assert v.shape == (b, h, w, 1, h, w)
+    assert abs(float(v[1, 3, 5, 0, 6, 2]) - 2.0 * d / np.sqrt(d)) < 1e-4
+    assert int((v != 0).sum()) == 1
+
+
+# ---------------------------------------------------------------- pyramid
+@pytest.mark.parametrize("shape", [(300, 46, 62), (64, 47, 156), (33, 17, 21), (10, 8, 8), (5, 55, 128), (3, 150, 200)])
+def test_pyramid_bit_exact_vs_oracle(shape):
+    from focusflow_official_b200 import _lib
+
+    q, h, w = shape
+    rng = np.random.default_rng(7)
+    l0 = (rng.standard_normal(shape) * 19).astype(np.float32)
+    nl = 4
+    lv = [t(l0[:, None])] + [torch.empty((q, 1, h >> i, w >> i), device=DEV) for i in range(1, nl)]
+    _lib.check(_lib.lib().ffcorr_pyramid_f32(_lib.ptr_array(lv), nl, q, h, w, _lib.current_stream()), "pyramid")
+    ref = co.pyramid(l0, nl)
+    for i in range(1, nl):
+        assert np.array_equal(lv[i][:, 0].cpu().numpy(), ref[i]), (shape, i)
+
+
+def test_pyramid_unaligned_base_and_many_levels():
+    from focusflow_official_b200 import _lib
+
+    q, h, w = 37, 33, 35
+    rng = np.random.default_rng(8)
+    l0 = rng.standard_normal((q, h, w)).astype(np.float32)
+    buf = torch.empty(q * h * w + 1, device=DEV)
+    buf[1:] = t(l0).flatten()  # 4-byte aligned only -> scalar path
+    nl = 6
+    lv = [buf[1:].view(q, 1, h, w)] + [torch.empty((q, 1, h >> i, w >> i), device=DEV) for i in range(1, nl)]
+    _lib.check(_lib.lib().ffcorr_pyramid_f32(_lib.ptr_array(lv), nl, q, h, w, _lib.current_stream()), "pyramid")
+    ref = co.pyramid(l0, nl)
+    for i in range(1, nl):
+        assert np.array_equal(lv[i][:, 0].cpu().numpy(), ref[i]), i
+
+
+# ---------------------------------------------------------------- lookup vs oracle
+def _coords_cases(rng, b, h, w):
+    grid = co.coords_grid(b, h, w)
+    n = lambda s: rng.standard_normal(grid.shape).astype(np.float32) * np.float32(s)
+    far = grid + n(200.0)
+    far[0, :, 0, 0] = [1e7, -1e7]
+    far[0, :, 0, 1] = [np.inf, 0]
+    return {"grid": grid, "half": grid + np.float32(0.5), "s1": grid + n(1), "s3": grid + n(3), "s20": grid + n(20), "far": far}
+
+
+@pytest.mark.parametrize("shape,radius,nl", [((1, 46, 62), 4, 4), ((2, 17, 21), 4, 4), ((1, 24, 40), 3, 4),
+                                             ((2, 12, 9), 2, 3), ((1, 9, 33), 1, 2), ((3, 8, 8), 4, 1)])
+def test_lookup_vs_oracle(shape, radius, nl):
+    b, h, w = shape
+    rng = np.random.default_rng(99)
+    q = b * h * w
+    pyr = [rng.standard_normal((q, h >> i, w >> i)).astype(np.float32) for i in range(nl)]
+    levels = [t(p[:, None]) for p in pyr]
+    for name, c in _coords_cases(rng, b, h, w).items():
+        ref = co.lookup(pyr, c, radius)
+        got = ff().lookup(levels, t(c), radius).cpu().numpy()
+        assert got.shape == ref.shape == (b, nl * (2 * radius + 1) ** 2, h, w)
+        assert np.isfinite(got).all(), name
+        assert max_rel(got, ref) <= 1e-5, (shape, name, max_rel(got, ref))
+
+
+def test_corrblock_surface_and_errors():
+    m = ff()
+    f = torch.randn(1, 16, 16, 24, device=DEV)
+    blk = m.CorrBlock(f, f)
+    assert blk.num_levels == 4 and blk.radius == 4 and len(blk.corr_pyramid) == 4
+    assert [tuple(l.shape) for l in blk.corr_pyramid] == [(384, 1, 16, 24), (384, 1, 8, 12), (384, 1, 4, 6), (384, 1, 2, 3)]
+    out = blk(m.coords_grid(1, 16, 24, DEV))
+    assert out.shape == (1, 324, 16, 24) and out.dtype == torch.float32 and out.is_contiguous()
+    with pytest.raises(ValueError):
+        blk(torch.zeros(1, 2, 8, 8, device=DEV))
+    with pytest.raises(NotImplementedError):
+        m.CorrBlock(f.cpu(), f.cpu())
+    with pytest.raises(ValueError):
+        m.CorrBlock(torch.randn(1, 8, 4, 4, device=DEV), torch.randn(1, 8, 4, 4, device=DEV))  # too small for 4 levels
+    with pytest.raises(RuntimeError):
+        m.lookup(blk.corr_pyramid, m.coords_grid(1, 16, 24, DEV), radius=7)
+
+
+def test_empty_batch():
+    m = ff()
+    f = torch.zeros(0, 32, 16, 16, device=DEV)
+    blk = m.CorrBlock(f, f)
+    assert blk(torch.zeros(0, 2, 16, 16, device=DEV)).shape == (0, 324, 16, 16)
+    assert m.FunctionCorrelation(torch.zeros(0, 8, 5, 5, device=DEV), torch.zeros(0, 8, 5, 5, device=DEV)).shape == (0, 81, 5, 5)
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE config 2)
+def test_full_size_config2_properties():
+    """B=8, 376x1248 -> fmap [8,256,47,156], N=7332 (tile tails in both GEMM dims)."""
+    m = ff()
+    torch.manual_seed(1234)
+    b, d, h, w = 8, 256, 47, 156
+    f1 = torch.randn(b, d, h, w, device=DEV) * 4.4
+    f2 = torch.randn(b, d, h, w, device=DEV) * 4.4
+    blk = m.CorrBlock(f1, f2)
+    n = h * w
+    l0 = blk.corr_pyramid[0].view(b, n, n)
+    # (1) sampled entries against an fp64 dot product
+    idx = torch.randint(0, n, (4096, 2), device=DEV)
+    bi = torch.randint(0, b, (4096,), device=DEV)
+    a = f1.view(b, d, n)[bi, :, idx[:, 0]].double()
+    c = f2.view(b, d, n)[bi, :, idx[:, 1]].double()
+    ref = (a * c).sum(1) / 16.0
+    got = l0[bi, idx[:, 0], idx[:, 1]].double()
+    assert float((got - ref).norm() / ref.norm()) <= 1e-3
+    # the last row / column of the last batch item (tails of the 128x256 tiling)
+    ref_row = (f1.view(b, d, n)[b - 1, :, n - 1].double()[:, None] * f2.view(b, d, n)[b - 1].double()).sum(0) / 16.0
+    assert float((l0[b - 1, n - 1].double() - ref_row).norm() / ref_row.norm()) <= 1e-3
+    # (2) checksum: sum_j C[i,j] = f1[:,i] . sum_j f2[:,j] / sqrt(D)   (linearity of the contraction)
+    colsum = f2.view(b, d, n).double().sum(2)
+    ref_sum = (f1.view(b, d, n).double() * colsum[:, :, None]).sum(1) / 16.0
+    got_sum = l0.double().sum(2)
+    assert float((got_sum - ref_sum).abs().max() / ref_sum.abs().max()) <= 2e-3
+    # (3) swapping the operands transposes the volume
+    blk_t = m.CorrBlock(f2[:1], f1[:1])
+    assert torch.equal(blk_t.corr_pyramid[0].view(n, n), l0[0].t().contiguous())
+    del blk_t
+    # (4) pyramid == ATen avg_pool2d bit for bit at full size
+    cur = blk.corr_pyramid[0]
+    for i in range(1, 4):
+        cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+        assert torch.equal(cur, blk.corr_pyramid[i]), i
+    # (5) lookup at exact integer coordinates reads the volume itself
+    coords = m.coords_grid(b, h, w, DEV)
+    out = blk(coords)
+    assert out.shape == (b, 324, h, w)
+    l0m = blk.corr_pyramid[0].view(b, h, w, h, w)
+    for (aa, bb) in [(4, 4), (0, 0), (8, 3), (2, 8)]:
+        dx, dy = aa - 4, bb - 4
+        ys = torch.arange(h, device=DEV)[:, None].expand(h, w)
+        xs = torch.arange(w, device=DEV)[None, :].expand(h, w)
+        ty, tx = ys + dy, xs + dx
+        ok = (ty >= 0) & (ty < h) & (tx >= 0) & (tx < w)
+        gathered = l0m[:, ys, xs, ty.clamp(0, h - 1), tx.clamp(0, w - 1)] * ok
+        ch = out[:, aa * 9 + bb]
+        assert float((ch - gathered).abs().max()) <= 2e-3 * float(l0m.abs().max())
+    # (6) idempotence / determinism
+    assert torch.equal(out, blk(coords))
+    # (7) a subset of queries against the CPU oracle on the real pyramid
+    coords_r = coords + torch.randn_like(coords) * 3
+    out_r = blk(coords_r)
+    sel = torch.arange(0, n, 97, device=DEV)
+    pyr = [lv.view(b, n, lv.shape[2], lv.shape[3])[b - 1, sel].cpu().numpy() for lv in blk.corr_pyramid]
+    cxy = coords_r.view(b, 2, n)[b - 1][:, sel].cpu().numpy()
+    ref_r = np.concatenate([co.lookup_level(pyr[i], cxy[0] / np.float32(2 ** i), cxy[1] / np.float32(2 ** i), 4)
+                            for i in range(4)], axis=1)
+    got_r = out_r.view(b, 324, n)[b - 1][:, sel].t().cpu().numpy()
+    assert max_rel(got_r, ref_r) <= 1e-5
+
+
+# ---------------------------------------------------------------- gradients
+def test_corrblock_gradients_match_torch_autograd():
+    m = ff()
+    torch.manual_seed(5)
+    b, d, h, w = 2, 32, 16, 20
+    f1 = torch.randn(b, d, h, w, device=DEV, requires_grad=True)
+    f2 = torch.randn(b, d, h, w, device=DEV, requires_grad=True)
+    coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 2
+    wgt = torch.randn(b, 324, h, w, device=DEV)
+
+    blk = m.CorrBlock(f1, f2, precision="fp32")
+    out = blk(coords.detach())
+    (out * wgt).sum().backward()
+    g1, g2 = f1.grad.clone(), f2.grad.clone()
+    f1.grad = None
+    f2.grad = None
+
+    # pure-torch restatement of corr.py (same formulas as the reference) as the autograd checker
+    n = h * w
+    corr = torch.matmul(f1.view(b, d, n).transpose(1, 2), f2.view(b, d, n)) / torch.sqrt(torch.tensor(float(d)))
+    cur = corr.reshape(b * n, 1, h, w)
+    pyr = [cur]
+    for _ in range(3):
+        cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+        pyr.append(cur)
+    c = coords.permute(0, 2, 3, 1).reshape(b * n, 1, 1, 2)
+    dd = torch.linspace(-4, 4, 9, device=DEV)
+    delta = torch.stack(torch.meshgrid(dd, dd, indexing="ij"), dim=-1).view(1, 9, 9, 2)
+    outs = []
+    for i, lv in enumerate(pyr):
+        cl = c / 2 ** i + delta
+        hh, ww = lv.shape[-2:]
+        gx = 2 * cl[..., 0] / (ww - 1) - 1
+        gy = 2 * cl[..., 1] / (hh - 1) - 1
+        s = torch.nn.functional.grid_sample(lv, torch.stack([gx, gy], -1), align_corners=True)
+        outs.append(s.view(b, h, w, -1))
+    ref = torch.cat(outs, -1).permute(0, 3, 1, 2)
+    assert float((ref - out).abs().max()) <= 1e-4 * float(ref.abs().max())
+    (ref * wgt).sum().backward()
+    assert float((g1 - f1.grad).norm() / f1.grad.norm()) <= 1e-4
+    assert float((g2 - f2.grad).norm() / f2.grad.norm()) <= 1e-4
+
+
+def test_lookup_backward_vs_oracle_adjoint():
+    from focusflow_official_b200 import _lib
+
+    rng = np.random.default_rng(21)
+    b, h, w = 1, 10, 12
+    q = b * h * w
+    coords = co.coords_grid(b, h, w) + rng.standard_normal((b, 2, h, w)).astype(np.float32) * 3
+    gout = rng.standard_normal((b, 2 * 81, h, w)).astype(np.float32)
+    glv = [torch.zeros(q, 1, h >> i, w >> i, device=DEV) for i in range(2)]
+    _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), 2, t(coords).data_ptr(), t(gout).data_ptr(), b, h, w, 4,
+                                                _lib.current_stream()), "bwd")
+    c = coords.transpose(0, 2, 3, 1).reshape(q, 2)
+    g = gout.transpose(0, 2, 3, 1).reshape(q, 2, 81)
+    for i in range(2):
+        ref = co.lookup_level_backward(g[:, i], (q, h >> i, w >> i), c[:, 0] / np.float32(2 ** i), c[:, 1] / np.float32(2 ** i), 4)
+        got = glv[i][:, 0].cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), i
+
+
+# ---------------------------------------------------------------- PWC cost volume
+PWC_SHAPES = [(2, 32, 28, 64), (1, 64, 56, 128), (2, 96, 28, 64), (2, 128, 14, 32), (2, 196, 7, 16),
+              (1, 3, 5, 5), (2, 40, 9, 13), (1, 17, 33, 70)]
+
+
+@pytest.mark.parametrize("shape", PWC_SHAPES)
+def test_pwc_forward_vs_oracle(shape):
+    rng = np.random.default_rng(3)
+    one = rng.standard_normal(shape).astype(np.float32)
+    two = rng.standard_normal(shape).astype(np.float32)
+    ref = po.forward_c(one, two)
+    got = ff().FunctionCorrelation(tenOne=t(one), tenTwo=t(two)).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), shape
+    fused = ff().correlation_leaky(t(one), t(two), 0.1).cpu().numpy()
+    assert np.array_equal(fused, np.where(got > 0, got, got * np.float32(0.1)).astype(np.float32))
+
+
+def test_pwc_full_size_level2_properties():
+    """Config 3, pyramid level 2: B=16, C=32, 112x256."""
+    m = ff()
+    torch.manual_seed(3)
+    one = torch.randn(16, 32, 112, 256, device=DEV)
+    two = torch.randn(16, 32, 112, 256, device=DEV)
+    out = m.FunctionCorrelation(one, two)
+    assert out.shape == (16, 81, 112, 256)
+    # centre channel is the plain channel mean of one*two; shifted channels are shifted products
+    assert float((out[:, 40] - (one * two).mean(1)).abs().max()) <= 1e-5
+    dy, dx = 3, -2
+    ref = (one[:, :, : 112 - dy, -dx:] * two[:, :, dy:, : 256 + dx]).mean(1)
+    assert float((out[:, (dy + 4) * 9 + dx + 4, : 112 - dy, -dx:] - ref).abs().max()) <= 1e-5
+    assert float(out[:, (dy + 4) * 9 + dx + 4, 112 - dy:, :].abs().max()) == 0.0
+    # linearity in the second argument
+    out2 = m.FunctionCorrelation(one, two * 2.0)
+    assert float((out2 - 2 * out).abs().max()) <= 1e-5
+    # swap symmetry: corr(one,two)[dy,dx](y,x) == corr(two,one)[-dy,-dx](y+dy,x+dx)
+    outs = m.FunctionCorrelation(two, one)
+    lhs = out[:, (dy + 4) * 9 + dx + 4, : 112 - dy, -dx:]
+    rhs = outs[:, (-dy + 4) * 9 + (-dx) + 4, dy:, : 256 + dx]
+    assert float((lhs - rhs).abs().max()) <= 1e-5
+
+
+def test_pwc_backward_vs_oracle():
+    m = ff()
+    rng = np.random.default_rng(4)
+    shape = (2, 20, 11, 14)
+    one = rng.standard_normal(shape).astype(np.float32)
+    two = rng.standard_normal(shape).astype(np.float32)
+    g = rng.standard_normal((2, 81, 11, 14)).astype(np.float32)
+    a = t(one).requires_grad_(True)
+    bb = t(two).requires_grad_(True)
+    m.ModuleCorrelation()(a, bb).backward(t(g))
+    r1, r2 = po.backward_c(one, two, g)
+    assert np.abs(a.grad.cpu().numpy() - r1).max() <= 1e-5 * max(1.0, np.abs(r1).max())
+    assert np.abs(bb.grad.cpu().numpy() - r2).max() <= 1e-5 * max(1.0, np.abs(r2).max())
+    with pytest.raises(NotImplementedError):
+        m.FunctionCorrelation(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))

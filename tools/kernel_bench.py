@@ -1,0 +1,165 @@
+"""Per-kernel timing of the correlation path (CUDA events, L2 flushed between launches).
+
+Prints one JSON line per kernel with the algorithmic bytes / flops of SURVEY.md 8d and the
+achieved fraction of the measured peaks in MEASURED_PEAKS.json.  Development tool; bench.py
+reuses `time_kernels()` for its roofline block.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["source"] = "fallback"
+    return d
+
+
+class L2Flusher:
+    def __init__(self, dev, mb=512):
+        self.buf = torch.empty(mb * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def time_cuda(fn, iters=10, warmup=3, flush=None):
+    """Median / min duration in ms of fn() measured with CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def raft_shapes(config):
+    return {1: (1, 256, 46, 62), 2: (8, 256, 47, 156), 4: (8, 256, 55, 128), 5: (8, 256, 46, 62)}[config]
+
+
+def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, verbose=False):
+    import focusflow_official_b200 as ff
+    from focusflow_official_b200 import _lib
+
+    peaks = load_peaks()
+    L = _lib.lib()
+    b, d, h, w = raft_shapes(config)
+    n = h * w
+    torch.manual_seed(1234)
+    f1 = torch.randn(b, d, h, w, device=dev) * 4.4
+    f2 = torch.randn(b, d, h, w, device=dev) * 4.4
+    nl, r = 4, 4
+    levels = [torch.empty(b * n, 1, h >> i, w >> i, device=dev) for i in range(nl)]
+    code = _lib.PRECISIONS[precision]
+    ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, code)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    ptrs = _lib.ptr_array(levels)
+    stream = _lib.current_stream()
+    coords = ff.coords_grid(b, h, w, dev) + torch.randn(b, 2, h, w, device=dev) * sigma
+    out = torch.empty(b, nl * 81, h, w, device=dev)
+    flush = L2Flusher(dev)
+
+    def k_volume():
+        _lib.check(L.ffcorr_volume_f32(f1.data_ptr(), f2.data_ptr(), levels[0].data_ptr(), b, d, h, w, code,
+                                       ws.data_ptr(), ws_bytes, stream), "volume")
+
+    def k_pyramid():
+        _lib.check(L.ffcorr_pyramid_f32(ptrs, nl, b * n, h, w, stream), "pyramid")
+
+    def k_lookup():
+        _lib.check(L.ffcorr_lookup_f32(ptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, stream), "lookup")
+
+    res = []
+    lv_elems = [(h >> i) * (w >> i) for i in range(nl)]
+    vol_flops = 2.0 * b * n * n * d
+    vol_bytes = b * (2 * n * d * 4 + n * n * 4)
+    pyr_bytes = 4.0 * b * n * sum(lv_elems)
+    look_bytes = b * n * (nl * (2 * r + 2) ** 2 * 4 + nl * (2 * r + 1) ** 2 * 4 + 8)
+    for name, fn, byts, flops in (("volume", k_volume, vol_bytes, vol_flops), ("pyramid", k_pyramid, pyr_bytes, 0.0),
+                                  ("lookup", k_lookup, look_bytes, 0.0)):
+        med, best = time_cuda(fn, iters=iters, flush=flush)
+        gbs = byts / (med * 1e-3) / 1e9
+        rec = {"kernel": name, "config": config, "ms": round(med, 4), "ms_min": round(best, 4),
+               "algorithmic_bytes": int(byts), "GBps": round(gbs, 1), "frac_hbm": round(gbs / peaks["hbm_gbs"], 4),
+               "peaks": peaks["source"]}
+        if flops:
+            tf = flops / (med * 1e-3) / 1e12
+            rec.update({"TFLOPs": round(tf, 1), "frac_bf16_burst": round(tf / peaks["bf16_tflops"], 4), "precision": precision})
+        res.append(rec)
+        if verbose:
+            print(json.dumps(rec), flush=True)
+    return res
+
+
+def time_pwc(iters=10, dev="cuda:0", batch=16, verbose=False):
+    import focusflow_official_b200 as ff
+
+    peaks = load_peaks()
+    flush = L2Flusher(dev)
+    shapes = [(32, 112, 256), (64, 56, 128), (96, 28, 64), (128, 14, 32), (196, 7, 16)]
+    res = []
+    tot_ms = tot_b = 0.0
+    for c, hh, ww in shapes:
+        one = torch.randn(batch, c, hh, ww, device=dev)
+        two = torch.randn(batch, c, hh, ww, device=dev)
+        med, best = time_cuda(lambda: ff.FunctionCorrelation(one, two), iters=iters, flush=flush)
+        byts = 4.0 * batch * hh * ww * (2 * c + 81)
+        flops = 162.0 * c * batch * hh * ww
+        tot_ms += med
+        tot_b += byts
+        rec = {"kernel": "pwc81", "C": c, "H": hh, "W": ww, "B": batch, "ms": round(med, 4), "ms_min": round(best, 4),
+               "GBps": round(byts / med / 1e6, 1), "frac_hbm": round(byts / med / 1e6 / peaks["hbm_gbs"], 4),
+               "TFLOPs_fp32": round(flops / med / 1e9, 2)}
+        res.append(rec)
+        if verbose:
+            print(json.dumps(rec), flush=True)
+    rec = {"kernel": "pwc81_total", "ms": round(tot_ms, 4), "GBps": round(tot_b / tot_ms / 1e6, 1),
+           "frac_hbm": round(tot_b / tot_ms / 1e6 / peaks["hbm_gbs"], 4)}
+    res.append(rec)
+    if verbose:
+        print(json.dumps(rec), flush=True)
+    return res
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--precision", default="fp16")
+    ap.add_argument("--sigma", type=float, default=3.0)
+    ap.add_argument("--pwc", action="store_true")
+    ap.add_argument("--all-precisions", action="store_true")
+    a = ap.parse_args()
+    if a.all_precisions:
+        for pr in ("fp16", "tf32", "bf16x3"):
+            time_kernels(a.config, a.iters, pr, sigma=a.sigma, verbose=True)
+    else:
+        time_kernels(a.config, a.iters, a.precision, sigma=a.sigma, verbose=True)
+    if a.pwc:
+        time_pwc(a.iters, verbose=True)
