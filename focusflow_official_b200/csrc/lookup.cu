@@ -262,8 +262,9 @@ using namespace ffcorr;
 
 extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
                                  int B, int h, int w, int radius, void* stream) {
-    FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "lookup: null pointer");
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup: B=%d", B);
+    if (B == 0) return FFCORR_OK;  // empty batch: pointers may legitimately be null
+    FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "lookup: null pointer");
     FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup: radius=%d outside [1,4]", radius);
     if (int rc = check_levels(num_levels, h, w, "lookup")) return rc;
     if (B == 0) return FFCORR_OK;
@@ -292,8 +293,9 @@ extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const 
 
 extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, const float* coords,
                                      const float* grad_out, int B, int h, int w, int radius, void* stream) {
-    FFCORR_REQUIRE(grad_lvl && coords && grad_out, FFCORR_EINVAL, "lookup_bwd: null pointer");
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup_bwd: B=%d", B);
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(grad_lvl && coords && grad_out, FFCORR_EINVAL, "lookup_bwd: null pointer");
     FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup_bwd: radius=%d outside [1,4]", radius);
     if (int rc = check_levels(num_levels, h, w, "lookup_bwd")) return rc;
     if (B == 0) return FFCORR_OK;

@@ -164,8 +164,9 @@ using namespace ffcorr;
 
 extern "C" int ffcorr_pwc81_f32(const float* one, const float* two, float* out, int B, int C, int H, int W,
                                 float leaky_slope, void* stream) {
-    FFCORR_REQUIRE(one && two && out, FFCORR_EINVAL, "pwc81: null pointer");
     FFCORR_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, FFCORR_EINVAL, "pwc81: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(one && two && out, FFCORR_EINVAL, "pwc81: null pointer");
     FFCORR_REQUIRE(leaky_slope < 1.0f, FFCORR_EINVAL, "pwc81: leaky_slope=%f must be < 1 (negative = off)", leaky_slope);
     if (B == 0) return FFCORR_OK;
     dim3 grid(ceil_div(W, PT_X), ceil_div(H, PT_Y), B);
@@ -176,8 +177,9 @@ extern "C" int ffcorr_pwc81_f32(const float* one, const float* two, float* out, 
 
 extern "C" int ffcorr_pwc81_bwd_f32(const float* one, const float* two, const float* grad_out, float* grad_one,
                                     float* grad_two, int B, int C, int H, int W, void* stream) {
-    FFCORR_REQUIRE(one && two && grad_out, FFCORR_EINVAL, "pwc81_bwd: null pointer");
     FFCORR_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, FFCORR_EINVAL, "pwc81_bwd: bad shape");
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(one && two && grad_out, FFCORR_EINVAL, "pwc81_bwd: null pointer");
     if (B == 0 || (!grad_one && !grad_two)) return FFCORR_OK;
     const int64_t total = (int64_t)B * C * H * W;
     const int64_t want = ceil_div64(total, 256);

@@ -122,9 +122,9 @@ extern "C" int ffcorr_pyramid_f32(float* const* lvl, int num_levels, int64_t Q, 
     FFCORR_REQUIRE(lvl != nullptr, FFCORR_EINVAL, "pyramid: null level table");
     FFCORR_REQUIRE(Q >= 0, FFCORR_EINVAL, "pyramid: Q=%lld", (long long)Q);
     if (int rc = check_levels(num_levels, h, w, "pyramid")) return rc;
+    if (Q == 0 || num_levels == 1) return FFCORR_OK;
     for (int i = 0; i < num_levels; ++i)
         FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "pyramid: lvl[%d] is null", i);
-    if (Q == 0 || num_levels == 1) return FFCORR_OK;
     cudaStream_t s = (cudaStream_t)stream;
 
     // fused single-pass path: up to 4 levels, group of maps must fit in shared memory
@@ -184,9 +184,9 @@ extern "C" int ffcorr_pyramid_bwd_f32(float* const* grad_lvl, int num_levels, in
     FFCORR_REQUIRE(grad_lvl != nullptr, FFCORR_EINVAL, "pyramid_bwd: null level table");
     FFCORR_REQUIRE(Q >= 0, FFCORR_EINVAL, "pyramid_bwd: Q=%lld", (long long)Q);
     if (int rc = check_levels(num_levels, h, w, "pyramid_bwd")) return rc;
+    if (Q == 0) return FFCORR_OK;
     for (int i = 0; i < num_levels; ++i)
         FFCORR_REQUIRE(grad_lvl[i] != nullptr, FFCORR_EINVAL, "pyramid_bwd: grad_lvl[%d] is null", i);
-    if (Q == 0) return FFCORR_OK;
     cudaStream_t s = (cudaStream_t)stream;
     for (int i = num_levels - 1; i >= 1; --i) {
         const int hi = h >> (i - 1), wi = w >> (i - 1), ho = h >> i, wo = w >> i;

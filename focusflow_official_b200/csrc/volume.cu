@@ -528,10 +528,10 @@ extern "C" size_t ffcorr_volume_workspace_bytes(int B, int D, int h, int w, int 
 
 extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
                                  int precision, void* workspace, size_t workspace_bytes, void* stream) {
-    FFCORR_REQUIRE(fmap1 && fmap2 && lvl0, FFCORR_EINVAL, "volume: null pointer");
     FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume: bad shape B=%d D=%d h=%d w=%d", B, D, h, w);
     FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "volume: h*w=%lld too large", (long long)h * w);
-    if (B == 0) return FFCORR_OK;
+    if (B == 0) return FFCORR_OK;  // empty batch: pointers may legitimately be null
+    FFCORR_REQUIRE(fmap1 && fmap2 && lvl0, FFCORR_EINVAL, "volume: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const int N = h * w;
     const float sqrt_d = sqrtf((float)D);
@@ -622,9 +622,9 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
 
 extern "C" int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1, const float* fmap2, float* gfmap1,
                                      float* gfmap2, int B, int D, int h, int w, void* stream) {
-    FFCORR_REQUIRE(grad_lvl0 && fmap1 && fmap2, FFCORR_EINVAL, "volume_bwd: null pointer");
     FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume_bwd: bad shape");
     if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(grad_lvl0 && fmap1 && fmap2, FFCORR_EINVAL, "volume_bwd: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const int N = h * w;
     const float sqrt_d = sqrtf((float)D);

@@ -63,7 +63,7 @@ def raft_shapes(config):
     return {1: (1, 256, 46, 62), 2: (8, 256, 47, 156), 4: (8, 256, 55, 128), 5: (8, 256, 46, 62)}[config]
 
 
-def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, verbose=False):
+def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, verbose=False, warmup=3):
     import focusflow_official_b200 as ff
     from focusflow_official_b200 import _lib
 
@@ -103,7 +103,7 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     look_bytes = b * n * (nl * (2 * r + 2) ** 2 * 4 + nl * (2 * r + 1) ** 2 * 4 + 8)
     for name, fn, byts, flops in (("volume", k_volume, vol_bytes, vol_flops), ("pyramid", k_pyramid, pyr_bytes, 0.0),
                                   ("lookup", k_lookup, look_bytes, 0.0)):
-        med, best = time_cuda(fn, iters=iters, flush=flush)
+        med, best = time_cuda(fn, iters=iters, warmup=warmup, flush=flush)
         gbs = byts / (med * 1e-3) / 1e9
         rec = {"kernel": name, "config": config, "ms": round(med, 4), "ms_min": round(best, 4),
                "algorithmic_bytes": int(byts), "GBps": round(gbs, 1), "frac_hbm": round(gbs / peaks["hbm_gbs"], 4),
@@ -117,7 +117,7 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     return res
 
 
-def time_pwc(iters=10, dev="cuda:0", batch=16, verbose=False):
+def time_pwc(iters=10, dev="cuda:0", batch=16, verbose=False, warmup=3):
     import focusflow_official_b200 as ff
 
     peaks = load_peaks()
@@ -128,7 +128,7 @@ def time_pwc(iters=10, dev="cuda:0", batch=16, verbose=False):
     for c, hh, ww in shapes:
         one = torch.randn(batch, c, hh, ww, device=dev)
         two = torch.randn(batch, c, hh, ww, device=dev)
-        med, best = time_cuda(lambda: ff.FunctionCorrelation(one, two), iters=iters, flush=flush)
+        med, best = time_cuda(lambda: ff.FunctionCorrelation(one, two), iters=iters, warmup=warmup, flush=flush)
         byts = 4.0 * batch * hh * ww * (2 * c + 81)
         flops = 162.0 * c * batch * hh * ww
         tot_ms += med
@@ -154,12 +154,13 @@ if __name__ == "__main__":
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--sigma", type=float, default=3.0)
     ap.add_argument("--pwc", action="store_true")
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--all-precisions", action="store_true")
     a = ap.parse_args()
     if a.all_precisions:
         for pr in ("fp16", "tf32", "bf16x3"):
-            time_kernels(a.config, a.iters, pr, sigma=a.sigma, verbose=True)
+            time_kernels(a.config, a.iters, pr, sigma=a.sigma, verbose=True, warmup=a.warmup)
     else:
-        time_kernels(a.config, a.iters, a.precision, sigma=a.sigma, verbose=True)
+        time_kernels(a.config, a.iters, a.precision, sigma=a.sigma, verbose=True, warmup=a.warmup)
     if a.pwc:
-        time_pwc(a.iters, verbose=True)
+        time_pwc(a.iters, verbose=True, warmup=a.warmup)
