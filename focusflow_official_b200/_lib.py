@@ -28,6 +28,8 @@ _PROTOS = {
     "ffcorr_version": (_i, []),
     "ffcorr_last_error": (ctypes.c_char_p, []),
     "ffcorr_device_info": (_i, [ctypes.POINTER(_i)] * 3),
+    "ffcorr_set_l2_fetch_granularity": (_i, [_i]),
+    "ffcorr_get_l2_fetch_granularity": (_i, [ctypes.POINTER(_i)]),
     "ffcorr_volume_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
     "ffcorr_volume_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_pyramid_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),

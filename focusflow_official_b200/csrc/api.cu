@@ -57,3 +57,16 @@ extern "C" int ffcorr_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (cc_minor) *cc_minor = min;
     return FFCORR_OK;
 }
+
+extern "C" int ffcorr_set_l2_fetch_granularity(int bytes) {
+    FFCORR_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, FFCORR_EINVAL, "l2 fetch granularity must be 32, 64 or 128");
+    FFCORR_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    return FFCORR_OK;
+}
+
+extern "C" int ffcorr_get_l2_fetch_granularity(int* bytes) {
+    size_t v = 0;
+    FFCORR_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+    if (bytes) *bytes = (int)v;
+    return FFCORR_OK;
+}

@@ -22,6 +22,8 @@
 // ATen un-normalises them again (GridSampler.cuh:26).  That fp32 round trip perturbs
 // every tap differently (up to ~2e-5 px), which is visible at the 1e-5 parity bar, so
 // it is reproduced per tap with explicitly rounded intrinsics (no FMA contraction).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ffcorr {
@@ -51,7 +53,7 @@ __device__ __forceinline__ float source_index(float x, float size_m1) {
 // |index| beyond this is outside every supported map (h, w <= 16384): all taps are zero.
 constexpr float kWildLimit = 3.0e4f;
 
-template <int R>
+template <int R, int QU>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const LookupParams p) {
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;        // window extent incl. the +-1 floor deviation of the round trip
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
     const int64_t map_elems = (int64_t)lh * lw;
     const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * map_elems;
 
-    constexpr int QU = 4;  // queries in flight per lane: QU * NLOAD independent loads
+    // QU queries in flight per lane: QU * NLOAD independent loads
 #pragma unroll 1
     for (int q0 = 0; q0 < kTile; q0 += QU) {
         float v[QU][NLOAD];
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_kernel(const LookupBwdParams p
     }
 }
 
-template <int R>
+template <int R, int QU>
 int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
     constexpr int WIN = (K + 2) * (K + 2);
@@ -246,12 +248,12 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     int dev = 0;
     FFCORR_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_dev = dev;
     }
     const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup: grid too large (%lld blocks)", (long long)blocks);
-    lookup_kernel<R><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    lookup_kernel<R, QU><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
     return check_launch("lookup_kernel");
 }
 
@@ -283,11 +285,12 @@ extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const 
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
+    static const int qu = [] { const char* e = getenv("FFCORR_LOOKUP_QU"); return e ? atoi(e) : 4; }();
     switch (radius) {
-        case 1: return launch_lookup<1>(p, s);
-        case 2: return launch_lookup<2>(p, s);
-        case 3: return launch_lookup<3>(p, s);
-        default: return launch_lookup<4>(p, s);
+        case 1: return launch_lookup<1, 4>(p, s);
+        case 2: return launch_lookup<2, 4>(p, s);
+        case 3: return launch_lookup<3, 4>(p, s);
+        default: return qu == 8 ? launch_lookup<4, 8>(p, s) : (qu == 2 ? launch_lookup<4, 2>(p, s) : launch_lookup<4, 4>(p, s));
     }
 }
 

@@ -42,34 +42,79 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_fused_kernel(const PyrPar
     const int e0 = g * p.n[0];
     const float* __restrict__ src = p.l0 + q0 * p.n[0];
     if (VEC4) {
+        // all of a thread's 16-byte loads are issued before the first shared-memory store, so a
+        // block has its whole group in flight at once (8 x 16 B x 256 threads = 32 KB per round)
         const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
         float4* d4 = reinterpret_cast<float4*>(sm);
         const int n4 = e0 >> 2;
-        for (int i = tid; i < n4; i += kPyrThreads) d4[i] = __ldcs(s4 + i);
+        constexpr int U = 8;
+        for (int base = 0; base < n4; base += U * kPyrThreads) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kPyrThreads + tid;
+                if (i < n4) v[u] = __ldcs(s4 + i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kPyrThreads + tid;
+                if (i < n4) d4[i] = v[u];
+            }
+        }
         for (int i = (n4 << 2) + tid; i < e0; i += kPyrThreads) sm[i] = __ldcs(src + i);
     } else {
-        for (int i = tid; i < e0; i += kPyrThreads) sm[i] = __ldcs(src + i);
+        constexpr int U = 8;
+        for (int base = 0; base < e0; base += U * kPyrThreads) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kPyrThreads + tid;
+                if (i < e0) v[u] = __ldcs(src + i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kPyrThreads + tid;
+                if (i < e0) sm[i] = v[u];
+            }
+        }
     }
     __syncthreads();
 
-    // ---- levels 1.. from shared memory ----
+    // ---- levels 1.. from shared memory: a warp per output row, lanes along x ----
+    // (one integer division per ROW, not per element; 8-byte smem reads when the input
+    //  width is even so a lane fetches its 2x2 window with two LDS.64)
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = kPyrThreads / 32;
     float* sin = sm;
     float* sout = sm + (size_t)p.G * p.n[0];
 #pragma unroll 1
     for (int l = 1; l < p.num_levels; ++l) {
-        const int hi = p.h[l - 1], wi = p.w[l - 1], ni = p.n[l - 1];
+        const int wi = p.w[l - 1], ni = p.n[l - 1];
         const int ho = p.h[l], wo = p.w[l], no = p.n[l];
-        (void)hi; (void)ho;
-        const int eo = g * no;
         float* __restrict__ dst = p.out[l] + q0 * no;
-        for (int i = tid; i < eo; i += kPyrThreads) {
-            const int m = i / no;
-            const int r = i - m * no;
-            const int y = r / wo;
-            const int x = r - y * wo;
-            const float v = pool4(sin + m * ni + (2 * y) * wi + 2 * x, wi);
-            sout[i] = v;
-            dst[i] = v;
+        const int rows = g * ho;
+        const bool even = ((wi & 1) == 0) && (((sin - sm) & 1) == 0);
+        for (int row = warp; row < rows; row += NW) {
+            const int m = row / ho;
+            const int y = row - m * ho;
+            const float* r0 = sin + m * ni + (2 * y) * wi;
+            const int o = m * no + y * wo;
+            if (even) {
+                const float2* a2 = reinterpret_cast<const float2*>(r0);
+                const float2* b2 = reinterpret_cast<const float2*>(r0 + wi);
+                for (int x = lane; x < wo; x += 32) {
+                    const float2 a = a2[x], bb = b2[x];
+                    const float v = (((a.x + a.y) + bb.x) + bb.y) * 0.25f;
+                    sout[o + x] = v;
+                    dst[o + x] = v;
+                }
+            } else {
+                for (int x = lane; x < wo; x += 32) {
+                    const float v = pool4(r0 + 2 * x, wi);
+                    sout[o + x] = v;
+                    dst[o + x] = v;
+                }
+            }
         }
         __syncthreads();
         sin = sout;

@@ -172,7 +172,7 @@ struct GemmParams {
     float* out;     // only used by the non-TMA epilogue (N % 4 != 0)
 };
 
-template <bool TF32, bool TMA_STORE>
+template <bool TF32, bool TMA_STORE, bool DIV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p, const uint32_t idesc) {
@@ -296,7 +296,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float a = __uint_as_float(v[i]);
-                    f[i] = p.use_div ? __fdiv_rn(a, p.divisor) : a * p.scale;
+                    f[i] = DIV ? __fdiv_rn(a, p.divisor) : a * p.scale;  // compile-time: keeps the loop body in the I-cache
                 }
                 const int col0 = n0 + c * STORE_COLS;
                 if (TMA_STORE) {
@@ -344,42 +344,89 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // ------------------------------------------------------------------------------------------
 enum : int { CVT_F16 = 0, CVT_BF16X3_A = 1, CVT_BF16X3_B = 2, CVT_F32 = 3 };
 
+constexpr int PP_D = 32;    // K (channel) extent of a pre-pass tile
+constexpr int PP_N = 128;   // pixel extent of a pre-pass tile
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    __nv_bfloat162 h;
+    h.x = a;
+    h.y = b;
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Transposing convert.  Reads are 16-byte vectors along the pixel axis, writes are full 32-byte
+// sectors along K (16 consecutive channels of one pixel per thread).
 template <int MODE>
 __global__ void __launch_bounds__(256) operand_prepass_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                                                               void* __restrict__ o1, void* __restrict__ o2,
                                                               int B, int D, int N, int Dp /* padded K per segment */) {
-    __shared__ float tile[32][33];
+    __shared__ __align__(16) float tile[PP_D][PP_N + 4];
     const int which = blockIdx.z / B;          // 0: fmap1 (A operand), 1: fmap2 (B operand)
     const int b = blockIdx.z - which * B;
     const float* __restrict__ in = (which == 0 ? f1 : f2) + (size_t)b * D * N;
-    const int n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    void* __restrict__ outp = which == 0 ? o1 : o2;
+    const int n0 = blockIdx.x * PP_N, d0 = blockIdx.y * PP_D;
+    const int tid = threadIdx.x;
+    const bool vec_ok = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int d = d0 + ty + 8 * i, n = n0 + tx;
-        tile[ty + 8 * i][tx] = (d < D && n < N) ? __ldg(in + (size_t)d * N + n) : 0.0f;
+        const int dd = (tid >> 5) + 8 * i, nn = (tid & 31) * 4;
+        const int d = d0 + dd, n = n0 + nn;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d < D) {
+            const float* src = in + (size_t)d * N + n;
+            if (vec_ok) {
+                if (n < N) v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+                if (n + 0 < N) v.x = __ldg(src + 0);
+                if (n + 1 < N) v.y = __ldg(src + 1);
+                if (n + 2 < N) v.z = __ldg(src + 2);
+                if (n + 3 < N) v.w = __ldg(src + 3);
+            }
+        }
+        *reinterpret_cast<float4*>(&tile[dd][nn]) = v;
     }
     __syncthreads();
+    const int nl = tid & (PP_N - 1), half = tid >> 7;
+    const int n = n0 + nl;
+    if (n >= N) return;
+    float x[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = n0 + ty + 8 * i, d = d0 + tx;
-        if (n >= N) continue;
-        const float x = tile[tx][ty + 8 * i];
-        if (MODE == CVT_F16) {
-            __half* o = reinterpret_cast<__half*>(which == 0 ? o1 : o2) + ((size_t)b * N + n) * Dp;
-            o[d] = __float2half_rn(x);
-        } else if (MODE == CVT_F32) {
-            float* o = reinterpret_cast<float*>(which == 0 ? o1 : o2) + ((size_t)b * N + n) * Dp;
-            o[d] = x;
-        } else {
-            // bf16 hi/lo split; A rows hold [hi | hi | lo], B rows [hi | lo | hi] so that one
-            // K = 3*Dp GEMM computes hi*hi + hi*lo + lo*hi with fp32 accumulation.
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(which == 0 ? o1 : o2) + ((size_t)b * N + n) * (3 * (size_t)Dp);
-            const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-            o[d] = hi;
-            o[Dp + d] = (which == 0) ? hi : lo;
-            o[2 * Dp + d] = (which == 0) ? lo : hi;
+    for (int k = 0; k < 16; ++k) x[k] = tile[half * 16 + k][nl];
+    const int dcol = d0 + half * 16;
+    if (MODE == CVT_F16) {
+        __half* o = reinterpret_cast<__half*>(outp) + ((size_t)b * N + n) * Dp + dcol;
+        uint4 q0 = make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
+        uint4 q1 = make_uint4(pack_h2(x[8], x[9]), pack_h2(x[10], x[11]), pack_h2(x[12], x[13]), pack_h2(x[14], x[15]));
+        reinterpret_cast<uint4*>(o)[0] = q0;
+        reinterpret_cast<uint4*>(o)[1] = q1;
+    } else if (MODE == CVT_F32) {
+        float* o = reinterpret_cast<float*>(outp) + ((size_t)b * N + n) * Dp + dcol;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            reinterpret_cast<float4*>(o)[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+    } else {
+        // bf16 hi/lo split; A rows hold [hi | hi | lo], B rows [hi | lo | hi] so that one
+        // K = 3*Dp GEMM computes hi*hi + hi*lo + lo*hi with fp32 accumulation.
+        __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            hi[k] = __float2bfloat16_rn(x[k]);
+            lo[k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi[k]));
+        }
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + ((size_t)b * N + n) * (3 * (size_t)Dp) + dcol;
+#pragma unroll
+        for (int seg = 0; seg < 3; ++seg) {
+            const bool use_lo = (which == 0) ? (seg == 2) : (seg == 1);
+            const __nv_bfloat16* v = use_lo ? lo : hi;
+            uint4 q0 = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
+            uint4 q1 = make_uint4(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]), pack_bf2(v[12], v[13]), pack_bf2(v[14], v[15]));
+            reinterpret_cast<uint4*>(o + (size_t)seg * Dp)[0] = q0;
+            reinterpret_cast<uint4*>(o + (size_t)seg * Dp)[1] = q1;
         }
     }
 }
@@ -558,7 +605,7 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
 
     // ---- 1. operand pre-pass ----
     {
-        dim3 grid(ceil_div(N, 32), Dp / 32, 2 * B);
+        dim3 grid(ceil_div(N, PP_N), Dp / PP_D, 2 * B);
         FFCORR_REQUIRE(grid.y < 65536 && grid.z < 65536, FFCORR_EINVAL, "volume: pre-pass grid too large");
         if (precision == FFCORR_PREC_FP16)
             operand_prepass_kernel<CVT_F16><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp);
@@ -607,15 +654,21 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
     const int64_t num_tiles = (int64_t)p.tiles_m * p.tiles_n * B;
     FFCORR_REQUIRE(num_tiles < (1ll << 31), FFCORR_EINVAL, "volume: too many tiles");
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-#define FF_GEMM(TF, TS)                                                                                  \
-    do {                                                                                                 \
-        if (int rc = set_smem(volume_gemm_kernel<TF, TS>, SMEM_GEMM_TOTAL)) return rc;                   \
-        volume_gemm_kernel<TF, TS><<<grid, GEMM_THREADS, SMEM_GEMM_TOTAL, s>>>(ta, tb, tc, p, idesc);    \
+#define FF_GEMM(TF, TS, DV)                                                                                  \
+    do {                                                                                                     \
+        if (int rc = set_smem(volume_gemm_kernel<TF, TS, DV>, SMEM_GEMM_TOTAL)) return rc;                   \
+        volume_gemm_kernel<TF, TS, DV><<<grid, GEMM_THREADS, SMEM_GEMM_TOTAL, s>>>(ta, tb, tc, p, idesc);    \
     } while (0)
-    if (tf32 && tma_store) FF_GEMM(true, true);
-    else if (tf32) FF_GEMM(true, false);
-    else if (tma_store) FF_GEMM(false, true);
-    else FF_GEMM(false, false);
+#define FF_GEMM_DV(TF, TS)            \
+    do {                              \
+        if (p.use_div) FF_GEMM(TF, TS, true); \
+        else FF_GEMM(TF, TS, false);  \
+    } while (0)
+    if (tf32 && tma_store) FF_GEMM_DV(true, true);
+    else if (tf32) FF_GEMM_DV(true, false);
+    else if (tma_store) FF_GEMM_DV(false, true);
+    else FF_GEMM_DV(false, false);
+#undef FF_GEMM_DV
 #undef FF_GEMM
     return check_launch("volume_gemm_kernel");
 }

@@ -63,6 +63,14 @@ const char* ffcorr_last_error(void);
 int ffcorr_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /*
+ * Device-wide hint for the DRAM->L2 fetch size (cudaLimitMaxL2FetchGranularity: 32, 64 or 128).
+ * The lookup is a gather of 40-byte window rows; with the default 64-byte granularity about
+ * half of every fetched pair of sectors is never used.  The host code sets 32 once per process.
+ */
+int ffcorr_set_l2_fetch_granularity(int bytes);
+int ffcorr_get_l2_fetch_granularity(int* bytes);
+
+/*
  * All-pairs correlation volume, level 0 of the pyramid.
  *   fmap1, fmap2 : [B, D, h, w]          (raft.py:191-193 hands them over as fp32 NCHW)
  *   lvl0         : [B*h*w, h, w]         == reference [B*N, 1, h, w], N = h*w

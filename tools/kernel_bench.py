@@ -69,6 +69,8 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
 
     peaks = load_peaks()
     L = _lib.lib()
+    if os.environ.get("FFCORR_L2_FETCH"):
+        _lib.check(L.ffcorr_set_l2_fetch_granularity(int(os.environ["FFCORR_L2_FETCH"])), "l2 fetch")
     b, d, h, w = raft_shapes(config)
     n = h * w
     torch.manual_seed(1234)
