@@ -376,3 +376,30 @@ def test_pwc_backward_vs_oracle():
     assert np.abs(bb.grad.cpu().numpy() - r2).max() <= 1e-5 * max(1.0, np.abs(r2).max())
     with pytest.raises(NotImplementedError):
         m.FunctionCorrelation(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
+
+
+# ---------------------------------------------------------------- end-to-end EPE (BASELINE: <= 0.01 px after 12 iters)
+def test_e2e_epe_vs_reference_golden():
+    """The PyTorch host model + B200 CorrBlock against FF_RAFT_FUSION outputs recorded by
+    oracle/make_golden.py (reference on CPU, same deterministic weights and inputs)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_host_model import make_model
+    from weights import synthetic_pair
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ffraft_e2e.npz"))
+    torch.backends.cudnn.allow_tf32 = False  # isolate the correlation path: fp32 convs like the CPU reference
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = make_model(DEV)
+    for tag in ("a", "b"):
+        b, hh, ww, iters = [int(v) for v in g[f"{tag}_shape"]]
+        im1, im2, m1, m2 = (x.to(DEV) for x in synthetic_pair(b, hh, ww, seed=1234 + b))
+        for prec in ("fp16", "fp32"):
+            model.flow_net.corr_precision = prec
+            with torch.no_grad():
+                lo, up = model(im1, im2, m1, m2, raft_iters=iters, test_mode=True)
+            epe = torch.linalg.norm(up.cpu() - torch.from_numpy(g[f"{tag}_flow_up"]), dim=1)
+            print(f"e2e {tag} {prec}: EPE mean {float(epe.mean()):.2e} max {float(epe.max()):.2e}")
+            assert float(epe.max()) <= 1e-2, (tag, prec, float(epe.max()))  # BASELINE: EPE within 0.01 px
+            assert float(epe.mean()) <= 2e-3

@@ -1,0 +1,55 @@
+"""Deterministic weights and synthetic inputs shared by the golden generator
+(oracle/make_golden.py, runs the reference) and the tests / bench (run this repo's host model).
+
+Weights are a pure function of (seed, state_dict key, shape), so the reference model and the
+re-written host model get bit-identical parameters without committing a 30 MB checkpoint.
+"""
+from __future__ import annotations
+
+import zlib
+
+import numpy as np
+import torch
+
+
+def fill_state_dict(sd: dict, seed: int = 1234) -> dict:
+    """In-place, key-wise deterministic fill (kaiming-like scale so activations stay O(1))."""
+    for key in sorted(sd.keys()):
+        t = sd[key]
+        rng = np.random.RandomState((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31 - 1))
+        if key.endswith("num_batches_tracked"):
+            t.fill_(1)
+            continue
+        shape = tuple(t.shape)
+        if key.endswith("running_var"):
+            v = 1.0 + 0.1 * rng.rand(*shape)
+        elif key.endswith("running_mean"):
+            v = 0.05 * rng.randn(*shape)
+        elif t.dim() == 4:  # conv weight [out, in, kh, kw]: fan_out kaiming like the reference init
+            fan_out = shape[0] * shape[2] * shape[3]
+            v = rng.randn(*shape) * np.sqrt(2.0 / fan_out)
+            if key.endswith("flow_head.conv2.weight"):
+                v = v * 0.004  # keep the random-init refinement contractive (sub-px updates, like a trained net)
+        elif key.endswith("weight"):  # norm scale
+            v = 1.0 + 0.05 * rng.randn(*shape)
+        else:  # biases
+            v = 0.02 * rng.randn(*shape)
+        t.copy_(torch.from_numpy(np.asarray(v, dtype=np.float32)).reshape(shape))
+    return sd
+
+
+def synthetic_pair(batch: int, height: int, width: int, seed: int = 1234, keypoints: int = 500, border: int = 31):
+    """SURVEY 8d synthetic inputs: image1 ~ U[0,255), image2 = image1 shifted by (3,5) px + N(0,2),
+    ORB-style point mask (255 at `keypoints` random pixels >= `border` px from the edge)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    im1 = torch.rand(batch, 3, height, width, generator=g) * 255.0
+    im2 = torch.roll(im1, shifts=(3, 5), dims=(2, 3)) + torch.randn(batch, 3, height, width, generator=g) * 2.0
+    im2 = im2.clamp_(0.0, 255.0)
+    bd = min(border, height // 4, width // 4)
+    mask = torch.zeros(batch, 1, height, width)
+    ys = torch.randint(bd, height - bd, (batch, keypoints), generator=g)
+    xs = torch.randint(bd, width - bd, (batch, keypoints), generator=g)
+    for b in range(batch):
+        mask[b, 0, ys[b], xs[b]] = 255.0
+    return im1, im2, mask, mask.clone()
