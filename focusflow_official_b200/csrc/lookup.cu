@@ -30,7 +30,7 @@ namespace ffcorr {
 
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 2;
 constexpr int kTile = 32;  // queries per warp
 
 struct LookupParams {
@@ -53,20 +53,30 @@ __device__ __forceinline__ float source_index(float x, float size_m1) {
 // |index| beyond this is outside every supported map (h, w <= 16384): all taps are zero.
 constexpr float kWildLimit = 3.0e4f;
 
-template <int R, int QU>
+template <int LD>
+__device__ __forceinline__ float gather_load(const float* p) {
+    if (LD == 1) return *p;            // ld.global (L1-allocating)
+    if (LD == 2) return __ldcg(p);     // ld.global.cg (L2 only)
+    if (LD == 3) return __ldcs(p);     // ld.global.cs (streaming)
+    if (LD == 4) { float v; asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+    return __ldg(p);                   // ld.global.nc
+}
+
+template <int R, int QU, int LD>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const LookupParams p) {
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;        // window extent incl. the +-1 floor deviation of the round trip
     constexpr int WIN = W2 * W2;     // odd -> lane-per-query smem reads are conflict-free
     constexpr int NLOAD = (WIN + 31) / 32;
     static_assert(WIN % 2 == 1, "window stride must be odd");
+    static_assert(W2 <= 15, "row/column masks are 16 bits");
 
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     float* swin = smem + warp * (kTile * WIN);
 
-    // block -> (level, batch, 4 tiles); level-major so level 0 goes first
+    // block -> (level, batch, tiles); level-major so level 0 goes first
     int bid = blockIdx.x;
     const int per_level = p.B * p.blocks_per_batch;
     const int level = bid / per_level;
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
     const float* __restrict__ lvl = p.lvl[level];
     const float inv_scale = __int_as_float((127 - level) << 23);  // 2^-level, exact (corr.py:40)
 
-    // ---------------- phase A: per-query window origin ----------------
+    // ---------------- phase A: per-query window origin and in-bounds masks ----------------
     float cx = 0.f, cy = 0.f;
     if (valid) {
         const float* c = p.coords + (size_t)b * 2 * N + n;
@@ -97,62 +107,66 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
     const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
     const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
                       !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
-    int x_lo = 0, y_lo = 0, ncols = 0, nrows = 0;
+    const int map_elems = lh * lw;                // < 2^24 (checked on the host)
+    int x_lo = 0, y_lo = 0;
+    int my_mask = 0;                              // bits [0,16): valid window rows, [16,32): valid columns
+    int my_qoff = 0;                              // element offset of the window origin from the tile's first map
     if (valid && !wild) {
         x_lo = (int)floorf(ixf);
         y_lo = (int)floorf(iyf);
-        ncols = min((int)floorf(ixl) + 2 - x_lo, W2);
-        nrows = min((int)floorf(iyl) + 2 - y_lo, W2);
+        const int ncols = min((int)floorf(ixl) + 2 - x_lo, W2);
+        const int nrows = min((int)floorf(iyl) + 2 - y_lo, W2);
+        const int rlo = max(0, -y_lo), rhi = min(nrows, lh - y_lo);
+        const int clo = max(0, -x_lo), chi = min(ncols, lw - x_lo);
+        const int rm = (rhi > rlo) ? (((1 << rhi) - 1) & ~((1 << rlo) - 1)) : 0;
+        const int cm = (chi > clo) ? (((1 << chi) - 1) & ~((1 << clo) - 1)) : 0;
+        my_mask = (rm && cm) ? (rm | (cm << 16)) : 0;
+        my_qoff = lane * map_elems + y_lo * lw + x_lo;   // |.| < 2^31: 31*2^24 + 3e4*2^14
     }
-    const int pack_xy = (int)(((unsigned)x_lo & 0xFFFFu) | ((unsigned)y_lo << 16));
-    const int pack_rc = nrows | (ncols << 8);
+
+    const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
 
     // ---------------- phase B: cooperative gather into smem ----------------
-    int er[NLOAD], ec[NLOAD];
+    // element e = lane + 32 j of a window -> (row, col) = (e / W2, e % W2); its in-bounds test is
+    // one AND against the query's mask, its address one IMAD.WIDE from a per-lane base pointer.
+    const float* pj[NLOAD];
+    int bits[NLOAD];
 #pragma unroll
     for (int j = 0; j < NLOAD; ++j) {
         const int e = lane + 32 * j;
-        er[j] = e / W2;
-        ec[j] = e - er[j] * W2;
+        const int er = e / W2, ec = e - er * W2;
+        pj[j] = tile_base + (er * lw + ec);
+        bits[j] = (e < WIN) ? ((1 << er) | (1 << (16 + ec))) : 0x80008000;  // never matches
     }
-    const int64_t map_elems = (int64_t)lh * lw;
-    const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * map_elems;
-
-    // QU queries in flight per lane: QU * NLOAD independent loads
+    float* sdst = swin + lane;
 #pragma unroll 1
     for (int q0 = 0; q0 < kTile; q0 += QU) {
         float v[QU][NLOAD];
 #pragma unroll
         for (int u = 0; u < QU; ++u) {
-            const int q = q0 + u;
-            const int xy = __shfl_sync(0xffffffffu, pack_xy, q);
-            const int rc = __shfl_sync(0xffffffffu, pack_rc, q);
-            const int xl = (int)(short)(xy & 0xFFFF);
-            const int yl = xy >> 16;
-            const int nr = rc & 0xFF, nc = rc >> 8;
-            const float* __restrict__ base = tile_base + (int64_t)q * map_elems;
+            const int qoff = __shfl_sync(0xffffffffu, my_qoff, q0 + u);
+            const int msk = __shfl_sync(0xffffffffu, my_mask, q0 + u);
 #pragma unroll
             for (int j = 0; j < NLOAD; ++j) {
-                const int gy = yl + er[j], gx = xl + ec[j];
-                const bool ok = (er[j] < nr) && (ec[j] < nc) &&
-                                ((unsigned)gy < (unsigned)lh) && ((unsigned)gx < (unsigned)lw);
-                v[u][j] = ok ? __ldg(base + gy * lw + gx) : 0.0f;
+                const bool ok = (msk & bits[j]) == bits[j];
+                v[u][j] = ok ? gather_load<LD>(pj[j] + qoff) : 0.0f;
             }
         }
 #pragma unroll
         for (int u = 0; u < QU; ++u) {
 #pragma unroll
             for (int j = 0; j < NLOAD; ++j) {
-                const int e = lane + 32 * j;
-                if (e < WIN) swin[(q0 + u) * WIN + e] = v[u][j];
+                if (32 * j + 31 < WIN || lane + 32 * j < WIN) sdst[u * WIN + 32 * j] = v[u][j];
             }
         }
+        sdst += QU * WIN;
     }
     __syncwarp();
 
     // ---------------- phase C: lane-per-query evaluation ----------------
     int rx[K], ry[K];
     float wx0[K], wx1[K], wy0[K], wy1[K];
+    bool deviated = false;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
         const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
@@ -164,28 +178,61 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
         wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
         wy1[a] = wild ? 0.f : __fsub_rn(iy, fy);
         wy0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
-        rx[a] = wild ? 0 : min(max((int)fx - x_lo, 0), W2 - 2);
-        ry[a] = (wild ? 0 : min(max((int)fy - y_lo, 0), W2 - 2)) * W2;
+        rx[a] = wild ? a : min(max((int)fx - x_lo, 0), W2 - 2);
+        ry[a] = wild ? a : min(max((int)fy - y_lo, 0), W2 - 2);
+        deviated |= (rx[a] != a) | (ry[a] != a);
     }
+    if (!valid) deviated = false;  // padding lanes of the last tile must not force the slow path
 
     const float* sq = swin + lane * WIN;
     const int CT = p.num_levels * K * K;
     float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
+
+    if (!__any_sync(0xffffffffu, deviated)) {
+        // Fast path (no tap of any query in the warp changed its floor through the round trip):
+        // tap (a, b) sits at window (b, a), so every smem offset is a compile-time constant and the
+        // bilinear form factors into a horizontal pass shared by the two outputs that use a row.
+        // out = wy0*(wx0*v00 + wx1*v01) + wy1*(wx0*v10 + wx1*v11): same value as the reference's
+        // nw/ne/sw/se form up to fp32 rounding (~1e-7 relative).
+        float tprev[K];
 #pragma unroll
-    for (int a = 0; a < K; ++a) {
+        for (int r = 0; r <= K; ++r) {
+            float vrow[K + 1];
 #pragma unroll
-        for (int bb = 0; bb < K; ++bb) {
-            const float* s = sq + ry[bb] + rx[a];
-            const float v00 = s[0], v01 = s[1], v10 = s[W2], v11 = s[W2 + 1];
-            const float nw = __fmul_rn(wx0[a], wy0[bb]);
-            const float ne = __fmul_rn(wx1[a], wy0[bb]);
-            const float sw = __fmul_rn(wx0[a], wy1[bb]);
-            const float se = __fmul_rn(wx1[a], wy1[bb]);
-            float o = __fmul_rn(v00, nw);
-            o = __fmaf_rn(v01, ne, o);
-            o = __fmaf_rn(v10, sw, o);
-            o = __fmaf_rn(v11, se, o);
-            if (valid) op[(int64_t)(a * K + bb) * N] = o;
+            for (int c = 0; c <= K; ++c) vrow[c] = sq[r * W2 + c];
+            float tcur[K];
+#pragma unroll
+            for (int a = 0; a < K; ++a) tcur[a] = __fmaf_rn(wx1[a], vrow[a + 1], __fmul_rn(wx0[a], vrow[a]));
+            if (r > 0) {
+                const int bb = r - 1;
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    const float o = __fmaf_rn(wy1[bb], tcur[a], __fmul_rn(wy0[bb], tprev[a]));
+                    if (valid) op[(int64_t)(a * K + bb) * N] = o;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
+        }
+    } else {
+        // Exact general path (integer / near-integer coordinates, e.g. the first iteration): per-tap
+        // window indices, corners weighted and accumulated in ATen's order nw, ne, sw, se.
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+#pragma unroll
+            for (int bb = 0; bb < K; ++bb) {
+                const float* s = sq + ry[bb] * W2 + rx[a];
+                const float v00 = s[0], v01 = s[1], v10 = s[W2], v11 = s[W2 + 1];
+                const float nw = __fmul_rn(wx0[a], wy0[bb]);
+                const float ne = __fmul_rn(wx1[a], wy0[bb]);
+                const float sw = __fmul_rn(wx0[a], wy1[bb]);
+                const float se = __fmul_rn(wx1[a], wy1[bb]);
+                float o = __fmul_rn(v00, nw);
+                o = __fmaf_rn(v01, ne, o);
+                o = __fmaf_rn(v10, sw, o);
+                o = __fmaf_rn(v11, se, o);
+                if (valid) op[(int64_t)(a * K + bb) * N] = o;
+            }
         }
     }
 }
@@ -239,7 +286,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_kernel(const LookupBwdParams p
     }
 }
 
-template <int R, int QU>
+template <int R, int QU, int LD = 0>
 int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
     constexpr int WIN = (K + 2) * (K + 2);
@@ -248,12 +295,12 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     int dev = 0;
     FFCORR_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_dev = dev;
     }
     const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup: grid too large (%lld blocks)", (long long)blocks);
-    lookup_kernel<R, QU><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    lookup_kernel<R, QU, LD><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
     return check_launch("lookup_kernel");
 }
 
@@ -285,12 +332,19 @@ extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const 
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
-    static const int qu = [] { const char* e = getenv("FFCORR_LOOKUP_QU"); return e ? atoi(e) : 4; }();
+    static const int qu = [] { const char* e = getenv("FFCORR_LOOKUP_QU"); return e ? atoi(e) : 8; }();
     switch (radius) {
         case 1: return launch_lookup<1, 4>(p, s);
         case 2: return launch_lookup<2, 4>(p, s);
         case 3: return launch_lookup<3, 4>(p, s);
-        default: return qu == 8 ? launch_lookup<4, 8>(p, s) : (qu == 2 ? launch_lookup<4, 2>(p, s) : launch_lookup<4, 4>(p, s));
+        default: {
+            static const int ld = [] { const char* e = getenv("FFCORR_LOOKUP_LD"); return e ? atoi(e) : 0; }();
+            if (ld == 1) return launch_lookup<4, 8, 1>(p, s);
+            if (ld == 2) return launch_lookup<4, 8, 2>(p, s);
+            if (ld == 3) return launch_lookup<4, 8, 3>(p, s);
+            if (ld == 4) return launch_lookup<4, 8, 4>(p, s);
+            return qu == 4 ? launch_lookup<4, 4>(p, s) : (qu == 2 ? launch_lookup<4, 2>(p, s) : launch_lookup<4, 8>(p, s));
+        }
     }
 }
 
