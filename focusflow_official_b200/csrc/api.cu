@@ -1,6 +1,8 @@
 // libffcorr: error buffer, version and device info.
 #include <stdarg.h>
 
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 
 namespace ffcorr {
@@ -27,6 +29,39 @@ int sm_count() {
         cached_sms = n;
     }
     return cached_sms;
+}
+
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle, const char* what) {
+    PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
+    FFCORR_REQUIRE(fn != nullptr, FFCORR_EDEVICE, "cuTensorMapEncodeTiled is not available from the driver");
+    FFCORR_REQUIRE(rank >= 1 && rank <= 5, FFCORR_EINVAL, "tensor map rank %d", rank);
+    cuuint64_t d[5], st[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i + 1 < rank) st[i] = strides_bytes[i];
+    }
+    CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FFCORR_REQUIRE(r == CUDA_SUCCESS, FFCORR_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return FFCORR_OK;
 }
 
 int check_levels(int num_levels, int h, int w, const char* who) {

@@ -1,6 +1,7 @@
 // Shared helpers for libffcorr (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -44,6 +45,11 @@ int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 // shared argument validation for the pyramid-shaped entry points (api.cu)
 int check_levels(int num_levels, int h, int w, const char* who);
+
+// cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no libcuda link); rank <= 5, no interleave,
+// zero OOB fill.  dims/box are innermost-first, strides_bytes has rank-1 entries (dims 1..rank-1).
+int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle, const char* what);
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

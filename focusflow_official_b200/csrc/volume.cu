@@ -17,10 +17,8 @@
 //   2*128*256*D flop (AI ~ 120 flop/B at D=256 < B200 ridge ~215), so the design spends shared
 //   memory on store buffering rather than on a deep operand pipeline.
 // Exact path: FFCORR_PREC_FP32, a CUDA-core SGEMM (also serves the two backward GEMMs).
-#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
-#include <cudaTypedefs.h>
 
 #include "common.cuh"
 
@@ -176,9 +174,11 @@ template <bool TF32, bool TMA_STORE, bool DIV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p, const uint32_t idesc) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // Index the extern array directly: rounding the pointer up through uintptr_t loses the shared
+    // address space (generic ST.E instead of STS in the epilogue).  128B-swizzle needs 1024-byte alignment.
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
+    if (smem_base & 1023u) __trap();
     const uint32_t bar_base = smem_base + SMEM_OFF_BAR;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -491,33 +491,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled get_encode_fn() {
-    static PFN_cuTensorMapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-    }
-    return fn;
-}
-
 int encode_3d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
               uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, const char* what) {
-    PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
-    FFCORR_REQUIRE(fn != nullptr, FFCORR_EDEVICE, "cuTensorMapEncodeTiled is not available from the driver");
     (void)elem_bytes;
-    cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-    cuuint32_t box[3] = {b0, b1, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FFCORR_REQUIRE(r == CUDA_SUCCESS, FFCORR_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
-    return FFCORR_OK;
+    const uint64_t dims[3] = {d0, d1, d2};
+    const uint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    const uint32_t box[3] = {b0, b1, 1};
+    return encode_tensor_map(m, dt, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
 }
 
 struct PrecInfo {
