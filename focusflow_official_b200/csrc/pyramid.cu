@@ -23,6 +23,8 @@ struct PyrParams {
     int h[kFusedLevels], w[kFusedLevels];
     int n[kFusedLevels];        // elements per map per level
     int num_levels;             // 2..4
+    unsigned magic_w[kFusedLevels];  // ceil(2^32 / w[l])      -> row = umulhi(i, magic)
+    unsigned magic_p[kFusedLevels];  // ceil(2^32 / ((w[l]+1)/2))
     int G;                      // maps per block
     int64_t Q;
 };
@@ -31,9 +33,77 @@ __device__ __forceinline__ float pool4(const float* s, int w) {
     return (((s[0] + s[1]) + s[w]) + s[w + 1]) * 0.25f;
 }
 
+// round a float offset up to 16 bytes (level buffers in shared memory start 16-byte aligned)
+__host__ __device__ __forceinline__ int align4(int x) { return (x + 3) & ~3; }
+
+// One pooling level for a group of g maps held in shared memory.  Work items are flattened over
+// (row, x) so all 256 threads stay busy; the row index comes from a multiply-high by a host-computed
+// reciprocal (no integer division).  When the input width is even a thread fetches the two input rows of
+// TWO adjacent outputs with two LDS.128, halving the instruction count per output.
+__device__ __forceinline__ void pool_level(const PyrParams& p, int l, int g, const float* __restrict__ sin,
+                                           float* __restrict__ sout, float* __restrict__ dst, bool keep, int tid) {
+    const int wi = p.w[l - 1], ni = p.n[l - 1];
+    const int ho = p.h[l], wo = p.w[l], no = p.n[l];
+    // 16-byte loads need BOTH input rows 16-byte aligned: wi % 4 == 0 (row 2y+1 starts at (2y+1)*wi)
+    const bool vec = ((wi & 3) == 0) && ((((uintptr_t)sin) & 15) == 0) && (g == 1 || (ni & 3) == 0);
+    const bool vec2 = ((wi & 1) == 0) && ((((uintptr_t)sin) & 7) == 0) && (g == 1 || (ni & 1) == 0);
+    if (vec) {
+        const int P = (wo + 1) >> 1;
+        const int items = ho * P;
+        const bool st2 = ((wo & 1) == 0) && ((no & 1) == 0) && ((((uintptr_t)dst) & 7) == 0) && ((((uintptr_t)sout) & 7) == 0);
+        for (int m = 0; m < g; ++m) {
+            const float* s0 = sin + m * ni;
+            float* so = sout + m * no;
+            float* go = dst + (size_t)m * no;
+            for (int i = tid; i < items; i += kPyrThreads) {
+                const int y = (P == 1) ? i : (int)__umulhi((unsigned)i, p.magic_p[l]);
+                const int xp = i - y * P;
+                const float4 a = *reinterpret_cast<const float4*>(s0 + (2 * y) * wi + 4 * xp);
+                const float4 b = *reinterpret_cast<const float4*>(s0 + (2 * y + 1) * wi + 4 * xp);
+                const float v0 = (((a.x + a.y) + b.x) + b.y) * 0.25f;
+                const float v1 = (((a.z + a.w) + b.z) + b.w) * 0.25f;
+                const int o = y * wo + 2 * xp;
+                if (st2) {
+                    if (keep) *reinterpret_cast<float2*>(so + o) = make_float2(v0, v1);
+                    __stcs(reinterpret_cast<float2*>(go + o), make_float2(v0, v1));
+                } else {
+                    const bool has1 = 2 * xp + 1 < wo;
+                    if (keep) {
+                        so[o] = v0;
+                        if (has1) so[o + 1] = v1;
+                    }
+                    __stcs(go + o, v0);
+                    if (has1) __stcs(go + o + 1, v1);
+                }
+            }
+        }
+    } else {
+        const int items = ho * wo;
+        for (int m = 0; m < g; ++m) {
+            const float* s0 = sin + m * ni;
+            float* so = sout + m * no;
+            float* go = dst + (size_t)m * no;
+            for (int i = tid; i < items; i += kPyrThreads) {
+                const int y = (wo == 1) ? i : (int)__umulhi((unsigned)i, p.magic_w[l]);
+                const int x = i - y * wo;
+                float v;
+                if (vec2) {  // even width: each input row of the 2x2 window is one aligned LDS.64
+                    const float2 a = *reinterpret_cast<const float2*>(s0 + (2 * y) * wi + 2 * x);
+                    const float2 b = *reinterpret_cast<const float2*>(s0 + (2 * y + 1) * wi + 2 * x);
+                    v = (((a.x + a.y) + b.x) + b.y) * 0.25f;
+                } else {
+                    v = pool4(s0 + (2 * y) * wi + 2 * x, wi);
+                }
+                if (keep) so[i] = v;
+                __stcs(go + i, v);
+            }
+        }
+    }
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(kPyrThreads) pyramid_fused_kernel(const PyrParams p) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const int64_t q0 = (int64_t)blockIdx.x * p.G;
     const int g = (int)min((int64_t)p.G, p.Q - q0);
     const int tid = threadIdx.x;
@@ -80,45 +150,92 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_fused_kernel(const PyrPar
     }
     __syncthreads();
 
-    // ---- levels 1.. from shared memory: a warp per output row, lanes along x ----
-    // (one integer division per ROW, not per element; 8-byte smem reads when the input
-    //  width is even so a lane fetches its 2x2 window with two LDS.64)
-    const int warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = kPyrThreads / 32;
-    float* sin = sm;
-    float* sout = sm + (size_t)p.G * p.n[0];
+    // ---- levels 1.. from shared memory ----
+    const float* sin = sm;
+    int off = align4(p.G * p.n[0]);
 #pragma unroll 1
     for (int l = 1; l < p.num_levels; ++l) {
-        const int wi = p.w[l - 1], ni = p.n[l - 1];
-        const int ho = p.h[l], wo = p.w[l], no = p.n[l];
-        float* __restrict__ dst = p.out[l] + q0 * no;
-        const int rows = g * ho;
-        const bool even = ((wi & 1) == 0) && (((sin - sm) & 1) == 0);
-        for (int row = warp; row < rows; row += NW) {
-            const int m = row / ho;
-            const int y = row - m * ho;
-            const float* r0 = sin + m * ni + (2 * y) * wi;
-            const int o = m * no + y * wo;
-            if (even) {
-                const float2* a2 = reinterpret_cast<const float2*>(r0);
-                const float2* b2 = reinterpret_cast<const float2*>(r0 + wi);
-                for (int x = lane; x < wo; x += 32) {
-                    const float2 a = a2[x], bb = b2[x];
-                    const float v = (((a.x + a.y) + bb.x) + bb.y) * 0.25f;
-                    sout[o + x] = v;
-                    dst[o + x] = v;
-                }
-            } else {
-                for (int x = lane; x < wo; x += 32) {
-                    const float v = pool4(r0 + 2 * x, wi);
-                    sout[o + x] = v;
-                    dst[o + x] = v;
-                }
-            }
-        }
+        float* sout = sm + off;
+        pool_level(p, l, g, sin, sout, p.out[l] + q0 * p.n[l], l < p.num_levels - 1, tid);
         __syncthreads();
         sin = sout;
-        sout = sout + (size_t)p.G * no;
+        off = align4(off + p.G * p.n[l]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent, bulk-copy fed variant (group bytes % 16 == 0, 16-byte aligned base): level 0 of each
+// group arrives through cp.async.bulk into a 3-stage mbarrier ring, so every block always has
+// (stages-1) groups in flight while it pools the current one; no thread spends instructions or
+// registers on the 1.7 GB level-0 read.
+// ------------------------------------------------------------------------------------------
+constexpr int kPyrStages = 3;
+
+__device__ __forceinline__ void py_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void py_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void py_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void py_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kPyrThreads) pyramid_bulk_kernel(const PyrParams p, const int64_t num_groups) {
+    extern __shared__ __align__(128) float sm[];
+    const int tid = threadIdx.x;
+    const int stage_floats = p.G * p.n[0];                       // multiple of 4 (host guarantees)
+    const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
+    float* scratch = sm + (size_t)kPyrStages * stage_floats;     // levels 1..L-2 of the current group
+    const uint32_t sm_u32 = (uint32_t)__cvta_generic_to_shared(sm);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(scratch + align4(align4(p.G * p.n[1]) + p.G * p.n[2]) + 4) & ~7u;
+
+    if (tid == 0) {
+        for (int s = 0; s < kPyrStages; ++s) py_mbar_init(bar0 + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t grp, int k) {  // thread 0 only; groups are always full here
+        const uint32_t bar = bar0 + 8u * (k % kPyrStages);
+        py_mbar_expect_tx(bar, stage_bytes);
+        py_bulk_load(sm_u32 + (uint32_t)(k % kPyrStages) * stage_bytes, p.l0 + grp * stage_floats, stage_bytes, bar);
+    };
+    if (tid == 0) {
+        int k = 0;
+        for (int64_t grp = blockIdx.x; grp < num_groups && k < kPyrStages; grp += gridDim.x, ++k) issue(grp, k);
+    }
+
+    int k = 0;
+    for (int64_t grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++k) {
+        py_mbar_wait(bar0 + 8u * (k % kPyrStages), (uint32_t)((k / kPyrStages) & 1));
+        const int64_t q0 = grp * p.G;
+        const float* sin = sm + (size_t)(k % kPyrStages) * stage_floats;
+        int off = 0;
+#pragma unroll 1
+        for (int l = 1; l < p.num_levels; ++l) {
+            float* sout = scratch + off;
+            pool_level(p, l, p.G, sin, sout, p.out[l] + q0 * p.n[l], l < p.num_levels - 1, tid);
+            __syncthreads();
+            sin = sout;
+            off = align4(off + p.G * p.n[l]);
+        }
+        // the stage (and the scratch) are free again: refill the stage with the group kPyrStages ahead
+        if (tid == 0) {
+            const int64_t nxt = grp + (int64_t)kPyrStages * gridDim.x;
+            if (nxt < num_groups) issue(nxt, k + kPyrStages);
+        }
     }
 }
 
@@ -184,7 +301,10 @@ extern "C" int ffcorr_pyramid_f32(float* const* lvl, int num_levels, int64_t Q, 
         p.w[i] = w >> i;
         p.n[i] = p.h[i] * p.w[i];
         p.out[i] = lvl[i];
-        per_map += p.n[i];
+        per_map += p.n[i] + 4;   // + alignment slack per level buffer
+        p.magic_w[i] = (unsigned)((0x100000000ull + p.w[i] - 1) / (unsigned)p.w[i]);
+        const unsigned pr = (unsigned)((p.w[i] + 1) / 2);
+        p.magic_p[i] = (unsigned)((0x100000000ull + pr - 1) / pr);
     }
     // maps per block: 16-byte aligned groups, ~8K level-0 elements per block, <= 96 KB smem
     const int n0 = p.n[0];
@@ -202,7 +322,30 @@ extern "C" int ffcorr_pyramid_f32(float* const* lvl, int num_levels, int64_t Q, 
         smem = (size_t)G * per_map * sizeof(float);
     }
     int done_levels = 1;
-    if (smem <= 200 * 1024) {
+    const size_t bulk_smem = ((size_t)kPyrStages * G * n0 + (size_t)G * (p.n[1] + p.n[2]) + 32) * sizeof(float) + 64;
+    const int64_t full_groups = Q / G;
+    if (vec4 && fused >= 2 && bulk_smem <= 110 * 1024 && full_groups >= 1 && (uint64_t)G * n0 * 4 < (1u << 20)) {
+        // persistent bulk-copy pipeline over the full groups, 2 blocks per SM
+        p.G = G;
+        const int64_t want = 2ll * sm_count();
+        const int grid = (int)(full_groups < want ? full_groups : want);
+        FFCORR_CUDA(cudaFuncSetAttribute(pyramid_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+        pyramid_bulk_kernel<<<grid, kPyrThreads, bulk_smem, s>>>(p, full_groups);
+        if (int rc = check_launch("pyramid_bulk_kernel")) return rc;
+        const int64_t rest = Q - full_groups * G;
+        if (rest > 0) {  // tail maps (fewer than G): the block-per-group kernel, scalar loads
+            PyrParams t = p;
+            t.l0 = p.l0 + full_groups * G * (int64_t)n0;
+            for (int i = 1; i < fused; ++i) t.out[i] = p.out[i] + full_groups * G * (int64_t)p.n[i];
+            t.Q = rest;
+            t.G = (int)rest;
+            const size_t tsm = (size_t)rest * per_map * sizeof(float);
+            FFCORR_CUDA(cudaFuncSetAttribute(pyramid_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+            pyramid_fused_kernel<false><<<1, kPyrThreads, tsm, s>>>(t);
+            if (int rc = check_launch("pyramid_fused_kernel(tail)")) return rc;
+        }
+        done_levels = fused;
+    } else if (smem <= 200 * 1024) {
         p.G = G;
         const int64_t blocks = ceil_div64(Q, G);
         FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "pyramid: grid too large");
