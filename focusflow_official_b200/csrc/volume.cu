@@ -19,6 +19,7 @@
 // Exact path: FFCORR_PREC_FP32, a CUDA-core SGEMM (also serves the two backward GEMMs).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -123,6 +124,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// 64 consecutive fp32 columns (two x32 loads back to back; both stay in flight until wait::ld)
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&r)[64]) {
+    uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+    uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
+    tmem_ld_32x32(taddr, lo);
+    tmem_ld_32x32(taddr + 32u, hi);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
@@ -135,7 +143,7 @@ constexpr int UMMA_K_BYTES = 32;     // K extent of one tcgen05.mma: 16 x 16-bit
 constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr int STORE_COLS = 32;       // fp32 columns per store box (128 B rows)
-constexpr int STORE_BUFS = 4;        // per epilogue warp
+constexpr int STORE_BUFS = 4;        // per epilogue warp: 2 pairs = 2 TMA-store groups in flight
 constexpr int EPI_WARPS = 4;
 constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 
@@ -148,6 +156,8 @@ constexpr int SMEM_OFF_B = SMEM_OFF_A + STAGES * SMEM_A_STAGE;
 constexpr int SMEM_OFF_BAR = SMEM_OFF_B + STAGES * SMEM_B_STAGE;
 constexpr int SMEM_GEMM_TOTAL = SMEM_OFF_BAR + 128 + 1024;  // + barriers + alignment slack
 static_assert(SMEM_GEMM_TOTAL <= 227 * 1024, "shared memory budget");
+static_assert(BN == 256 && STORE_COLS == 32 && STORE_BUFS % 2 == 0, "the epilogue is written for 4 x 64-column chunks");
+constexpr int STORE_PAIRS = STORE_BUFS / 2;
 
 // K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -268,7 +278,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int ew = warp - 2;                      // private store ring
         uint8_t* my_bufs = smem + (size_t)ew * STORE_BUFS * SMEM_STORE_BUF;
         const uint32_t my_bufs_u32 = smem_base + (uint32_t)(ew * STORE_BUFS * SMEM_STORE_BUF);
-        int buf = 0;
+        int pair = 0;   // store ring: 2 pairs of 32x32 boxes per warp
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int b = t / tiles_per_batch;
@@ -281,52 +291,66 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             const int row0 = m0 + quarter * 32;
-#pragma unroll 1
-            for (int c = 0; c < BN / STORE_COLS; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + (uint32_t)(c * STORE_COLS), v);
-                tmem_ld_wait();
-                if (c == BN / STORE_COLS - 1) {
-                    // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
-                }
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float a = __uint_as_float(v[i]);
-                    f[i] = DIV ? __fdiv_rn(a, p.divisor) : a * p.scale;  // compile-time: keeps the loop body in the I-cache
-                }
-                const int col0 = n0 + c * STORE_COLS;
+            // 4 chunks of 64 columns, software pipelined: the TMEM load of chunk c+1 is in flight while
+            // chunk c is scaled, staged (two 128B-swizzled 32x32 boxes, ONE proxy fence) and handed to TMA.
+            auto process = [&](uint32_t (&v)[64], int c) {
+                const int col0 = n0 + c * 64;
                 if (TMA_STORE) {
-                    if (row0 < p.N && col0 < p.N) {  // warp-uniform: box entirely outside -> skip
-                        if (lane == 0) tma_store_wait_read<STORE_BUFS - 1>();
-                        __syncwarp();
-                        uint8_t* dst = my_bufs + (size_t)buf * SMEM_STORE_BUF + lane * 128;
+                    if (row0 >= p.N || col0 >= p.N) return;   // warp-uniform: both boxes outside
+                    if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();   // the pair used STORE_PAIRS groups ago has been read
+                    __syncwarp();
+                    uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            float4 q = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                            *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = q;  // 128B swizzle
+                            float4 q;
+                            const int i0 = hlf * 32 + 4 * j;
+                            q.x = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 0]), p.divisor) : __uint_as_float(v[i0 + 0]) * p.scale;
+                            q.y = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 1]), p.divisor) : __uint_as_float(v[i0 + 1]) * p.scale;
+                            q.z = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 2]), p.divisor) : __uint_as_float(v[i0 + 2]) * p.scale;
+                            q.w = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 3]), p.divisor) : __uint_as_float(v[i0 + 3]) * p.scale;
+                            *reinterpret_cast<float4*>(dst + hlf * SMEM_STORE_BUF + ((j ^ (lane & 7)) << 4)) = q;  // 128B swizzle
                         }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_3d(&tmap_c, my_bufs_u32 + (uint32_t)(buf * SMEM_STORE_BUF), col0, row0, b);
-                            tma_store_commit();
-                        }
-                        buf = (buf + 1) % STORE_BUFS;
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
+                        tma_store_3d(&tmap_c, src, col0, row0, b);
+                        if (col0 + 32 < p.N) tma_store_3d(&tmap_c, src + SMEM_STORE_BUF, col0 + 32, row0, b);
+                        tma_store_commit();
+                    }
+                    pair = (pair + 1) % STORE_PAIRS;
                 } else {
                     const int row = row0 + lane;
                     if (row < p.N) {
                         float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.N + col0;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.N) o[i] = f[i];
+                        for (int i = 0; i < 64; ++i) {
+                            const float a = __uint_as_float(v[i]);
+                            if (col0 + i < p.N) o[i] = DIV ? __fdiv_rn(a, p.divisor) : a * p.scale;
+                        }
                     }
                 }
-            }
+            };
+            uint32_t va[64], vb[64];
+            tmem_ld_32x64(t_row, va);
+            tmem_ld_wait();
+            tmem_ld_32x64(t_row + 64u, vb);
+            process(va, 0);
+            tmem_ld_wait();
+            tmem_ld_32x64(t_row + 128u, va);
+            process(vb, 1);
+            tmem_ld_wait();
+            tmem_ld_32x64(t_row + 192u, vb);
+            process(va, 2);
+            tmem_ld_wait();
+            // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            process(vb, 3);
         }
         if (TMA_STORE && lane == 0) tma_store_wait_all();
     }

@@ -60,7 +60,8 @@ def time_cuda(fn, iters=10, warmup=3, flush=None):
 
 
 def raft_shapes(config):
-    return {1: (1, 256, 46, 62), 2: (8, 256, 47, 156), 4: (8, 256, 55, 128), 5: (8, 256, 46, 62)}[config]
+    return {1: (1, 256, 46, 62), 2: (8, 256, 47, 156), 4: (8, 256, 55, 128), 5: (8, 256, 46, 62),
+            6: (8, 256, 56, 128), 7: (8, 256, 48, 160)}[config]  # 6/7: tile-aligned shapes (diagnosis)
 
 
 def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, verbose=False, warmup=3):
