@@ -196,12 +196,14 @@ class LaunchMeter:
         self.lookup_events = []
         self.build_events = []
         self.enabled = False
+        self.tiled = False
 
     def install(self):
         from focusflow_official_b200 import corr as C
 
         meter = self
         raw_lookup, raw_build = C._lookup_raw, C._volume_pyramid_raw
+        raw_lookup_t, raw_build_t = C._lookup_tiled_raw, C._volume_pyramid_tiled_raw
 
         def lookup(levels, ptrs, coords, radius):
             if not meter.enabled:
@@ -225,7 +227,31 @@ class LaunchMeter:
             meter.launches += 3 if prec != 1 else 2  # operand pre-pass + GEMM + pyramid
             return out
 
+        def lookup_t(levels, ptrs, coords, radius):
+            if not meter.enabled:
+                return raw_lookup_t(levels, ptrs, coords, radius)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = raw_lookup_t(levels, ptrs, coords, radius)
+            e1.record()
+            meter.lookup_events.append((e0, e1))
+            meter.launches += 1
+            meter.tiled = True
+            return out
+
+        def build_t(f1, f2, nl, prec):
+            if not meter.enabled:
+                return raw_build_t(f1, f2, nl, prec)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = raw_build_t(f1, f2, nl, prec)
+            e1.record()
+            meter.build_events.append((e0, e1))
+            meter.launches += 3  # operand pre-pass + GEMM + pyramid
+            return out
+
         C._lookup_raw, C._volume_pyramid_raw = lookup, build
+        C._lookup_tiled_raw, C._volume_pyramid_tiled_raw = lookup_t, build_t
 
     def mean_ms(self, events):
         if not events:
@@ -334,7 +360,7 @@ def run_gpu_arm(args, rank, world, local):
         "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"FocusRAFT inference batch {b}/GPU, KITTI shape {H}x{W}, {ITERS} iters, B200",
-                   "batch_per_gpu": b, "iters": ITERS, "corr_precision": "fp16 operands, fp32 accumulate",
+                   "batch_per_gpu": b, "iters": ITERS, "corr_precision": "fp16 operands, fp32 accumulate", "pyramid_layout": "tiled 4x4" if meter.tiled else "row-major",
                    "host_convs": "PyTorch/cuDNN TF32 (reference ALLOW_TF32)", "channels_last": bool(args.channels_last),
                    "l2": "per-step working set (2.3 GB pyramid + activations) >> 126 MB L2, no flush needed",
                    "sharding": "by image pair, no data-path collective"},
@@ -342,7 +368,8 @@ def run_gpu_arm(args, rank, world, local):
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "lookup_kernel<4> (ffcorr_lookup_f32)", "bound": "hbm",
+        "roofline": {"kernel": "lookup_tiled_kernel<4> (ffcorr_lookup_tiled_f32)" if meter.tiled else "lookup_kernel<4> (ffcorr_lookup_f32)",
+                     "bound": "hbm",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(achieved / peaks["hbm_gbs"], 4) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,

@@ -34,6 +34,13 @@ _PROTOS = {
     "ffcorr_volume_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_pyramid_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_lookup_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_tiled_map_elems": (ctypes.c_int64, [_i, _i, _i]),
+    "ffcorr_tiled_supported": (_i, [_i, _i, _i]),
+    "ffcorr_volume_tiled_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "ffcorr_pyramid_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
+    "ffcorr_lookup_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_untile_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
+    "ffcorr_tile_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_lookup_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ffcorr_pyramid_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_volume_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

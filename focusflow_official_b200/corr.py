@@ -22,9 +22,15 @@ import torch
 
 from . import _lib
 
-__all__ = ["CorrBlock", "coords_grid", "correlation_volume", "correlation_pyramid", "lookup"]
+import os
+
+__all__ = ["CorrBlock", "coords_grid", "correlation_volume", "correlation_pyramid", "lookup",
+           "tiled_pyramid", "lookup_tiled", "tile_levels", "untile_levels"]
 
 DEFAULT_PRECISION = "fp16"
+# storage of the pyramid inside CorrBlock when no gradient is needed: "tiled" (4x4-pixel tiles, the fast
+# path) or "rowmajor" (the reference layout; always used under autograd and for precision="fp32")
+DEFAULT_LAYOUT = os.environ.get("FFCORR_LAYOUT", "tiled")
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -61,6 +67,76 @@ def _volume_pyramid_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: in
     _lib.check(L.ffcorr_pyramid_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream), "ffcorr_pyramid_f32")
     # `ws` may be freed here: the caching allocator is stream-ordered on the current stream.
     return levels
+
+
+def _tiled_elems(h: int, w: int, level: int) -> int:
+    return int(_lib.lib().ffcorr_tiled_map_elems(h, w, level))
+
+
+def tiled_supported(h: int, w: int, num_levels: int) -> bool:
+    return bool(_lib.lib().ffcorr_tiled_supported(num_levels, h, w))
+
+
+def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, precision: int) -> List[torch.Tensor]:
+    """Volume + pyramid in the tiled layout: level i is [B*h*w, tiled_map_elems(h, w, i)]."""
+    b, d, h, w = fmap1.shape
+    L = _lib.lib()
+    levels = [torch.empty((b * h * w, _tiled_elems(h, w, i)), device=fmap1.device, dtype=torch.float32)
+              for i in range(num_levels)]
+    ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
+    ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
+    stream = _lib.current_stream()
+    _lib.check(L.ffcorr_volume_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), levels[0].data_ptr(), b, d, h, w, precision,
+                                         ws.data_ptr(), ws_bytes, stream), "ffcorr_volume_tiled_f32")
+    _lib.check(L.ffcorr_pyramid_tiled_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream),
+               "ffcorr_pyramid_tiled_f32")
+    return levels
+
+
+def _lookup_tiled_raw(levels, level_ptrs, coords: torch.Tensor, radius: int) -> torch.Tensor:
+    b, _, h, w = coords.shape
+    k = 2 * radius + 1
+    out = torch.empty((b, len(levels) * k * k, h, w), device=coords.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ffcorr_lookup_tiled_f32(level_ptrs, len(levels), coords.data_ptr(), out.data_ptr(), b, h, w, radius,
+                                                  _lib.current_stream()), "ffcorr_lookup_tiled_f32")
+    return out
+
+
+def untile_levels(tiled_levels, b: int, h: int, w: int) -> List[torch.Tensor]:
+    """Tiled levels -> the reference's [B*h*w, 1, h>>i, w>>i] tensors."""
+    out = []
+    for i, t in enumerate(tiled_levels):
+        hi, wi = h >> i, w >> i
+        dst = torch.empty((b * h * w, 1, hi, wi), device=t.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ffcorr_untile_f32(t.data_ptr(), dst.data_ptr(), b * h * w, hi, wi, _lib.current_stream()),
+                   "ffcorr_untile_f32")
+        out.append(dst)
+    return out
+
+
+def tile_levels(levels) -> List[torch.Tensor]:
+    """Reference-layout levels ([Q, 1, h_i, w_i]) -> tiled storage (used by tests and tools)."""
+    out = []
+    for lv in levels:
+        _require_cuda(lv, "level")
+        lv = lv.float().contiguous()
+        q, _, hi, wi = lv.shape
+        dst = torch.empty((q, _tiled_elems(hi, wi, 0)), device=lv.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ffcorr_tile_f32(lv.data_ptr(), dst.data_ptr(), q, hi, wi, _lib.current_stream()), "ffcorr_tile_f32")
+        out.append(dst)
+    return out
+
+
+def tiled_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None) -> List[torch.Tensor]:
+    """Volume + pyramid in the tiled layout (inference only)."""
+    fmap1, fmap2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
+    return _volume_pyramid_tiled_raw(fmap1, fmap2, num_levels, _precision_code(precision))
+
+
+def lookup_tiled(tiled_levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None) -> torch.Tensor:
+    _require_cuda(coords, "coords")
+    coords = coords.float().contiguous()
+    return _lookup_tiled_raw(tiled_levels, level_ptrs if level_ptrs is not None else _lib.ptr_array(tiled_levels), coords, radius)
 
 
 def _lookup_raw(levels, level_ptrs, coords: torch.Tensor, radius: int) -> torch.Tensor:
@@ -171,18 +247,48 @@ def lookup(levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None) -> to
 
 
 class CorrBlock:
-    def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4, precision: Optional[str] = None):
+    def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4, precision: Optional[str] = None,
+                 layout: Optional[str] = None):
         self.num_levels = num_levels
         self.radius = radius
-        self.corr_pyramid = correlation_pyramid(fmap1, fmap2, num_levels, precision)
-        self._ptrs = _lib.ptr_array(self.corr_pyramid)
-        self._shape = (fmap1.shape[0], fmap1.shape[2], fmap1.shape[3])
+        b, _, h, w = fmap1.shape
+        self._shape = (b, h, w)
+        layout = layout or DEFAULT_LAYOUT
+        if layout not in ("tiled", "rowmajor"):
+            raise ValueError(f"layout must be 'tiled' or 'rowmajor', got {layout!r}")
+        needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
+        code = _precision_code(precision)
+        if (h >> (num_levels - 1)) < 1 or (w >> (num_levels - 1)) < 1:
+            raise ValueError(f"{h}x{w} feature map is too small for {num_levels} pyramid levels")
+        self._tiled = (layout == "tiled" and not needs_grad and code != _lib.PREC_FP32 and b > 0
+                       and fmap1.is_cuda and tiled_supported(h, w, num_levels))
+        if self._tiled:
+            f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
+            if f1.shape != f2.shape:
+                raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
+            self._levels = _volume_pyramid_tiled_raw(f1, f2, num_levels, code)
+            self._rowmajor = None                      # materialised on first access of .corr_pyramid
+        else:
+            self._levels = correlation_pyramid(fmap1, fmap2, num_levels, precision)
+            self._rowmajor = self._levels
+        self._ptrs = _lib.ptr_array(self._levels)
+
+    @property
+    def corr_pyramid(self) -> List[torch.Tensor]:
+        """The reference's ``[B*h*w, 1, h>>i, w>>i]`` list (``corr.py:16,23-27``); converted lazily when the
+        block stores its pyramid in the tiled layout."""
+        if self._rowmajor is None:
+            b, h, w = self._shape
+            self._rowmajor = untile_levels(self._levels, b, h, w)
+        return self._rowmajor
 
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
         b, two, h, w = coords.shape
         if (b, h, w) != self._shape or two != 2:
             raise ValueError(f"coords {tuple(coords.shape)} does not match the volume built for B,h,w={self._shape}")
-        return lookup(self.corr_pyramid, coords, self.radius, self._ptrs)
+        if self._tiled:
+            return lookup_tiled(self._levels, coords, self.radius, self._ptrs)
+        return lookup(self._levels, coords, self.radius, self._ptrs)
 
     @staticmethod
     def corr(fmap1, fmap2, precision: Optional[str] = None):

@@ -238,6 +238,239 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
 }
 
 // ---------------------------------------------------------------------------------
+// Tiled ("T4") pyramid variant.  Levels are stored per query map as 4x4-pixel tiles of 64 contiguous
+// bytes with exact-zero padding (pyramid.cu), so zero padding of the sampler needs no per-element bounds
+// test -- only "does this tile exist" -- and a window costs ~10.6 64-byte requests instead of ~17.
+// Phases A and C are those of lookup_kernel; phase B gathers 16 tiles x 4 rows = 64 float4 slots per
+// window (2 per lane) and scatters each into the dense 11x11 smem window.
+// ---------------------------------------------------------------------------------
+struct LookupTiledParams {
+    const float* lvl[FFCORR_MAX_LEVELS];
+    int lh[FFCORR_MAX_LEVELS], lw[FFCORR_MAX_LEVELS];     // true level sizes (for the coordinate round trip)
+    int th[FFCORR_MAX_LEVELS], tw[FFCORR_MAX_LEVELS];     // tiles per column / row
+    const float* coords;
+    float* out;
+    int B, N, num_levels;
+    int tiles_per_batch;
+    int blocks_per_batch;
+};
+
+template <int R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_tiled_kernel(const LookupTiledParams p) {
+    constexpr int K = 2 * R + 1;
+    constexpr int W2 = K + 2;
+    constexpr int WIN = W2 * W2;
+    constexpr int QU = 4;
+    static_assert(W2 + 3 <= 16, "a window must fit in a 4x4 block of tiles");
+
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    float* swin = smem + warp * (kTile * WIN);
+
+    int bid = blockIdx.x;
+    const int per_level = p.B * p.blocks_per_batch;
+    const int level = bid / per_level;
+    bid -= level * per_level;
+    const int b = bid / p.blocks_per_batch;
+    const int tile = (bid - b * p.blocks_per_batch) * kWarpsPerBlock + warp;
+    if (tile >= p.tiles_per_batch) return;
+
+    const int N = p.N;
+    const int n0 = tile * kTile;
+    const int n = n0 + lane;
+    const bool valid = n < N;
+    const int lh = p.lh[level], lw = p.lw[level];
+    const int th = p.th[level], tw = p.tw[level];
+    const int map_elems = th * tw * 16;
+    const float* __restrict__ lvl = p.lvl[level];
+    const float inv_scale = __int_as_float((127 - level) << 23);
+
+    // ---------------- phase A ----------------
+    float cx = 0.f, cy = 0.f;
+    if (valid) {
+        const float* c = p.coords + (size_t)b * 2 * N + n;
+        cx = __ldg(c) * inv_scale;
+        cy = __ldg(c + N) * inv_scale;
+    }
+    const float sx = (float)(lw - 1), sy = (float)(lh - 1);
+    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
+    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
+    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
+    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
+    const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
+                      !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
+    int x_lo = 0, y_lo = 0;
+    int my_base = 0;    // float offset of the window's first tile inside the query map: (ty0*tw + tx0)*16
+    int my_pack = 0;    // combo = (y_lo&3)*4 + (x_lo&3) in bits [0,4); bit 4+k: tile k = tyi*4+txi exists
+    if (valid && !wild) {
+        x_lo = (int)floorf(ixf);
+        y_lo = (int)floorf(iyf);
+        const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
+        my_base = (ty0 * tw + tx0) * 16;
+        int tmask = 0;
+#pragma unroll
+        for (int tyi = 0; tyi < 4; ++tyi)
+#pragma unroll
+            for (int txi = 0; txi < 4; ++txi)
+                if ((unsigned)(ty0 + tyi) < (unsigned)th && (unsigned)(tx0 + txi) < (unsigned)tw) tmask |= 1 << (tyi * 4 + txi);
+        my_pack = ((y_lo & 3) * 4 + (x_lo & 3)) | (tmask << 4);
+    }
+
+    // ---------------- phase B: tile gather ----------------
+    // slot s = lane + 32 j (j = 0, 1) = one row of one tile of the 4x4 tile block that covers the window:
+    // tile (tyi, txi) = ((s >> 4) & 3, (s >> 2) & 3), tile row iy = s & 3.  Everything that depends only on the
+    // slot is hoisted: its offset inside the map / the window, and 16-bit masks indexed by `combo` that say
+    // for which sub-tile shifts the slot (lmask) and each of its 4 elements (vmask) fall inside the window.
+    const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
+    const float* gptr[2];
+    int soff[2], tbit[2];
+    unsigned lmask[2], vmask[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int s = lane + 32 * j;
+        const int tyi = (s >> 4) & 3, txi = (s >> 2) & 3, iy = s & 3;
+        gptr[j] = tile_base + (tyi * tw + txi) * 16 + iy * 4;
+        soff[j] = (4 * tyi + iy) * W2 + 4 * txi;
+        tbit[j] = 4 + tyi * 4 + txi;
+        unsigned rm = 0;                                     // bit sy: window row 4*tyi+iy-sy is inside [0, W2)
+#pragma unroll
+        for (int sy2 = 0; sy2 < 4; ++sy2) rm |= (unsigned)((4 * tyi + iy - sy2 >= 0) && (4 * tyi + iy - sy2 < W2)) << (4 * sy2);
+        lmask[j] = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            unsigned cm = 0;                                 // bit sx: window column 4*txi+e-sx is inside [0, W2)
+#pragma unroll
+            for (int sx2 = 0; sx2 < 4; ++sx2) cm |= (unsigned)((4 * txi + e - sx2 >= 0) && (4 * txi + e - sx2 < W2)) << sx2;
+            vmask[j][e] = rm * cm;                           // bit (sy*4 + sx)
+            lmask[j] |= vmask[j][e];
+        }
+    }
+    auto load_group = [&](int q0, float4 (&v)[QU][2], int (&pk)[QU]) {
+#pragma unroll
+        for (int u = 0; u < QU; ++u) {
+            const int base = __shfl_sync(0xffffffffu, my_base, q0 + u);
+            pk[u] = __shfl_sync(0xffffffffu, my_pack, q0 + u);
+            const int combo = pk[u] & 15;
+            const float* __restrict__ mq = gptr[0] + ((q0 + u) * map_elems + base);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const bool ok = ((pk[u] >> tbit[j]) & 1) && ((lmask[j] >> combo) & 1);
+                v[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(mq + (gptr[j] - gptr[0]))) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    auto store_group = [&](int q0, const float4 (&v)[QU][2], const int (&pk)[QU]) {
+        float* sbase = swin + q0 * WIN;
+#pragma unroll
+        for (int u = 0; u < QU; ++u) {
+            const int combo = pk[u] & 15;
+            const int shift = (combo >> 2) * W2 + (combo & 3);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float* d = sbase + u * WIN + soff[j] - shift;
+                if ((vmask[j][0] >> combo) & 1) d[0] = v[u][j].x;
+                if ((vmask[j][1] >> combo) & 1) d[1] = v[u][j].y;
+                if ((vmask[j][2] >> combo) & 1) d[2] = v[u][j].z;
+                if ((vmask[j][3] >> combo) & 1) d[3] = v[u][j].w;
+            }
+        }
+    };
+    {
+        // software pipeline: the loads of group g+1 are issued before group g is written to shared memory,
+        // so 2*QU windows' worth of 16-byte loads stay in flight per lane for the whole phase
+        float4 va[QU][2], vb[QU][2];
+        int pa[QU], pb[QU];
+        static_assert((kTile / QU) % 2 == 0, "ping-pong needs an even number of groups");
+        load_group(0, va, pa);
+#pragma unroll 1
+        for (int q0 = 0; q0 < kTile; q0 += 2 * QU) {
+            load_group(q0 + QU, vb, pb);
+            store_group(q0, va, pa);
+            if (q0 + 2 * QU < kTile) load_group(q0 + 2 * QU, va, pa);
+            store_group(q0 + QU, vb, pb);
+        }
+    }
+    __syncwarp();
+
+    // ---------------- phase C (identical to lookup_kernel) ----------------
+    int rx[K], ry[K];
+    float wx0[K], wx1[K], wy0[K], wy1[K];
+    bool deviated = false;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
+        const float fx = floorf(ix);
+        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
+        const float fy = floorf(iy);
+        wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
+        wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+        wy1[a] = wild ? 0.f : __fsub_rn(iy, fy);
+        wy0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+        rx[a] = wild ? a : min(max((int)fx - x_lo, 0), W2 - 2);
+        ry[a] = wild ? a : min(max((int)fy - y_lo, 0), W2 - 2);
+        deviated |= (rx[a] != a) | (ry[a] != a);
+    }
+    if (!valid) deviated = false;
+
+    const float* sq = swin + lane * WIN;
+    const int CT = p.num_levels * K * K;
+    float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
+    if (!__any_sync(0xffffffffu, deviated)) {
+        float tprev[K];
+#pragma unroll
+        for (int r = 0; r <= K; ++r) {
+            float vrow[K + 1];
+#pragma unroll
+            for (int c = 0; c <= K; ++c) vrow[c] = sq[r * W2 + c];
+            float tcur[K];
+#pragma unroll
+            for (int a = 0; a < K; ++a) tcur[a] = __fmaf_rn(wx1[a], vrow[a + 1], __fmul_rn(wx0[a], vrow[a]));
+            if (r > 0) {
+                const int bb = r - 1;
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    const float o = __fmaf_rn(wy1[bb], tcur[a], __fmul_rn(wy0[bb], tprev[a]));
+                    if (valid) op[(int64_t)(a * K + bb) * N] = o;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+#pragma unroll
+            for (int bb = 0; bb < K; ++bb) {
+                const float* s = sq + ry[bb] * W2 + rx[a];
+                const float v00 = s[0], v01 = s[1], v10 = s[W2], v11 = s[W2 + 1];
+                const float nw = __fmul_rn(wx0[a], wy0[bb]);
+                const float ne = __fmul_rn(wx1[a], wy0[bb]);
+                const float sw = __fmul_rn(wx0[a], wy1[bb]);
+                const float se = __fmul_rn(wx1[a], wy1[bb]);
+                float o = __fmul_rn(v00, nw);
+                o = __fmaf_rn(v01, ne, o);
+                o = __fmaf_rn(v10, sw, o);
+                o = __fmaf_rn(v11, se, o);
+                if (valid) op[(int64_t)(a * K + bb) * N] = o;
+            }
+        }
+    }
+}
+
+template <int R>
+int launch_lookup_tiled(const LookupTiledParams& p, cudaStream_t stream) {
+    constexpr int K = 2 * R + 1;
+    constexpr int WIN = (K + 2) * (K + 2);
+    const size_t smem = (size_t)kWarpsPerBlock * kTile * WIN * sizeof(float);
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
+    FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
+    lookup_tiled_kernel<R><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    return check_launch("lookup_tiled_kernel");
+}
+
+// ---------------------------------------------------------------------------------
 // adjoint w.r.t. the pyramid: one thread per output-gradient element, 4 atomics each.
 // ---------------------------------------------------------------------------------
 struct LookupBwdParams {
@@ -375,4 +608,38 @@ extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, con
     const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
     lookup_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("lookup_bwd_kernel");
+}
+
+
+extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                                       int B, int h, int w, int radius, void* stream) {
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup_tiled: B=%d", B);
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "lookup_tiled: null pointer");
+    FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup_tiled: radius=%d outside [1,4]", radius);
+    if (int rc = check_levels(num_levels, h, w, "lookup_tiled")) return rc;
+    LookupTiledParams p{};
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "lookup_tiled: lvl[%d] is null", i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "lookup_tiled: lvl[%d] must be 16-byte aligned", i);
+        p.lvl[i] = lvl[i];
+        p.lh[i] = h >> i;
+        p.lw[i] = w >> i;
+        p.th[i] = ceil_div(p.lh[i], 4);
+        p.tw[i] = ceil_div(p.lw[i], 4);
+    }
+    p.coords = coords;
+    p.out = out;
+    p.B = B;
+    p.N = h * w;
+    p.num_levels = num_levels;
+    p.tiles_per_batch = ceil_div(p.N, kTile);
+    p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (radius) {
+        case 1: return launch_lookup_tiled<1>(p, s);
+        case 2: return launch_lookup_tiled<2>(p, s);
+        case 3: return launch_lookup_tiled<3>(p, s);
+        default: return launch_lookup_tiled<4>(p, s);
+    }
 }

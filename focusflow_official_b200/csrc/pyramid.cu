@@ -239,6 +239,124 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_bulk_kernel(const PyrPara
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled ("T4") layout: every level is stored per query map as [th][tw][4][4] floats, th = ceil(h/4),
+// tw = ceil(w/4), padding elements are exact zeros.  A 4x4 tile is 64 contiguous bytes -- the granularity
+// at which the memory system serves the lookup's gathers -- so a (2r+2)^2 window touches ~10.6 requests
+// instead of ~17 with row-major maps.  Pooling is tile-local: one output tile row (4 outputs) reads two
+// rows of two adjacent input tiles = four LDS.128, and is stored with one STS.128 + one STG.128.
+// ------------------------------------------------------------------------------------------
+struct TiledPyrParams {
+    const float* l0;
+    float* out[kFusedLevels];
+    int h[kFusedLevels], w[kFusedLevels];       // true level sizes
+    int th[kFusedLevels], tw[kFusedLevels];     // tiles per column / row
+    int np[kFusedLevels];                       // floats per map: th*tw*16
+    unsigned magic_tw[kFusedLevels];            // ceil(2^32 / tw)
+    int num_levels;
+};
+
+__device__ __forceinline__ void pool_level_tiled(const TiledPyrParams& p, int l, const float* __restrict__ sin,
+                                                 float* __restrict__ sout, float* __restrict__ dst, bool keep, int tid) {
+    const int twi = p.tw[l - 1];
+    const int tho = p.th[l], two = p.tw[l], ho = p.h[l], wo = p.w[l];
+    const int items = tho * two * 4;            // one item = one row of one output tile
+    for (int i = tid; i < items; i += kPyrThreads) {
+        const int t = i >> 2, iy = i & 3;
+        const int ty = (two == 1) ? t : (int)__umulhi((unsigned)t, p.magic_tw[l]);
+        const int tx = t - ty * two;
+        const int y = 4 * ty + iy;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y < ho && 4 * tx < wo) {
+            // input rows 2y, 2y+1 live in input tile row (2ty + (iy >> 1)), in-tile rows (2*iy)&3 and +1
+            const float* ta = sin + ((2 * ty + (iy >> 1)) * twi + 2 * tx) * 16 + ((2 * iy) & 3) * 4;
+            const float4 a0 = *reinterpret_cast<const float4*>(ta);
+            const float4 a1 = *reinterpret_cast<const float4*>(ta + 4);
+            o.x = (((a0.x + a0.y) + a1.x) + a1.y) * 0.25f;
+            if (4 * tx + 1 < wo) o.y = (((a0.z + a0.w) + a1.z) + a1.w) * 0.25f;
+            if (4 * tx + 2 < wo) {
+                const float4 b0 = *reinterpret_cast<const float4*>(ta + 16);
+                const float4 b1 = *reinterpret_cast<const float4*>(ta + 20);
+                o.z = (((b0.x + b0.y) + b1.x) + b1.y) * 0.25f;
+                if (4 * tx + 3 < wo) o.w = (((b0.z + b0.w) + b1.z) + b1.w) * 0.25f;
+            }
+        }
+        if (keep) *reinterpret_cast<float4*>(sout + 4 * i) = o;
+        __stcs(reinterpret_cast<float4*>(dst + 4 * i), o);
+    }
+}
+
+__global__ void __launch_bounds__(kPyrThreads) pyramid_tiled_kernel(const TiledPyrParams p, const int64_t Q) {
+    extern __shared__ __align__(128) float sm[];
+    const int tid = threadIdx.x;
+    const int stage_floats = p.np[0];
+    const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
+    float* scratch = sm + (size_t)kPyrStages * stage_floats;
+    const uint32_t sm_u32 = (uint32_t)__cvta_generic_to_shared(sm);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(scratch + p.np[1] + p.np[2] + 4) & ~7u;
+    if (tid == 0) {
+        for (int s = 0; s < kPyrStages; ++s) py_mbar_init(bar0 + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t q, int k) {  // thread 0 only
+        const uint32_t bar = bar0 + 8u * (k % kPyrStages);
+        py_mbar_expect_tx(bar, stage_bytes);
+        py_bulk_load(sm_u32 + (uint32_t)(k % kPyrStages) * stage_bytes, p.l0 + q * stage_floats, stage_bytes, bar);
+    };
+    if (tid == 0) {
+        int k = 0;
+        for (int64_t q = blockIdx.x; q < Q && k < kPyrStages; q += gridDim.x, ++k) issue(q, k);
+    }
+    int k = 0;
+    for (int64_t q = blockIdx.x; q < Q; q += gridDim.x, ++k) {
+        py_mbar_wait(bar0 + 8u * (k % kPyrStages), (uint32_t)((k / kPyrStages) & 1));
+        const float* sin = sm + (size_t)(k % kPyrStages) * stage_floats;
+        int off = 0;
+#pragma unroll 1
+        for (int l = 1; l < p.num_levels; ++l) {
+            float* sout = scratch + off;
+            pool_level_tiled(p, l, sin, sout, p.out[l] + q * p.np[l], l < p.num_levels - 1, tid);
+            __syncthreads();
+            sin = sout;
+            off += p.np[l];
+        }
+        if (tid == 0) {
+            const int64_t nxt = q + (int64_t)kPyrStages * gridDim.x;
+            if (nxt < Q) issue(nxt, k + kPyrStages);
+        }
+    }
+}
+
+// tiled -> reference row-major [Q, h, w] (CorrBlock.corr_pyramid for inspection / tests)
+__global__ void __launch_bounds__(256) untile_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t Q,
+                                                     int h, int w, int tw, int np) {
+    const int64_t total = Q * h * w;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % w);
+        const int64_t t = idx / w;
+        const int y = (int)(t % h);
+        const int64_t q = t / h;
+        dst[idx] = __ldg(src + q * np + ((y >> 2) * tw + (x >> 2)) * 16 + (y & 3) * 4 + (x & 3));
+    }
+}
+
+// reference row-major [Q, h, w] -> tiled (zero padding), used by tests to feed golden pyramids to the tiled lookup
+__global__ void __launch_bounds__(256) tile_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t Q,
+                                                   int h, int w, int tw, int np) {
+    const int64_t total = Q * np;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % np);
+        const int64_t q = idx / np;
+        const int t = e >> 4, iy = (e >> 2) & 3, ix = e & 3;
+        const int ty = t / tw, tx = t - ty * tw;
+        const int y = 4 * ty + iy, x = 4 * tx + ix;
+        dst[idx] = (y < h && x < w) ? __ldg(src + (q * h + y) * (int64_t)w + x) : 0.0f;
+    }
+}
+
 // generic one-level kernel straight from global memory (huge maps / > 4 levels)
 __global__ void __launch_bounds__(256) pool_level_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                          int64_t Q, int hi, int wi, int ho, int wo) {
@@ -382,4 +500,82 @@ extern "C" int ffcorr_pyramid_bwd_f32(float* const* grad_lvl, int num_levels, in
         if (int rc = check_launch("pool_level_bwd_kernel")) return rc;
     }
     return FFCORR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------ tiled layout
+extern "C" int64_t ffcorr_tiled_map_elems(int h, int w, int level) {
+    if (h < 1 || w < 1 || level < 0 || level >= FFCORR_MAX_LEVELS) return 0;
+    const int hl = h >> level, wl = w >> level;
+    if (hl < 1 || wl < 1) return 0;
+    return (int64_t)ceil_div(hl, 4) * ceil_div(wl, 4) * 16;
+}
+
+static int fill_tiled_params(TiledPyrParams* p, float* const* lvl, int num_levels, int h, int w) {
+    for (int i = 0; i < num_levels; ++i) {
+        p->h[i] = h >> i;
+        p->w[i] = w >> i;
+        p->th[i] = ceil_div(p->h[i], 4);
+        p->tw[i] = ceil_div(p->w[i], 4);
+        p->np[i] = p->th[i] * p->tw[i] * 16;
+        p->out[i] = lvl[i];
+        p->magic_tw[i] = (unsigned)((0x100000000ull + p->tw[i] - 1) / (unsigned)p->tw[i]);
+    }
+    p->l0 = lvl[0];
+    p->num_levels = num_levels;
+    return FFCORR_OK;
+}
+
+static size_t tiled_pyramid_smem(const TiledPyrParams& p) {
+    return ((size_t)kPyrStages * p.np[0] + (size_t)p.np[1] + p.np[2] + 16) * sizeof(float) + 64;
+}
+
+extern "C" int ffcorr_tiled_supported(int num_levels, int h, int w) {
+    if (num_levels < 1 || num_levels > kFusedLevels || h < 1 || w < 1 || h > 16384 || w > 16384) return 0;
+    if ((h >> (num_levels - 1)) < 1 || (w >> (num_levels - 1)) < 1) return 0;
+    TiledPyrParams p{};
+    float* dummy[kFusedLevels] = {nullptr, nullptr, nullptr, nullptr};
+    fill_tiled_params(&p, dummy, num_levels, h, w);
+    return tiled_pyramid_smem(p) <= 200 * 1024 && (uint64_t)p.np[0] * 4 < (1u << 20);
+}
+
+extern "C" int ffcorr_pyramid_tiled_f32(float* const* lvl, int num_levels, int64_t Q, int h, int w, void* stream) {
+    FFCORR_REQUIRE(lvl != nullptr, FFCORR_EINVAL, "pyramid_tiled: null level table");
+    FFCORR_REQUIRE(Q >= 0, FFCORR_EINVAL, "pyramid_tiled: Q=%lld", (long long)Q);
+    if (int rc = check_levels(num_levels, h, w, "pyramid_tiled")) return rc;
+    FFCORR_REQUIRE(ffcorr_tiled_supported(num_levels, h, w), FFCORR_EINVAL,
+                   "pyramid_tiled: %dx%d with %d levels is outside the tiled path (use the row-major entry points)", h, w, num_levels);
+    if (Q == 0 || num_levels == 1) return FFCORR_OK;
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "pyramid_tiled: lvl[%d] is null", i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "pyramid_tiled: lvl[%d] must be 16-byte aligned", i);
+    }
+    TiledPyrParams p{};
+    fill_tiled_params(&p, lvl, num_levels, h, w);
+    const size_t smem = tiled_pyramid_smem(p);
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    const int64_t want = (int64_t)per_sm * sm_count();
+    const int grid = (int)(Q < want ? Q : want);
+    FFCORR_CUDA(cudaFuncSetAttribute(pyramid_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pyramid_tiled_kernel<<<grid, kPyrThreads, smem, (cudaStream_t)stream>>>(p, Q);
+    return check_launch("pyramid_tiled_kernel");
+}
+
+extern "C" int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int h, int w, void* stream) {
+    FFCORR_REQUIRE(Q >= 0 && h >= 1 && w >= 1, FFCORR_EINVAL, "untile: bad shape");
+    if (Q == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(tiled && dst, FFCORR_EINVAL, "untile: null pointer");
+    const int tw = ceil_div(w, 4);
+    untile_kernel<<<grid_for(Q * h * w, 256), 256, 0, (cudaStream_t)stream>>>(tiled, dst, Q, h, w, tw, ceil_div(h, 4) * tw * 16);
+    return check_launch("untile_kernel");
+}
+
+extern "C" int ffcorr_tile_f32(const float* src, float* tiled, int64_t Q, int h, int w, void* stream) {
+    FFCORR_REQUIRE(Q >= 0 && h >= 1 && w >= 1, FFCORR_EINVAL, "tile: bad shape");
+    if (Q == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(tiled && src, FFCORR_EINVAL, "tile: null pointer");
+    const int tw = ceil_div(w, 4);
+    const int np = ceil_div(h, 4) * tw * 16;
+    tile_kernel<<<grid_for(Q * np, 256), 256, 0, (cudaStream_t)stream>>>(src, tiled, Q, h, w, tw, np);
+    return check_launch("tile_kernel");
 }

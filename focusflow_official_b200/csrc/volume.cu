@@ -170,7 +170,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 struct GemmParams {
-    int N;          // rows == cols of the volume per batch item
+    int N;          // rows of the volume per batch item (queries)
+    int Ncols;      // columns (targets): N, or the padded tile-major count for the tiled layout
     int B;
     int num_kb;     // K blocks of 128 bytes
     int tiles_m, tiles_n;
@@ -302,7 +303,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             auto process = [&](uint32_t (&v)[64], int c) {
                 const int col0 = n0 + c * 64;
                 if (TMA_STORE) {
-                    if (row0 >= p.N || col0 >= p.N) return;   // warp-uniform: both boxes outside
+                    if (row0 >= p.N || col0 >= p.Ncols) return;   // warp-uniform: both boxes outside
                     if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();   // the pair used STORE_PAIRS groups ago has been read
                     __syncwarp();
                     uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
@@ -324,18 +325,18 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (lane == 0) {
                         const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
                         tma_store_3d(&tmap_c, src, col0, row0, b);
-                        if (col0 + 32 < p.N) tma_store_3d(&tmap_c, src + SMEM_STORE_BUF, col0 + 32, row0, b);
+                        if (col0 + 32 < p.Ncols) tma_store_3d(&tmap_c, src + SMEM_STORE_BUF, col0 + 32, row0, b);
                         tma_store_commit();
                     }
                     pair = (pair + 1) % STORE_PAIRS;
                 } else {
                     const int row = row0 + lane;
                     if (row < p.N) {
-                        float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.N + col0;
+                        float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.Ncols + col0;
 #pragma unroll
                         for (int i = 0; i < 64; ++i) {
                             const float a = __uint_as_float(v[i]);
-                            if (col0 + i < p.N) o[i] = DIV ? __fdiv_rn(a, p.divisor) : a * p.scale;
+                            if (col0 + i < p.Ncols) o[i] = DIV ? __fdiv_rn(a, p.divisor) : a * p.scale;
                         }
                     }
                 }
@@ -390,32 +391,54 @@ __device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
 
 // Transposing convert.  Reads are 16-byte vectors along the pixel axis, writes are full 32-byte
 // sectors along K (16 consecutive channels of one pixel per thread).
+// Tiled ("T4") target order for the B operand: row n' of the staged operand is pixel
+// (y, x) = (4*ty + iy, 4*tx + ix) with n' = (ty*TW + tx)*16 + iy*4 + ix, zero rows for the padding up to
+// multiples of 4, so the GEMM writes every query's map directly as 4x4-pixel tiles of 64 contiguous bytes.
+struct TiledB {
+    int enabled;
+    int h, w;      // feature-map size
+    int tw;        // tiles per row: ceil(w / 4)
+    int np;        // padded pixel count: ceil4(h) * ceil4(w)
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(256) operand_prepass_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                                                               void* __restrict__ o1, void* __restrict__ o2,
-                                                              int B, int D, int N, int Dp /* padded K per segment */) {
+                                                              int B, int D, int N, int Dp /* padded K per segment */,
+                                                              const TiledB tb) {
     __shared__ __align__(16) float tile[PP_D][PP_N + 4];
     const int which = blockIdx.z / B;          // 0: fmap1 (A operand), 1: fmap2 (B operand)
     const int b = blockIdx.z - which * B;
     const float* __restrict__ in = (which == 0 ? f1 : f2) + (size_t)b * D * N;
     void* __restrict__ outp = which == 0 ? o1 : o2;
+    const bool tiled = tb.enabled && which == 1;
+    const int Nout = tiled ? tb.np : N;        // rows of the staged operand
     const int n0 = blockIdx.x * PP_N, d0 = blockIdx.y * PP_D;
+    if (n0 >= Nout) return;
     const int tid = threadIdx.x;
-    const bool vec_ok = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    const bool vec_ok = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (!tiled || (tb.w & 3) == 0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int dd = (tid >> 5) + 8 * i, nn = (tid & 31) * 4;
         const int d = d0 + dd, n = n0 + nn;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d < D) {
-            const float* src = in + (size_t)d * N + n;
+        if (d < D && n < Nout) {
+            int src_n = n, lim = N - n;            // source pixel of output row n, and how many of the 4 exist
+            if (tiled) {                           // n is a multiple of 4: one row of one 4x4 tile
+                const int t = n >> 4, iy = (n >> 2) & 3;
+                const int ty = t / tb.tw, tx = t - ty * tb.tw;
+                const int y = 4 * ty + iy, x = 4 * tx;
+                src_n = y * tb.w + x;
+                lim = (y < tb.h) ? tb.w - x : 0;
+            }
+            const float* src = in + (size_t)d * N + src_n;
             if (vec_ok) {
-                if (n < N) v = __ldg(reinterpret_cast<const float4*>(src));
+                if (lim >= 4) v = __ldg(reinterpret_cast<const float4*>(src));
             } else {
-                if (n + 0 < N) v.x = __ldg(src + 0);
-                if (n + 1 < N) v.y = __ldg(src + 1);
-                if (n + 2 < N) v.z = __ldg(src + 2);
-                if (n + 3 < N) v.w = __ldg(src + 3);
+                if (lim > 0) v.x = __ldg(src + 0);
+                if (lim > 1) v.y = __ldg(src + 1);
+                if (lim > 2) v.z = __ldg(src + 2);
+                if (lim > 3) v.w = __ldg(src + 3);
             }
         }
         *reinterpret_cast<float4*>(&tile[dd][nn]) = v;
@@ -423,19 +446,19 @@ __global__ void __launch_bounds__(256) operand_prepass_kernel(const float* __res
     __syncthreads();
     const int nl = tid & (PP_N - 1), half = tid >> 7;
     const int n = n0 + nl;
-    if (n >= N) return;
+    if (n >= Nout) return;
     float x[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) x[k] = tile[half * 16 + k][nl];
     const int dcol = d0 + half * 16;
     if (MODE == CVT_F16) {
-        __half* o = reinterpret_cast<__half*>(outp) + ((size_t)b * N + n) * Dp + dcol;
+        __half* o = reinterpret_cast<__half*>(outp) + ((size_t)b * Nout + n) * Dp + dcol;
         uint4 q0 = make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
         uint4 q1 = make_uint4(pack_h2(x[8], x[9]), pack_h2(x[10], x[11]), pack_h2(x[12], x[13]), pack_h2(x[14], x[15]));
         reinterpret_cast<uint4*>(o)[0] = q0;
         reinterpret_cast<uint4*>(o)[1] = q1;
     } else if (MODE == CVT_F32) {
-        float* o = reinterpret_cast<float*>(outp) + ((size_t)b * N + n) * Dp + dcol;
+        float* o = reinterpret_cast<float*>(outp) + ((size_t)b * Nout + n) * Dp + dcol;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             reinterpret_cast<float4*>(o)[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
@@ -448,7 +471,7 @@ __global__ void __launch_bounds__(256) operand_prepass_kernel(const float* __res
             hi[k] = __float2bfloat16_rn(x[k]);
             lo[k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi[k]));
         }
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + ((size_t)b * N + n) * (3 * (size_t)Dp) + dcol;
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + ((size_t)b * Nout + n) * (3 * (size_t)Dp) + dcol;
 #pragma unroll
         for (int seg = 0; seg < 3; ++seg) {
             const bool use_lo = (which == 0) ? (seg == 2) : (seg == 1);
@@ -577,14 +600,14 @@ using namespace ffcorr;
 extern "C" size_t ffcorr_volume_workspace_bytes(int B, int D, int h, int w, int precision) {
     PrecInfo pi;
     if (!prec_info(precision, &pi) || B <= 0 || D <= 0 || h <= 0 || w <= 0) return 0;
-    const size_t N = (size_t)h * w;
+    const size_t Np = align_up((size_t)h, 4) * align_up((size_t)w, 4);   // >= h*w; covers the tiled layout too
     const size_t Dp = align_up((size_t)D, pi.k_align);
-    const size_t one = align_up((size_t)B * N * Dp * pi.k_mult * pi.elem_bytes, 256);
+    const size_t one = align_up((size_t)B * Np * Dp * pi.k_mult * pi.elem_bytes, 256);
     return 2 * one;
 }
 
-extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
-                                 int precision, void* workspace, size_t workspace_bytes, void* stream) {
+static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w, int precision,
+                       void* workspace, size_t workspace_bytes, void* stream, bool tiled) {
     FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume: bad shape B=%d D=%d h=%d w=%d", B, D, h, w);
     FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "volume: h*w=%lld too large", (long long)h * w);
     if (B == 0) return FFCORR_OK;  // empty batch: pointers may legitimately be null
@@ -593,6 +616,8 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
     const int N = h * w;
     const float sqrt_d = sqrtf((float)D);
 
+    FFCORR_REQUIRE(!(tiled && precision == FFCORR_PREC_FP32), FFCORR_EINVAL,
+                   "volume: the tiled layout is produced by the tensor-core paths only");
     if (precision == FFCORR_PREC_FP32) {
         // C[i,j] = sum_d f1[d,i] f2[d,j]: A[m=i,k=d] (m contiguous), B[k=d,n=j] (n contiguous)
         return launch_sgemm(true, true, fmap1, fmap2, lvl0, N, N, D, 1, N, N, 1, N, (int64_t)D * N, (int64_t)D * N,
@@ -614,15 +639,22 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
     void* opB = ws + need / 2;
 
     // ---- 1. operand pre-pass ----
+    TiledB tlb{};
+    tlb.enabled = tiled ? 1 : 0;
+    tlb.h = h;
+    tlb.w = w;
+    tlb.tw = ceil_div(w, 4);
+    tlb.np = ceil_div(h, 4) * 4 * tlb.tw * 4;
+    const int Ncols = tiled ? tlb.np : N;       // columns of the volume == rows of the staged B operand
     {
-        dim3 grid(ceil_div(N, PP_N), Dp / PP_D, 2 * B);
+        dim3 grid(ceil_div(Ncols, PP_N), Dp / PP_D, 2 * B);
         FFCORR_REQUIRE(grid.y < 65536 && grid.z < 65536, FFCORR_EINVAL, "volume: pre-pass grid too large");
         if (precision == FFCORR_PREC_FP16)
-            operand_prepass_kernel<CVT_F16><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp);
+            operand_prepass_kernel<CVT_F16><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         else if (precision == FFCORR_PREC_TF32)
-            operand_prepass_kernel<CVT_F32><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp);
+            operand_prepass_kernel<CVT_F32><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         else
-            operand_prepass_kernel<CVT_BF16X3_A><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp);
+            operand_prepass_kernel<CVT_BF16X3_A><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         if (int rc = check_launch("operand_prepass_kernel")) return rc;
     }
 
@@ -635,11 +667,11 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
     const uint32_t box_k = (uint32_t)(BK_BYTES / pi.elem_bytes);
     const uint64_t row_bytes = (uint64_t)Kt * pi.elem_bytes;
     if (int rc = encode_3d(&ta, dt, pi.elem_bytes, opA, Kt, N, B, row_bytes, row_bytes * N, box_k, BM, "A")) return rc;
-    if (int rc = encode_3d(&tb, dt, pi.elem_bytes, opB, Kt, N, B, row_bytes, row_bytes * N, box_k, BN, "B")) return rc;
-    const bool tma_store = (N % 4 == 0);
+    if (int rc = encode_3d(&tb, dt, pi.elem_bytes, opB, Kt, Ncols, B, row_bytes, row_bytes * Ncols, box_k, BN, "B")) return rc;
+    const bool tma_store = (Ncols % 4 == 0);
     if (tma_store) {
-        if (int rc = encode_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, N, N, B, (uint64_t)N * 4, (uint64_t)N * N * 4,
-                               STORE_COLS, 32, "C"))
+        if (int rc = encode_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, Ncols, N, B, (uint64_t)Ncols * 4,
+                               (uint64_t)N * Ncols * 4, STORE_COLS, 32, "C"))
             return rc;
     } else {
         tc = ta;  // unused by the kernel
@@ -648,10 +680,11 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
     // ---- 3. GEMM ----
     GemmParams p{};
     p.N = N;
+    p.Ncols = Ncols;
     p.B = B;
     p.num_kb = Kt * pi.elem_bytes / BK_BYTES;
     p.tiles_m = ceil_div(N, BM);
-    p.tiles_n = ceil_div(N, BN);
+    p.tiles_n = ceil_div(Ncols, BN);
     p.divisor = sqrt_d;
     int e = 0;
     const float mant = frexpf(sqrt_d, &e);
@@ -681,6 +714,16 @@ extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* 
 #undef FF_GEMM_DV
 #undef FF_GEMM
     return check_launch("volume_gemm_kernel");
+}
+
+extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
+                                 int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    return volume_impl(fmap1, fmap2, lvl0, B, D, h, w, precision, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int ffcorr_volume_tiled_f32(const float* fmap1, const float* fmap2, float* lvl0_tiled, int B, int D, int h, int w,
+                                       int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    return volume_impl(fmap1, fmap2, lvl0_tiled, B, D, h, w, precision, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1, const float* fmap2, float* gfmap1,

@@ -104,6 +104,26 @@ int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coor
                       int B, int h, int w, int radius, void* stream);
 
 /*
+ * Tiled ("T4") pyramid layout -- the inference fast path.  Every level is stored per query map as
+ * [ceil(h_i/4)][ceil(w_i/4)][4][4] floats (ffcorr_tiled_map_elems() per map), padding = exact zeros.
+ * A 4x4 tile is 64 contiguous bytes, the granularity at which the memory system serves the lookup's
+ * gathers.  The three entry points below are drop-ins for ffcorr_volume_f32 / ffcorr_pyramid_f32 /
+ * ffcorr_lookup_f32 on that layout (same arguments, same results); ffcorr_untile_f32 / ffcorr_tile_f32
+ * convert a level to / from the reference's row-major [Q, h_i, w_i] (CorrBlock.corr_pyramid, tests).
+ * ffcorr_tiled_supported() tells whether a shape fits the tiled kernels (<= 4 levels, map <= ~48 KB).
+ */
+int64_t ffcorr_tiled_map_elems(int h, int w, int level);
+int ffcorr_tiled_supported(int num_levels, int h, int w);
+int ffcorr_volume_tiled_f32(const float* fmap1, const float* fmap2, float* lvl0_tiled,
+                            int B, int D, int h, int w, int precision,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int ffcorr_pyramid_tiled_f32(float* const* lvl, int num_levels, int64_t Q, int h, int w, void* stream);
+int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                            int B, int h, int w, int radius, void* stream);
+int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int h_level, int w_level, void* stream);
+int ffcorr_tile_f32(const float* src, float* tiled, int64_t Q, int h_level, int w_level, void* stream);
+
+/*
  * Adjoint of the lookup w.r.t. the pyramid.  grad_lvl[i] must be ZEROED by the caller;
  * contributions are accumulated with atomics (red.global.add.f32).
  */

@@ -403,3 +403,71 @@ def test_e2e_epe_vs_reference_golden():
             print(f"e2e {tag} {prec}: EPE mean {float(epe.mean()):.2e} max {float(epe.max()):.2e}")
             assert float(epe.max()) <= 1e-2, (tag, prec, float(epe.max()))  # BASELINE: EPE within 0.01 px
             assert float(epe.mean()) <= 2e-3
+
+
+# ---------------------------------------------------------------- tiled ("T4") layout: the inference fast path
+@pytest.mark.parametrize("shape", [(3, 16, 24), (2, 17, 21), (1, 46, 62), (2, 9, 33), (1, 5, 7)])
+def test_tile_untile_roundtrip_and_padding(shape):
+    m = ff()
+    q, h, w = shape
+    x = torch.randn(q, 1, h, w, device=DEV)
+    (tl,) = m.tile_levels([x])
+    th, tw = (h + 3) // 4, (w + 3) // 4
+    assert tl.shape == (q, th * tw * 16)
+    # padding is exact zero and the sum is preserved
+    assert float(tl.double().sum()) == pytest.approx(float(x.double().sum()), rel=1e-9, abs=1e-9)
+    from focusflow_official_b200 import _lib
+    back = torch.empty_like(x)
+    _lib.check(_lib.lib().ffcorr_untile_f32(tl.data_ptr(), back.data_ptr(), q, h, w, _lib.current_stream()), "untile")
+    assert torch.equal(back, x)
+    # explicit element check of the tile-major order
+    tt = tl.view(q, th, tw, 4, 4)
+    y, xx = min(h - 1, 6), min(w - 1, 5)
+    assert torch.equal(tt[:, y // 4, xx // 4, y % 4, xx % 4], x[:, 0, y, xx])
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_golden_lookup_tiled(path):
+    """Golden pyramids of the reference, re-laid out in tiles, through the tiled lookup kernel."""
+    g = np.load(path)
+    m = ff()
+    levels = m.tile_levels([t(g[f"level{i}"][:, None]) for i in range(4)])
+    for k in [k[len("coords_"):] for k in g.files if k.startswith("coords_")]:
+        out = m.lookup_tiled(levels, t(g[f"coords_{k}"]), 4).cpu().numpy()
+        ref = g[f"lookup_{k}"]
+        assert max_rel(out, ref) <= 1e-5, (k, max_rel(out, ref))
+
+
+@pytest.mark.parametrize("shape,radius,nl", [((1, 46, 62), 4, 4), ((2, 17, 21), 4, 4), ((1, 24, 40), 3, 4),
+                                             ((2, 12, 9), 2, 3), ((1, 9, 33), 1, 2), ((3, 8, 8), 4, 1)])
+def test_lookup_tiled_vs_oracle(shape, radius, nl):
+    b, h, w = shape
+    rng = np.random.default_rng(77)
+    q = b * h * w
+    pyr = [rng.standard_normal((q, h >> i, w >> i)).astype(np.float32) for i in range(nl)]
+    levels = ff().tile_levels([t(p[:, None]) for p in pyr])
+    for name, c in _coords_cases(rng, b, h, w).items():
+        ref = co.lookup(pyr, c, radius)
+        got = ff().lookup_tiled(levels, t(c), radius).cpu().numpy()
+        assert np.isfinite(got).all(), name
+        assert max_rel(got, ref) <= 1e-5, (shape, name, max_rel(got, ref))
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 46, 62), (2, 64, 17, 21), (2, 32, 16, 24), (1, 40, 9, 13)])
+def test_tiled_and_rowmajor_blocks_agree_bitwise(shape):
+    """Same kernels' arithmetic, two storage orders: pyramids and lookups must be identical."""
+    m = ff()
+    b, d, h, w = shape
+    nl = 4 if min(h, w) >= 16 else 1
+    torch.manual_seed(2)
+    f1 = torch.randn(shape, device=DEV) * 4.4
+    f2 = torch.randn(shape, device=DEV) * 4.4
+    a = m.CorrBlock(f1, f2, num_levels=nl, layout="tiled")
+    r = m.CorrBlock(f1, f2, num_levels=nl, layout="rowmajor")
+    assert a._tiled and not r._tiled
+    for i in range(nl):
+        assert torch.equal(a.corr_pyramid[i], r.corr_pyramid[i]), i
+    coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 3
+    assert torch.equal(a(coords), r(coords))
+    grid = m.coords_grid(b, h, w, DEV)
+    assert torch.equal(a(grid), r(grid))

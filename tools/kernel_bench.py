@@ -88,6 +88,10 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     out = torch.empty(b, nl * 81, h, w, device=dev)
     flush = L2Flusher(dev)
 
+    tl = [torch.empty(b * n, int(L.ffcorr_tiled_map_elems(h, w, i)), device=dev) for i in range(nl)]
+    tptrs = _lib.ptr_array(tl)
+    tiled_ok = bool(L.ffcorr_tiled_supported(nl, h, w)) and code != _lib.PREC_FP32
+
     def k_volume():
         _lib.check(L.ffcorr_volume_f32(f1.data_ptr(), f2.data_ptr(), levels[0].data_ptr(), b, d, h, w, code,
                                        ws.data_ptr(), ws_bytes, stream), "volume")
@@ -98,14 +102,27 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     def k_lookup():
         _lib.check(L.ffcorr_lookup_f32(ptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, stream), "lookup")
 
+    def k_volume_t():
+        _lib.check(L.ffcorr_volume_tiled_f32(f1.data_ptr(), f2.data_ptr(), tl[0].data_ptr(), b, d, h, w, code,
+                                             ws.data_ptr(), ws_bytes, stream), "volume_tiled")
+
+    def k_pyramid_t():
+        _lib.check(L.ffcorr_pyramid_tiled_f32(tptrs, nl, b * n, h, w, stream), "pyramid_tiled")
+
+    def k_lookup_t():
+        _lib.check(L.ffcorr_lookup_tiled_f32(tptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, stream), "lookup_tiled")
+
     res = []
     lv_elems = [(h >> i) * (w >> i) for i in range(nl)]
     vol_flops = 2.0 * b * n * n * d
     vol_bytes = b * (2 * n * d * 4 + n * n * 4)
     pyr_bytes = 4.0 * b * n * sum(lv_elems)
     look_bytes = b * n * (nl * (2 * r + 2) ** 2 * 4 + nl * (2 * r + 1) ** 2 * 4 + 8)
-    for name, fn, byts, flops in (("volume", k_volume, vol_bytes, vol_flops), ("pyramid", k_pyramid, pyr_bytes, 0.0),
-                                  ("lookup", k_lookup, look_bytes, 0.0)):
+    todo = [("volume", k_volume, vol_bytes, vol_flops), ("pyramid", k_pyramid, pyr_bytes, 0.0), ("lookup", k_lookup, look_bytes, 0.0)]
+    if tiled_ok:  # same algorithmic bytes: the padding of the tiled layout is overhead, not work
+        todo += [("volume_tiled", k_volume_t, vol_bytes, vol_flops), ("pyramid_tiled", k_pyramid_t, pyr_bytes, 0.0),
+                 ("lookup_tiled", k_lookup_t, look_bytes, 0.0)]
+    for name, fn, byts, flops in todo:
         med, best = time_cuda(fn, iters=iters, warmup=warmup, flush=flush)
         gbs = byts / (med * 1e-3) / 1e9
         rec = {"kernel": name, "config": config, "ms": round(med, 4), "ms_min": round(best, 4),
