@@ -155,6 +155,12 @@ def cpu_reference_run(steps: int, warmup: int, batch: int = 1):
     from oracle.corr_torch_cpu import TorchCorrBlock
     from weights import synthetic_pair
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can get
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     model = make_model("cpu", False)
     model.flow_net.corr_block = TorchCorrBlock
     im1, im2, m1, m2 = synthetic_pair(batch, H, W, seed=1234)
