@@ -458,6 +458,236 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_tiled_kernel(const
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Row-streaming variant of the tiled lookup: instead of staging whole 11x11 windows (15.5 KB of shared
+// memory per warp -> 14 warps per SM), the warp streams the 32 windows ROW BY ROW through a 3.3 KB double
+// buffer: gather window row r of all 32 queries (lane = (query, tile column), one 16-byte load per slot),
+// then every lane (= query) folds that row into its 9 running horizontal interpolants and emits the 9
+// outputs whose lower row it completes.  Shared memory no longer limits occupancy, the loads of row r+1
+// are in flight while row r is evaluated, and no slot is loaded that the window does not need.
+// ---------------------------------------------------------------------------------
+constexpr int kStreamWarps = 4;
+
+template <int R>
+__global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(const LookupTiledParams p) {
+    constexpr int K = 2 * R + 1;
+    constexpr int W2 = K + 2;
+    constexpr int RS = W2 + 2;                    // odd row stride per query: conflict-free lane-per-query reads
+    constexpr int ROWBUF = kTile * RS;
+    static_assert(RS % 2 == 1, "row stride must be odd");
+
+    __shared__ float srow_all[kStreamWarps][2][ROWBUF];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    float* srow = &srow_all[warp][0][0];
+
+    int bid = blockIdx.x;
+    const int per_level = p.B * p.blocks_per_batch;
+    const int level = bid / per_level;
+    bid -= level * per_level;
+    const int b = bid / p.blocks_per_batch;
+    const int tile = (bid - b * p.blocks_per_batch) * kStreamWarps + warp;
+    if (tile >= p.tiles_per_batch) return;
+
+    const int N = p.N;
+    const int n0 = tile * kTile;
+    const int n = n0 + lane;
+    const bool valid = n < N;
+    const int lh = p.lh[level], lw = p.lw[level];
+    const int th = p.th[level], tw = p.tw[level];
+    const int map_elems = th * tw * 16;
+    const float* __restrict__ lvl = p.lvl[level];
+    const float inv_scale = __int_as_float((127 - level) << 23);
+
+    // ---------------- phase A (lane = query) ----------------
+    float cx = 0.f, cy = 0.f;
+    if (valid) {
+        const float* c = p.coords + (size_t)b * 2 * N + n;
+        cx = __ldg(c) * inv_scale;
+        cy = __ldg(c + N) * inv_scale;
+    }
+    const float sx = (float)(lw - 1), sy = (float)(lh - 1);
+    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
+    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
+    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
+    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
+    const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
+                      !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
+    int x_lo = 0, y_lo = 0;
+    int my_base = 0;    // float offset of the window's first tile inside the query map: (ty0*tw + tx0)*16
+    int my_pack = 0;    // bits [0,2) x_lo&3, [2,4) y_lo&3, bit 4+k: tile k = tyi*4+txi of the 4x4 block exists
+    if (valid && !wild) {
+        x_lo = (int)floorf(ixf);
+        y_lo = (int)floorf(iyf);
+        const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
+        my_base = (ty0 * tw + tx0) * 16;
+        int tmask = 0;
+#pragma unroll
+        for (int tyi = 0; tyi < 4; ++tyi)
+#pragma unroll
+            for (int txi = 0; txi < 4; ++txi)
+                if ((unsigned)(ty0 + tyi) < (unsigned)th && (unsigned)(tx0 + txi) < (unsigned)tw) tmask |= 1 << (tyi * 4 + txi);
+        my_pack = (x_lo & 3) | ((y_lo & 3) << 2) | (tmask << 4);
+    }
+
+    // x-tap weights stay in registers; the y-tap weights are recomputed per row step (keeps the register
+    // count low enough for ~20 resident warps).  Floor deviations of the round trip (-1/0/+1 per tap) are
+    // packed 2 bits per tap: px for columns, py for rows.
+    float wx0[K], wx1[K];
+    unsigned px = 0, py = 0;
+    bool deviated = false;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
+        const float fx = floorf(ix);
+        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
+        const float fy = floorf(iy);
+        wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
+        wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+        const int dxa = wild ? 0 : min(max((int)fx - x_lo, 0), W2 - 2) - a;   // in {-1, 0, 1}
+        const int dya = wild ? 0 : min(max((int)fy - y_lo, 0), W2 - 2) - a;
+        px |= (unsigned)((dxa + 1) & 3) << (2 * a);
+        py |= (unsigned)((dya + 1) & 3) << (2 * a);
+        deviated |= (dxa != 0) | (dya != 0);
+    }
+    if (!valid) deviated = false;
+    const bool slow = __any_sync(0xffffffffu, deviated);
+    auto ytap = [&](int bb, float& w0, float& w1) {
+        const float iy = source_index(__fadd_rn(cy, (float)(bb - R)), sy);
+        const float fy = floorf(iy);
+        w1 = wild ? 0.f : __fsub_rn(iy, fy);
+        w0 = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+    };
+
+    // ---------------- gather slots (lane = (query qj, tile column txi), j = 0..3) ----------------
+    const int txi = lane & 3;
+    const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
+    const float* gp[4];     // first float of tile column txi in the window's first tile row
+    int gsy[4];             // y_lo & 3 of the slot's query
+    int gtm[4];             // tile-exists bits of tile column txi: bit tyi
+    int gcm[4];             // element e of the slot lands inside the window row: bit e
+    int gso[4];             // float offset in a row buffer of element 0 (may be negative; masked)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int qj = (lane >> 2) + 8 * j;
+        const int base = __shfl_sync(0xffffffffu, my_base, qj);
+        const int pk = __shfl_sync(0xffffffffu, my_pack, qj);
+        const int sxo = pk & 3;
+        gsy[j] = (pk >> 2) & 3;
+        gp[j] = tile_base + ((int64_t)qj * map_elems + base + txi * 16);
+        gtm[j] = ((pk >> (4 + txi)) & 1) | (((pk >> (8 + txi)) & 1) << 1) | (((pk >> (12 + txi)) & 1) << 2) |
+                 (((pk >> (16 + txi)) & 1) << 3);
+        const int c0 = 4 * txi - sxo;
+        gso[j] = qj * RS + c0;
+        int cm = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cm |= (int)((c0 + e >= 0) && (c0 + e < W2)) << e;
+        gcm[j] = cm;
+    }
+    auto load_row = [&](int r, float4 (&v)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = gsy[j] + r;               // row inside the 4x4 tile block
+            const bool ok = (gtm[j] >> (t >> 2)) & 1;
+            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(gp[j] + (t >> 2) * (tw * 16) + (t & 3) * 4))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_row = [&](float* buf, const float4 (&v)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float* d = buf + gso[j];
+            if (gcm[j] & 1) d[0] = v[j].x;
+            if (gcm[j] & 2) d[1] = v[j].y;
+            if (gcm[j] & 4) d[2] = v[j].z;
+            if (gcm[j] & 8) d[3] = v[j].w;
+        }
+    };
+
+    const int CT = p.num_levels * K * K;
+    float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
+    float4 v[4];
+    load_row(0, v);
+
+    if (!slow) {
+        // fast path: tap (a, b) reads window (b, a); row r feeds outputs bb = r - 1 (as its lower row)
+        float tprev[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) tprev[a] = 0.f;
+#pragma unroll 1
+        for (int r = 0; r <= K; ++r) {
+            float* buf = srow + (r & 1) * ROWBUF;
+            store_row(buf, v);
+            __syncwarp();
+            if (r < K) load_row(r + 1, v);          // in flight while this row is evaluated
+            const float* sq = buf + lane * RS;
+            float vrow[K + 1];
+#pragma unroll
+            for (int c = 0; c <= K; ++c) vrow[c] = sq[c];
+            float tcur[K];
+#pragma unroll
+            for (int a = 0; a < K; ++a) tcur[a] = __fmaf_rn(wx1[a], vrow[a + 1], __fmul_rn(wx0[a], vrow[a]));
+            if (r > 0) {
+                float w0, w1;
+                ytap(r - 1, w0, w1);
+                float* o_row = op + (int64_t)(r - 1) * N;
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    const float o = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
+                    if (valid) o_row[(int64_t)(a * K) * N] = o;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
+        }
+    } else {
+        // exact general path (integer / near-integer coordinates): row r completes the outputs whose lower
+        // corner row is r, i.e. ry[bb] + 1 == r; both rows are in the double buffer.  ATen's nw/ne/sw/se order.
+#pragma unroll 1
+        for (int r = 0; r < W2; ++r) {
+            float* buf = srow + (r & 1) * ROWBUF;
+            const float* prev = srow + ((r & 1) ^ 1) * ROWBUF + lane * RS;
+            store_row(buf, v);
+            __syncwarp();
+            if (r + 1 < W2) load_row(r + 1, v);
+            const float* cur = buf + lane * RS;
+#pragma unroll 1
+            for (int bb = 0; bb < K; ++bb) {
+                const int ryb = bb + (int)((py >> (2 * bb)) & 3u) - 1;
+                if (ryb + 1 == r) {
+                    float wy0b, wy1b;
+                    ytap(bb, wy0b, wy1b);
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        const int rxa = a + (int)((px >> (2 * a)) & 3u) - 1;
+                        const float v00 = prev[rxa], v01 = prev[rxa + 1], v10 = cur[rxa], v11 = cur[rxa + 1];
+                        const float nw = __fmul_rn(wx0[a], wy0b);
+                        const float ne = __fmul_rn(wx1[a], wy0b);
+                        const float sw = __fmul_rn(wx0[a], wy1b);
+                        const float se = __fmul_rn(wx1[a], wy1b);
+                        float o = __fmul_rn(v00, nw);
+                        o = __fmaf_rn(v01, ne, o);
+                        o = __fmaf_rn(v10, sw, o);
+                        o = __fmaf_rn(v11, se, o);
+                        if (valid) op[(int64_t)(a * K + bb) * N] = o;
+                    }
+                }
+            }
+            __syncwarp();   // prev/cur reads done before the buffer pair is overwritten two steps later
+        }
+    }
+}
+
+template <int R>
+int launch_lookup_tiled_stream(const LookupTiledParams& p0, cudaStream_t stream) {
+    LookupTiledParams p = p0;
+    p.blocks_per_batch = ceil_div(p.tiles_per_batch, kStreamWarps);
+    const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
+    FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
+    lookup_tiled_stream_kernel<R><<<(unsigned)blocks, kStreamWarps * 32, 0, stream>>>(p);
+    return check_launch("lookup_tiled_stream_kernel");
+}
+
 template <int R>
 int launch_lookup_tiled(const LookupTiledParams& p, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
@@ -636,6 +866,15 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
+    static const int variant = [] { const char* e = getenv("FFCORR_LOOKUP_TILED"); return e ? atoi(e) : 1; }();
+    if (variant == 1) {
+        switch (radius) {
+            case 1: return launch_lookup_tiled_stream<1>(p, s);
+            case 2: return launch_lookup_tiled_stream<2>(p, s);
+            case 3: return launch_lookup_tiled_stream<3>(p, s);
+            default: return launch_lookup_tiled_stream<4>(p, s);
+        }
+    }
     switch (radius) {
         case 1: return launch_lookup_tiled<1>(p, s);
         case 2: return launch_lookup_tiled<2>(p, s);

@@ -268,18 +268,39 @@ __device__ __forceinline__ void pool_level_tiled(const TiledPyrParams& p, int l,
         const int y = 4 * ty + iy;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y < ho && 4 * tx < wo) {
-            // input rows 2y, 2y+1 live in input tile row (2ty + (iy >> 1)), in-tile rows (2*iy)&3 and +1
+            // input rows 2y, 2y+1 live in input tile row (2ty + (iy >> 1)), in-tile rows (2*iy)&3 and +1.
+            // Bank groups: a 16-byte read of row k of input tile T sits in group (4T + k) mod 8, and an
+            // item's four reads cover groups {g, g+1, g+4, g+5}.  The 8 items of a quarter warp are 2 output
+            // tiles x 4 rows; odd tiles read the odd row first and, when the input has an even number of tiles
+            // per row (tile parity does not alternate with iy), the lower half starts with the right-hand
+            // tile -- then every step of the quarter warp hits 8 distinct groups.
             const float* ta = sin + ((2 * ty + (iy >> 1)) * twi + 2 * tx) * 16 + ((2 * iy) & 3) * 4;
-            const float4 a0 = *reinterpret_cast<const float4*>(ta);
-            const float4 a1 = *reinterpret_cast<const float4*>(ta + 4);
-            o.x = (((a0.x + a0.y) + a1.x) + a1.y) * 0.25f;
-            if (4 * tx + 1 < wo) o.y = (((a0.z + a0.w) + a1.z) + a1.w) * 0.25f;
-            if (4 * tx + 2 < wo) {
-                const float4 b0 = *reinterpret_cast<const float4*>(ta + 16);
-                const float4 b1 = *reinterpret_cast<const float4*>(ta + 20);
-                o.z = (((b0.x + b0.y) + b1.x) + b1.y) * 0.25f;
-                if (4 * tx + 3 < wo) o.w = (((b0.z + b0.w) + b1.z) + b1.w) * 0.25f;
+            const bool have_b = 4 * tx + 2 < wo;
+            const bool swr = (t & 1) != 0;
+            const bool swt = have_b && ((twi & 1) == 0) && ((iy >> 1) != 0);
+            const float* first = ta + (swt ? 16 : 0);
+            const float* second = ta + (swt ? 0 : 16);
+            const float4 x0 = *reinterpret_cast<const float4*>(first + (swr ? 4 : 0));
+            const float4 x1 = *reinterpret_cast<const float4*>(first + (swr ? 0 : 4));
+            // upper / lower input rows of the first-loaded tile
+            const float4 u0 = swr ? x1 : x0, l0 = swr ? x0 : x1;
+            const float p0 = (((u0.x + u0.y) + l0.x) + l0.y) * 0.25f;
+            const float p1 = (((u0.z + u0.w) + l0.z) + l0.w) * 0.25f;
+            float q0 = 0.f, q1 = 0.f;
+            if (have_b) {
+                const float4 x2 = *reinterpret_cast<const float4*>(second + (swr ? 4 : 0));
+                const float4 x3 = *reinterpret_cast<const float4*>(second + (swr ? 0 : 4));
+                const float4 u1 = swr ? x3 : x2, l1 = swr ? x2 : x3;
+                q0 = (((u1.x + u1.y) + l1.x) + l1.y) * 0.25f;
+                q1 = (((u1.z + u1.w) + l1.z) + l1.w) * 0.25f;
             }
+            // (p0, p1) belong to the left tile unless the tiles were swapped
+            o.x = swt ? q0 : p0;
+            o.y = swt ? q1 : p1;
+            o.z = swt ? p0 : q0;
+            o.w = swt ? p1 : q1;
+            if (4 * tx + 1 >= wo) o.y = 0.f;
+            if (4 * tx + 3 >= wo) o.w = 0.f;
         }
         if (keep) *reinterpret_cast<float4*>(sout + 4 * i) = o;
         __stcs(reinterpret_cast<float4*>(dst + 4 * i), o);
