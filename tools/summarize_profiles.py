@@ -7,7 +7,11 @@ out = "profiles"
 os.makedirs(out, exist_ok=True)
 
 # ---- 1. launch list: per-kernel totals and shares -------------------------------------------------
-rows = [r for r in csv.reader(open(os.path.join(src, "launches.csv"))) if len(r) > 10]
+lp = os.path.join(src, "launches.csv")
+if not os.path.exists(lp):
+    lp = os.path.join(src, "launches_ffcorr.csv")
+only_ffcorr = lp.endswith("launches_ffcorr.csv")
+rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
 hdr = rows[0]
 ki, mi, vi = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
 acc = collections.OrderedDict()
@@ -21,7 +25,7 @@ for r in rows[1:]:
 tot = sum(sum(v) for v in acc.values())
 mine = {k: v for k, v in acc.items() if "ffcorr" in k or any(s in k for s in ("lookup_kernel", "volume_gemm", "pyramid_", "operand_prepass", "pwc81"))}
 with open(os.path.join(out, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none" + (" -k <this repo's kernels only>" if only_ffcorr else "") + " python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n")
     f.write(f"# {n_launch} launches (warm-up step + timed step, + e2e steps), total {tot/1e3:.2f} ms of kernel time (cold-cache, serialised)\n")
     f.write(f"# share of this repo's kernels: {100*sum(sum(v) for v in mine.values())/tot:.2f}%\n")
     f.write(f"{'kernel':72s} {'n':>6s} {'mean_us':>10s} {'total_ms':>10s} {'share%':>8s}\n")
@@ -59,7 +63,7 @@ for rep in ("lookup_full", "build_full"):
             for w in WANT:
                 if w in idx:
                     f.write(f"  {w:82s} {d[idx[w]]:>16s} {u[idx[w]]}\n")
-            if "lookup_kernel" in name:
+            if "lookup" in name:
                 def num(key):
                     v = float(d[idx[key]].replace(",", ""))
                     unit = u[idx[key]].lower()
@@ -71,6 +75,10 @@ for rep in ("lookup_full", "build_full"):
 if traffic:
     json.dump(traffic, open(os.path.join(out, "lookup_traffic.json"), "w"), indent=1)
     print(traffic)
+for kb in ("kernel_bench_c2.jsonl", "kernel_bench_c4.jsonl", "kernel_bench_c1.jsonl"):
+    pth = os.path.join(src, kb)
+    if os.path.exists(pth):
+        open(os.path.join(out, f"{tag}_{kb}"), "w").write("".join(l for l in open(pth) if l.startswith("{")))
 b = os.path.join(src, "bench_r1.json")
 if os.path.exists(b):
     open(os.path.join(out, f"{tag}_bench.json"), "w").write(open(b).read())
