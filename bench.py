@@ -282,6 +282,9 @@ def run_gpu_arm(args, rank, world, local):
 
     peaks, peak_src = load_peaks()
     model = make_model(device, args.channels_last)
+    if args.update_cl:
+        model.flow_net.update_block.to(memory_format=torch.channels_last)
+        model.flow_net.update_channels_last = True
     meter = LaunchMeter()
     meter.install()
 
@@ -367,7 +370,7 @@ def run_gpu_arm(args, rank, world, local):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"FocusRAFT inference batch {b}/GPU, KITTI shape {H}x{W}, {ITERS} iters, B200",
                    "batch_per_gpu": b, "iters": ITERS, "corr_precision": "fp16 operands, fp32 accumulate", "pyramid_layout": "tiled 4x4" if meter.tiled else "row-major",
-                   "host_convs": "PyTorch/cuDNN TF32 (reference ALLOW_TF32)", "channels_last": bool(args.channels_last),
+                   "host_convs": "PyTorch/cuDNN TF32 (reference ALLOW_TF32)", "channels_last": bool(args.channels_last), "update_block_channels_last": bool(args.update_cl),
                    "l2": "per-step working set (2.3 GB pyramid + activations) >> 126 MB L2, no flush needed",
                    "sharding": "by image pair, no data-path collective"},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -396,6 +399,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--channels-last", dest="channels_last", action="store_true", default=False)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--update-nchw", dest="update_cl", action="store_false", default=True,
+                    help="run the GRU update block in NCHW instead of channels_last (host plumbing)")
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

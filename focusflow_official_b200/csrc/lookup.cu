@@ -472,7 +472,12 @@ template <int R>
 __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(const LookupTiledParams p) {
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;
-    constexpr int RS = W2 + 2;                    // odd row stride per query: conflict-free lane-per-query reads
+    // Row buffer of one query: the 16 columns of the 4x4 tile block shifted left by up to 3 (sub-tile offset
+    // of the window), so all four elements of every tile row are stored without per-element tests.
+    // Odd stride: lane-per-query reads are conflict-free.
+    constexpr int PADL = 3;
+    constexpr int RS = 19;                        // 3 + 16 columns of the 4x4 tile block, for every radius
+    static_assert(W2 <= 16 - 3, "window + sub-tile shift must fit in the 16 columns of the tile block");
     constexpr int ROWBUF = kTile * RS;
     static_assert(RS % 2 == 1, "row stride must be odd");
 
@@ -491,8 +496,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
 
     const int N = p.N;
     const int n0 = tile * kTile;
-    const int n = n0 + lane;
-    const bool valid = n < N;
+    // Lanes past the end of the last tile recompute the LAST query (identical values, identical address):
+    // benign duplicate stores instead of a per-store predicate in the hot loop.
+    const int n = min(n0 + lane, N - 1);
     const int lh = p.lh[level], lw = p.lw[level];
     const int th = p.th[level], tw = p.tw[level];
     const int map_elems = th * tw * 16;
@@ -500,12 +506,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     const float inv_scale = __int_as_float((127 - level) << 23);
 
     // ---------------- phase A (lane = query) ----------------
-    float cx = 0.f, cy = 0.f;
-    if (valid) {
-        const float* c = p.coords + (size_t)b * 2 * N + n;
-        cx = __ldg(c) * inv_scale;
-        cy = __ldg(c + N) * inv_scale;
-    }
+    const float* cptr = p.coords + (size_t)b * 2 * N + n;
+    const float cx = __ldg(cptr) * inv_scale;
+    const float cy = __ldg(cptr + N) * inv_scale;
     const float sx = (float)(lw - 1), sy = (float)(lh - 1);
     const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
     const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     int x_lo = 0, y_lo = 0;
     int my_base = 0;    // float offset of the window's first tile inside the query map: (ty0*tw + tx0)*16
     int my_pack = 0;    // bits [0,2) x_lo&3, [2,4) y_lo&3, bit 4+k: tile k = tyi*4+txi of the 4x4 block exists
-    if (valid && !wild) {
+    if (!wild) {
         x_lo = (int)floorf(ixf);
         y_lo = (int)floorf(iyf);
         const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
@@ -550,7 +553,6 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         py |= (unsigned)((dya + 1) & 3) << (2 * a);
         deviated |= (dxa != 0) | (dya != 0);
     }
-    if (!valid) deviated = false;
     const bool slow = __any_sync(0xffffffffu, deviated);
     auto ytap = [&](int bb, float& w0, float& w1) {
         const float iy = source_index(__fadd_rn(cy, (float)(bb - R)), sy);
@@ -562,65 +564,64 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     // ---------------- gather slots (lane = (query qj, tile column txi), j = 0..3) ----------------
     const int txi = lane & 3;
     const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
-    const float* gp[4];     // first float of tile column txi in the window's first tile row
-    int gsy[4];             // y_lo & 3 of the slot's query
+    const float* gp[4];     // running pointer: tile column txi, current window row
+    int gt[4];              // row inside the 4x4 tile block of the current window row: (y_lo & 3) + r
     int gtm[4];             // tile-exists bits of tile column txi: bit tyi
-    int gcm[4];             // element e of the slot lands inside the window row: bit e
-    int gso[4];             // float offset in a row buffer of element 0 (may be negative; masked)
+    int gso[4];             // float offset in a row buffer of the slot's first element (slack columns included)
+    const int last_q = N - 1 - n0;              // last real query of this tile (>= 0)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int qj = (lane >> 2) + 8 * j;
         const int base = __shfl_sync(0xffffffffu, my_base, qj);
         const int pk = __shfl_sync(0xffffffffu, my_pack, qj);
         const int sxo = pk & 3;
-        gsy[j] = (pk >> 2) & 3;
-        gp[j] = tile_base + ((int64_t)qj * map_elems + base + txi * 16);
+        gt[j] = (pk >> 2) & 3;
+        gp[j] = tile_base + ((int64_t)min(qj, last_q) * map_elems + base + txi * 16 + gt[j] * 4);
         gtm[j] = ((pk >> (4 + txi)) & 1) | (((pk >> (8 + txi)) & 1) << 1) | (((pk >> (12 + txi)) & 1) << 2) |
                  (((pk >> (16 + txi)) & 1) << 3);
-        const int c0 = 4 * txi - sxo;
-        gso[j] = qj * RS + c0;
-        int cm = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) cm |= (int)((c0 + e >= 0) && (c0 + e < W2)) << e;
-        gcm[j] = cm;
+        gso[j] = qj * RS + PADL + 4 * txi - sxo;
     }
-    auto load_row = [&](int r, float4 (&v)[4]) {
+    const int next_tile_row = tw * 16 - 12;     // from in-tile row 3 to row 0 of the tile below
+    // loads window row r (must be called with r = 0, 1, 2, ... in order: the pointers advance)
+    auto load_row = [&](float4 (&v)[4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int t = gsy[j] + r;               // row inside the 4x4 tile block
-            const bool ok = (gtm[j] >> (t >> 2)) & 1;
-            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(gp[j] + (t >> 2) * (tw * 16) + (t & 3) * 4))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool ok = (gtm[j] >> (gt[j] >> 2)) & 1;
+            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(gp[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gp[j] += ((gt[j] & 3) == 3) ? next_tile_row : 4;
+            ++gt[j];
         }
     };
     auto store_row = [&](float* buf, const float4 (&v)[4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float* d = buf + gso[j];
-            if (gcm[j] & 1) d[0] = v[j].x;
-            if (gcm[j] & 2) d[1] = v[j].y;
-            if (gcm[j] & 4) d[2] = v[j].z;
-            if (gcm[j] & 8) d[3] = v[j].w;
+            d[0] = v[j].x;
+            d[1] = v[j].y;
+            d[2] = v[j].z;
+            d[3] = v[j].w;
         }
     };
 
     const int CT = p.num_levels * K * K;
     float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
+    const int64_t stride_a = (int64_t)K * N;
     float4 v[4];
-    load_row(0, v);
+    load_row(v);
 
     if (!slow) {
         // fast path: tap (a, b) reads window (b, a); row r feeds outputs bb = r - 1 (as its lower row)
         float tprev[K];
 #pragma unroll
         for (int a = 0; a < K; ++a) tprev[a] = 0.f;
+        float* o_row = op;
 #pragma unroll 1
         for (int r = 0; r <= K; ++r) {
             float* buf = srow + (r & 1) * ROWBUF;
             store_row(buf, v);
             __syncwarp();
-            if (r < K) load_row(r + 1, v);          // in flight while this row is evaluated
-            const float* sq = buf + lane * RS;
+            if (r < K) load_row(v);                 // row r+1: in flight while this row is evaluated
+            const float* sq = buf + lane * RS + PADL;
             float vrow[K + 1];
 #pragma unroll
             for (int c = 0; c <= K; ++c) vrow[c] = sq[c];
@@ -630,12 +631,13 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
             if (r > 0) {
                 float w0, w1;
                 ytap(r - 1, w0, w1);
-                float* o_row = op + (int64_t)(r - 1) * N;
+                float* o_ptr = o_row;                       // channel a*K + (r-1); next a is K*N floats further
 #pragma unroll
                 for (int a = 0; a < K; ++a) {
-                    const float o = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
-                    if (valid) o_row[(int64_t)(a * K) * N] = o;
+                    *o_ptr = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
+                    o_ptr += stride_a;
                 }
+                o_row += N;
             }
 #pragma unroll
             for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
@@ -646,11 +648,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
 #pragma unroll 1
         for (int r = 0; r < W2; ++r) {
             float* buf = srow + (r & 1) * ROWBUF;
-            const float* prev = srow + ((r & 1) ^ 1) * ROWBUF + lane * RS;
+            const float* prev = srow + ((r & 1) ^ 1) * ROWBUF + lane * RS + PADL;
             store_row(buf, v);
             __syncwarp();
-            if (r + 1 < W2) load_row(r + 1, v);
-            const float* cur = buf + lane * RS;
+            if (r + 1 < W2) load_row(v);
+            const float* cur = buf + lane * RS + PADL;
 #pragma unroll 1
             for (int bb = 0; bb < K; ++bb) {
                 const int ryb = bb + (int)((py >> (2 * bb)) & 3u) - 1;
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
                         o = __fmaf_rn(v01, ne, o);
                         o = __fmaf_rn(v10, sw, o);
                         o = __fmaf_rn(v11, se, o);
-                        if (valid) op[(int64_t)(a * K + bb) * N] = o;
+                        op[(int64_t)(a * K + bb) * N] = o;
                     }
                 }
             }

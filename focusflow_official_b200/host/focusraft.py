@@ -231,6 +231,9 @@ class RAFTBody(nn.Module):
         self.update_block = UpdateBlock(self.corr_levels, self.corr_radius, self.hidden_dim)
         self.corr_block: Callable = B200CorrBlock
         self.corr_precision: Optional[str] = None
+        # host plumbing knob: run the GRU update block in channels_last (NHWC) so cuDNN's tensor-core
+        # kernels need no per-conv NCHW<->NHWC transposes; numerically the same convolutions
+        self.update_channels_last = False
 
     def freeze_bn(self):
         for m in self.modules():
@@ -259,13 +262,21 @@ class RAFTBody(nn.Module):
         if flow_init is not None:
             coords1 = coords1 + flow_init
 
+        cl = self.update_channels_last
+        if cl:
+            net = net.contiguous(memory_format=torch.channels_last)
+            inp = inp.contiguous(memory_format=torch.channels_last)
         predictions = []
         flow_up = None
         for it in range(iters):
             coords1 = coords1.detach()  # raft.py:216 -> the lookup never needs d/d coords
             corr = corr_fn(coords1)
+            flow = coords1 - coords0
+            if cl:
+                corr = corr.contiguous(memory_format=torch.channels_last)
+                flow = flow.contiguous(memory_format=torch.channels_last)
             need_up = (not test_mode) or it == iters - 1
-            net, up_mask, delta = self.update_block(net, inp, corr, coords1 - coords0, with_mask=need_up)
+            net, up_mask, delta = self.update_block(net, inp, corr, flow, with_mask=need_up)
             coords1 = coords1 + delta
             if need_up:
                 flow_up = convex_upsample(coords1 - coords0, up_mask)
