@@ -53,16 +53,7 @@ __device__ __forceinline__ float source_index(float x, float size_m1) {
 // |index| beyond this is outside every supported map (h, w <= 16384): all taps are zero.
 constexpr float kWildLimit = 3.0e4f;
 
-template <int LD>
-__device__ __forceinline__ float gather_load(const float* p) {
-    if (LD == 1) return *p;            // ld.global (L1-allocating)
-    if (LD == 2) return __ldcg(p);     // ld.global.cg (L2 only)
-    if (LD == 3) return __ldcs(p);     // ld.global.cs (streaming)
-    if (LD == 4) { float v; asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
-    return __ldg(p);                   // ld.global.nc
-}
-
-template <int R, int QU, int LD>
+template <int R, int QU>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const LookupParams p) {
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;        // window extent incl. the +-1 floor deviation of the round trip
@@ -149,7 +140,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
 #pragma unroll
             for (int j = 0; j < NLOAD; ++j) {
                 const bool ok = (msk & bits[j]) == bits[j];
-                v[u][j] = ok ? gather_load<LD>(pj[j] + qoff) : 0.0f;
+                v[u][j] = ok ? __ldg(pj[j] + qoff) : 0.0f;
             }
         }
 #pragma unroll
@@ -241,8 +232,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
 // Tiled ("T4") pyramid variant.  Levels are stored per query map as 4x4-pixel tiles of 64 contiguous
 // bytes with exact-zero padding (pyramid.cu), so zero padding of the sampler needs no per-element bounds
 // test -- only "does this tile exist" -- and a window costs ~10.6 64-byte requests instead of ~17.
-// Phases A and C are those of lookup_kernel; phase B gathers 16 tiles x 4 rows = 64 float4 slots per
-// window (2 per lane) and scatters each into the dense 11x11 smem window.
+// (A first version staged whole 11x11 windows like lookup_kernel: 15.5 KB of shared memory per warp, 0.081 ms at
+// config 2.  The row-streaming kernel below replaced it.)
 // ---------------------------------------------------------------------------------
 struct LookupTiledParams {
     const float* lvl[FFCORR_MAX_LEVELS];
@@ -255,236 +246,46 @@ struct LookupTiledParams {
     int blocks_per_batch;
 };
 
-template <int R>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_tiled_kernel(const LookupTiledParams p) {
-    constexpr int K = 2 * R + 1;
-    constexpr int W2 = K + 2;
-    constexpr int WIN = W2 * W2;
-    constexpr int QU = 4;
-    static_assert(W2 + 3 <= 16, "a window must fit in a 4x4 block of tiles");
-
-    extern __shared__ float smem[];
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    float* swin = smem + warp * (kTile * WIN);
-
-    int bid = blockIdx.x;
-    const int per_level = p.B * p.blocks_per_batch;
-    const int level = bid / per_level;
-    bid -= level * per_level;
-    const int b = bid / p.blocks_per_batch;
-    const int tile = (bid - b * p.blocks_per_batch) * kWarpsPerBlock + warp;
-    if (tile >= p.tiles_per_batch) return;
-
-    const int N = p.N;
-    const int n0 = tile * kTile;
-    const int n = n0 + lane;
-    const bool valid = n < N;
-    const int lh = p.lh[level], lw = p.lw[level];
-    const int th = p.th[level], tw = p.tw[level];
-    const int map_elems = th * tw * 16;
-    const float* __restrict__ lvl = p.lvl[level];
-    const float inv_scale = __int_as_float((127 - level) << 23);
-
-    // ---------------- phase A ----------------
-    float cx = 0.f, cy = 0.f;
-    if (valid) {
-        const float* c = p.coords + (size_t)b * 2 * N + n;
-        cx = __ldg(c) * inv_scale;
-        cy = __ldg(c + N) * inv_scale;
-    }
-    const float sx = (float)(lw - 1), sy = (float)(lh - 1);
-    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
-    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
-    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
-    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
-    const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
-                      !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
-    int x_lo = 0, y_lo = 0;
-    int my_base = 0;    // float offset of the window's first tile inside the query map: (ty0*tw + tx0)*16
-    int my_pack = 0;    // combo = (y_lo&3)*4 + (x_lo&3) in bits [0,4); bit 4+k: tile k = tyi*4+txi exists
-    if (valid && !wild) {
-        x_lo = (int)floorf(ixf);
-        y_lo = (int)floorf(iyf);
-        const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
-        my_base = (ty0 * tw + tx0) * 16;
-        int tmask = 0;
-#pragma unroll
-        for (int tyi = 0; tyi < 4; ++tyi)
-#pragma unroll
-            for (int txi = 0; txi < 4; ++txi)
-                if ((unsigned)(ty0 + tyi) < (unsigned)th && (unsigned)(tx0 + txi) < (unsigned)tw) tmask |= 1 << (tyi * 4 + txi);
-        my_pack = ((y_lo & 3) * 4 + (x_lo & 3)) | (tmask << 4);
-    }
-
-    // ---------------- phase B: tile gather ----------------
-    // slot s = lane + 32 j (j = 0, 1) = one row of one tile of the 4x4 tile block that covers the window:
-    // tile (tyi, txi) = ((s >> 4) & 3, (s >> 2) & 3), tile row iy = s & 3.  Everything that depends only on the
-    // slot is hoisted: its offset inside the map / the window, and 16-bit masks indexed by `combo` that say
-    // for which sub-tile shifts the slot (lmask) and each of its 4 elements (vmask) fall inside the window.
-    const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
-    const float* gptr[2];
-    int soff[2], tbit[2];
-    unsigned lmask[2], vmask[2][4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int s = lane + 32 * j;
-        const int tyi = (s >> 4) & 3, txi = (s >> 2) & 3, iy = s & 3;
-        gptr[j] = tile_base + (tyi * tw + txi) * 16 + iy * 4;
-        soff[j] = (4 * tyi + iy) * W2 + 4 * txi;
-        tbit[j] = 4 + tyi * 4 + txi;
-        unsigned rm = 0;                                     // bit sy: window row 4*tyi+iy-sy is inside [0, W2)
-#pragma unroll
-        for (int sy2 = 0; sy2 < 4; ++sy2) rm |= (unsigned)((4 * tyi + iy - sy2 >= 0) && (4 * tyi + iy - sy2 < W2)) << (4 * sy2);
-        lmask[j] = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            unsigned cm = 0;                                 // bit sx: window column 4*txi+e-sx is inside [0, W2)
-#pragma unroll
-            for (int sx2 = 0; sx2 < 4; ++sx2) cm |= (unsigned)((4 * txi + e - sx2 >= 0) && (4 * txi + e - sx2 < W2)) << sx2;
-            vmask[j][e] = rm * cm;                           // bit (sy*4 + sx)
-            lmask[j] |= vmask[j][e];
-        }
-    }
-    auto load_group = [&](int q0, float4 (&v)[QU][2], int (&pk)[QU]) {
-#pragma unroll
-        for (int u = 0; u < QU; ++u) {
-            const int base = __shfl_sync(0xffffffffu, my_base, q0 + u);
-            pk[u] = __shfl_sync(0xffffffffu, my_pack, q0 + u);
-            const int combo = pk[u] & 15;
-            const float* __restrict__ mq = gptr[0] + ((q0 + u) * map_elems + base);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const bool ok = ((pk[u] >> tbit[j]) & 1) && ((lmask[j] >> combo) & 1);
-                v[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(mq + (gptr[j] - gptr[0]))) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-    };
-    auto store_group = [&](int q0, const float4 (&v)[QU][2], const int (&pk)[QU]) {
-        float* sbase = swin + q0 * WIN;
-#pragma unroll
-        for (int u = 0; u < QU; ++u) {
-            const int combo = pk[u] & 15;
-            const int shift = (combo >> 2) * W2 + (combo & 3);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                float* d = sbase + u * WIN + soff[j] - shift;
-                if ((vmask[j][0] >> combo) & 1) d[0] = v[u][j].x;
-                if ((vmask[j][1] >> combo) & 1) d[1] = v[u][j].y;
-                if ((vmask[j][2] >> combo) & 1) d[2] = v[u][j].z;
-                if ((vmask[j][3] >> combo) & 1) d[3] = v[u][j].w;
-            }
-        }
-    };
-    {
-        // software pipeline: the loads of group g+1 are issued before group g is written to shared memory,
-        // so 2*QU windows' worth of 16-byte loads stay in flight per lane for the whole phase
-        float4 va[QU][2], vb[QU][2];
-        int pa[QU], pb[QU];
-        static_assert((kTile / QU) % 2 == 0, "ping-pong needs an even number of groups");
-        load_group(0, va, pa);
-#pragma unroll 1
-        for (int q0 = 0; q0 < kTile; q0 += 2 * QU) {
-            load_group(q0 + QU, vb, pb);
-            store_group(q0, va, pa);
-            if (q0 + 2 * QU < kTile) load_group(q0 + 2 * QU, va, pa);
-            store_group(q0 + QU, vb, pb);
-        }
-    }
-    __syncwarp();
-
-    // ---------------- phase C (identical to lookup_kernel) ----------------
-    int rx[K], ry[K];
-    float wx0[K], wx1[K], wy0[K], wy1[K];
-    bool deviated = false;
-#pragma unroll
-    for (int a = 0; a < K; ++a) {
-        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
-        const float fx = floorf(ix);
-        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
-        const float fy = floorf(iy);
-        wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
-        wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
-        wy1[a] = wild ? 0.f : __fsub_rn(iy, fy);
-        wy0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
-        rx[a] = wild ? a : min(max((int)fx - x_lo, 0), W2 - 2);
-        ry[a] = wild ? a : min(max((int)fy - y_lo, 0), W2 - 2);
-        deviated |= (rx[a] != a) | (ry[a] != a);
-    }
-    if (!valid) deviated = false;
-
-    const float* sq = swin + lane * WIN;
-    const int CT = p.num_levels * K * K;
-    float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
-    if (!__any_sync(0xffffffffu, deviated)) {
-        float tprev[K];
-#pragma unroll
-        for (int r = 0; r <= K; ++r) {
-            float vrow[K + 1];
-#pragma unroll
-            for (int c = 0; c <= K; ++c) vrow[c] = sq[r * W2 + c];
-            float tcur[K];
-#pragma unroll
-            for (int a = 0; a < K; ++a) tcur[a] = __fmaf_rn(wx1[a], vrow[a + 1], __fmul_rn(wx0[a], vrow[a]));
-            if (r > 0) {
-                const int bb = r - 1;
-#pragma unroll
-                for (int a = 0; a < K; ++a) {
-                    const float o = __fmaf_rn(wy1[bb], tcur[a], __fmul_rn(wy0[bb], tprev[a]));
-                    if (valid) op[(int64_t)(a * K + bb) * N] = o;
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
-        }
-    } else {
-#pragma unroll
-        for (int a = 0; a < K; ++a) {
-#pragma unroll
-            for (int bb = 0; bb < K; ++bb) {
-                const float* s = sq + ry[bb] * W2 + rx[a];
-                const float v00 = s[0], v01 = s[1], v10 = s[W2], v11 = s[W2 + 1];
-                const float nw = __fmul_rn(wx0[a], wy0[bb]);
-                const float ne = __fmul_rn(wx1[a], wy0[bb]);
-                const float sw = __fmul_rn(wx0[a], wy1[bb]);
-                const float se = __fmul_rn(wx1[a], wy1[bb]);
-                float o = __fmul_rn(v00, nw);
-                o = __fmaf_rn(v01, ne, o);
-                o = __fmaf_rn(v10, sw, o);
-                o = __fmaf_rn(v11, se, o);
-                if (valid) op[(int64_t)(a * K + bb) * N] = o;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------
-// Row-streaming variant of the tiled lookup: instead of staging whole 11x11 windows (15.5 KB of shared
-// memory per warp -> 14 warps per SM), the warp streams the 32 windows ROW BY ROW through a 3.3 KB double
-// buffer: gather window row r of all 32 queries (lane = (query, tile column), one 16-byte load per slot),
-// then every lane (= query) folds that row into its 9 running horizontal interpolants and emits the 9
-// outputs whose lower row it completes.  Shared memory no longer limits occupancy, the loads of row r+1
-// are in flight while row r is evaluated, and no slot is loaded that the window does not need.
+// Row-streaming tiled lookup: instead of staging whole 11x11 windows (15.5 KB of shared
+// memory per warp -> 14 warps per SM), the warp streams the 32 windows ROW BY ROW through a small ring of
+// row buffers filled by cp.async (LDGSTS: global -> shared without a register round trip, zero-fill for
+// tiles outside the map).  Gather role: lane = (query, tile column), one 16-byte piece of a tile row per
+// slot.  Evaluate role: lane = query; it folds window row r into its 9 running horizontal interpolants and
+// emits the 9 outputs whose lower row it completes.  kStreamStages - 1 rows are in flight per warp while
+// one is evaluated, so the memory system sees ~2 KB x (stages-1) x resident warps of outstanding requests.
 // ---------------------------------------------------------------------------------
 constexpr int kStreamWarps = 4;
+#ifndef FFCORR_STREAM_STAGES
+#define FFCORR_STREAM_STAGES 3
+#endif
+constexpr int kStreamStages = FFCORR_STREAM_STAGES;
+constexpr int kRowPitch = 20;     // floats per query row: the 16 columns of the 4x4 tile block + 4 (16-byte aligned)
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
 
 template <int R>
 __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(const LookupTiledParams p) {
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;
-    // Row buffer of one query: the 16 columns of the 4x4 tile block shifted left by up to 3 (sub-tile offset
-    // of the window), so all four elements of every tile row are stored without per-element tests.
-    // Odd stride: lane-per-query reads are conflict-free.
-    constexpr int PADL = 3;
-    constexpr int RS = 19;                        // 3 + 16 columns of the 4x4 tile block, for every radius
-    static_assert(W2 <= 16 - 3, "window + sub-tile shift must fit in the 16 columns of the tile block");
-    constexpr int ROWBUF = kTile * RS;
-    static_assert(RS % 2 == 1, "row stride must be odd");
+    constexpr int S = kStreamStages;
+    static_assert(S >= 2, "need at least a double buffer");
+    static_assert(W2 + 3 <= 16, "window + sub-tile shift must fit in the 16 columns of the tile block");
+    constexpr int ROWBUF = kTile * kRowPitch;
 
-    __shared__ float srow_all[kStreamWarps][2][ROWBUF];
+    __shared__ __align__(16) float sring[kStreamWarps][S][ROWBUF];
+    __shared__ float s_iy[kStreamWarps][K][kTile];      // y source index of tap bb, per query
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    float* srow = &srow_all[warp][0][0];
+    float* ring = &sring[warp][0][0];
+    float* siy = &s_iy[warp][0][0];
 
     int bid = blockIdx.x;
     const int per_level = p.B * p.blocks_per_batch;
@@ -533,9 +334,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         my_pack = (x_lo & 3) | ((y_lo & 3) << 2) | (tmask << 4);
     }
 
-    // x-tap weights stay in registers; the y-tap weights are recomputed per row step (keeps the register
-    // count low enough for ~20 resident warps).  Floor deviations of the round trip (-1/0/+1 per tap) are
-    // packed 2 bits per tap: px for columns, py for rows.
+    // x-tap weights stay in registers; the y source indices go to shared memory and the y-tap weights are
+    // rebuilt from them per row step.  Floor deviations of the round trip (-1/0/+1 per tap) are packed
+    // 2 bits per tap: px for columns, py for rows.
     float wx0[K], wx1[K];
     unsigned px = 0, py = 0;
     bool deviated = false;
@@ -545,6 +346,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         const float fx = floorf(ix);
         const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
         const float fy = floorf(iy);
+        siy[a * kTile + lane] = iy;
         wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
         wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
         const int dxa = wild ? 0 : min(max((int)fx - x_lo, 0), W2 - 2) - a;   // in {-1, 0, 1}
@@ -554,60 +356,74 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         deviated |= (dxa != 0) | (dya != 0);
     }
     const bool slow = __any_sync(0xffffffffu, deviated);
-    auto ytap = [&](int bb, float& w0, float& w1) {
-        const float iy = source_index(__fadd_rn(cy, (float)(bb - R)), sy);
+    auto ytap = [&](int bb, float& w0, float& w1) {      // only the lane's own entries: no sync needed
+        const float iy = siy[bb * kTile + lane];
         const float fy = floorf(iy);
         w1 = wild ? 0.f : __fsub_rn(iy, fy);
         w0 = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
     };
 
+    // Row buffer layout: query q owns kRowPitch floats at slot(q) * kRowPitch.  The tile block is stored
+    // unshifted (16-byte cp.async destinations); the evaluate role reads its 10 columns starting at x_lo & 3,
+    // so two queries collide on a bank when their slots are equal mod 8 AND their x_lo & 3 agree.  For a
+    // locally smooth flow x_lo advances by one every 2^level queries: slot = m*8 + g with m = (q >> level) & 3
+    // and g = the other three bits of q puts exactly the four queries with distinct x_lo & 3 on one phase.
+    const int lsh = min(level, 3);
+    auto slot_of = [lsh](int q) {
+        const int m = (q >> lsh) & 3;
+        const int g = (q & ((1 << lsh) - 1)) | ((q >> (lsh + 2)) << lsh);
+        return (m << 3) | g;
+    };
+
     // ---------------- gather slots (lane = (query qj, tile column txi), j = 0..3) ----------------
     const int txi = lane & 3;
     const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
-    const float* gp[4];     // running pointer: tile column txi, current window row
-    int gt[4];              // row inside the 4x4 tile block of the current window row: (y_lo & 3) + r
-    int gtm[4];             // tile-exists bits of tile column txi: bit tyi
-    int gso[4];             // float offset in a row buffer of the slot's first element (slack columns included)
+    int goff[4];        // float offset from tile_base of the slot's 16-byte piece in the current window row
+    unsigned gmask[4];  // bit r: the tile under window row r exists; bit 16+r: row r is the last row of its tile
+    unsigned gdst[4];   // byte offset of the slot inside a row buffer
     const int last_q = N - 1 - n0;              // last real query of this tile (>= 0)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int qj = (lane >> 2) + 8 * j;
         const int base = __shfl_sync(0xffffffffu, my_base, qj);
         const int pk = __shfl_sync(0xffffffffu, my_pack, qj);
-        const int sxo = pk & 3;
-        gt[j] = (pk >> 2) & 3;
-        gp[j] = tile_base + ((int64_t)min(qj, last_q) * map_elems + base + txi * 16 + gt[j] * 4);
-        gtm[j] = ((pk >> (4 + txi)) & 1) | (((pk >> (8 + txi)) & 1) << 1) | (((pk >> (12 + txi)) & 1) << 2) |
-                 (((pk >> (16 + txi)) & 1) << 3);
-        gso[j] = qj * RS + PADL + 4 * txi - sxo;
+        const int gy = (pk >> 2) & 3;
+        goff[j] = min(qj, last_q) * map_elems + base + txi * 16 + gy * 4;    // < 2^31 (host check: 32 maps)
+        const unsigned e = (unsigned)pk >> (4 + txi);
+        const unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
+                             (((e >> 12) & 1u) * 0xF000u);
+        gmask[j] = ((okT >> gy) & 0xFFFFu) | ((0x8888u >> gy) << 16);
+        gdst[j] = (unsigned)(slot_of(qj) * kRowPitch + 4 * txi) * 4u;
     }
     const int next_tile_row = tw * 16 - 12;     // from in-tile row 3 to row 0 of the tile below
-    // loads window row r (must be called with r = 0, 1, 2, ... in order: the pointers advance)
-    auto load_row = [&](float4 (&v)[4]) {
+    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
+    int rows_issued = 0;
+    uint32_t issue_saddr = ring_saddr;          // stage the next issued row lands in
+    // issues window row `rows_issued` (rows go out in order: the offsets advance); always commits a group
+    auto issue_row = [&](bool active) {
+        if (active) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool ok = (gtm[j] >> (gt[j] >> 2)) & 1;
-            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(gp[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
-            gp[j] += ((gt[j] & 3) == 3) ? next_tile_row : 4;
-            ++gt[j];
+            for (int j = 0; j < 4; ++j) {
+                const unsigned m = gmask[j] >> rows_issued;
+                const bool ok = m & 1u;
+                const float* src = tile_base + (ok ? goff[j] : 0);
+                cp_async16_zfill(issue_saddr + gdst[j], src, ok ? 16u : 0u);
+                goff[j] += (m & 0x10000u) ? next_tile_row : 4;
+            }
+            ++rows_issued;
+            issue_saddr += ROWBUF * 4;
+            if (issue_saddr == ring_saddr + S * ROWBUF * 4) issue_saddr = ring_saddr;
         }
-    };
-    auto store_row = [&](float* buf, const float4 (&v)[4]) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float* d = buf + gso[j];
-            d[0] = v[j].x;
-            d[1] = v[j].y;
-            d[2] = v[j].z;
-            d[3] = v[j].w;
-        }
+        cp_async_commit();
     };
 
     const int CT = p.num_levels * K * K;
     float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
     const int64_t stride_a = (int64_t)K * N;
-    float4 v[4];
-    load_row(v);
+    const int my_row = slot_of(lane) * kRowPitch + (x_lo & 3);
+
+#pragma unroll
+    for (int r = 0; r < S - 1; ++r) issue_row(true);       // W2 > S - 1 for every radius
 
     if (!slow) {
         // fast path: tap (a, b) reads window (b, a); row r feeds outputs bb = r - 1 (as its lower row)
@@ -615,13 +431,12 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
 #pragma unroll
         for (int a = 0; a < K; ++a) tprev[a] = 0.f;
         float* o_row = op;
+        const float* sq = ring + my_row;
 #pragma unroll 1
         for (int r = 0; r <= K; ++r) {
-            float* buf = srow + (r & 1) * ROWBUF;
-            store_row(buf, v);
-            __syncwarp();
-            if (r < K) load_row(v);                 // row r+1: in flight while this row is evaluated
-            const float* sq = buf + lane * RS + PADL;
+            cp_async_wait<S - 2>();                         // row r has landed (this lane's pieces) ...
+            __syncwarp();                                   // ... and everyone's; row r-1 is fully consumed
+            issue_row(r + S - 1 <= K);                      // refill the stage row r-1 occupied
             float vrow[K + 1];
 #pragma unroll
             for (int c = 0; c <= K; ++c) vrow[c] = sq[c];
@@ -641,18 +456,19 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
             }
 #pragma unroll
             for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
+            sq += ROWBUF;
+            if (sq == ring + my_row + S * ROWBUF) sq = ring + my_row;
         }
     } else {
         // exact general path (integer / near-integer coordinates): row r completes the outputs whose lower
-        // corner row is r, i.e. ry[bb] + 1 == r; both rows are in the double buffer.  ATen's nw/ne/sw/se order.
+        // corner row is r, i.e. ry[bb] + 1 == r; rows r-1 and r are both in the ring, so the refill of row
+        // r-1's stage waits until row r has been evaluated.  ATen's nw/ne/sw/se order.
+        const float* cur = ring + my_row;
+        const float* prev = cur;                            // unused at r = 0
 #pragma unroll 1
         for (int r = 0; r < W2; ++r) {
-            float* buf = srow + (r & 1) * ROWBUF;
-            const float* prev = srow + ((r & 1) ^ 1) * ROWBUF + lane * RS + PADL;
-            store_row(buf, v);
+            cp_async_wait<S - 2>();
             __syncwarp();
-            if (r + 1 < W2) load_row(v);
-            const float* cur = buf + lane * RS + PADL;
 #pragma unroll 1
             for (int bb = 0; bb < K; ++bb) {
                 const int ryb = bb + (int)((py >> (2 * bb)) & 3u) - 1;
@@ -675,7 +491,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
                     }
                 }
             }
-            __syncwarp();   // prev/cur reads done before the buffer pair is overwritten two steps later
+            __syncwarp();                                   // row r-1 no longer needed by anyone
+            issue_row(r + S - 1 < W2);
+            prev = cur;
+            cur += ROWBUF;
+            if (cur == ring + my_row + S * ROWBUF) cur = ring + my_row;
         }
     }
 }
@@ -688,18 +508,6 @@ int launch_lookup_tiled_stream(const LookupTiledParams& p0, cudaStream_t stream)
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
     lookup_tiled_stream_kernel<R><<<(unsigned)blocks, kStreamWarps * 32, 0, stream>>>(p);
     return check_launch("lookup_tiled_stream_kernel");
-}
-
-template <int R>
-int launch_lookup_tiled(const LookupTiledParams& p, cudaStream_t stream) {
-    constexpr int K = 2 * R + 1;
-    constexpr int WIN = (K + 2) * (K + 2);
-    const size_t smem = (size_t)kWarpsPerBlock * kTile * WIN * sizeof(float);
-    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
-    FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
-    lookup_tiled_kernel<R><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
-    return check_launch("lookup_tiled_kernel");
 }
 
 // ---------------------------------------------------------------------------------
@@ -751,7 +559,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_kernel(const LookupBwdParams p
     }
 }
 
-template <int R, int QU, int LD = 0>
+template <int R, int QU>
 int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
     constexpr int WIN = (K + 2) * (K + 2);
@@ -760,12 +568,12 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     int dev = 0;
     FFCORR_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_dev = dev;
     }
     const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup: grid too large (%lld blocks)", (long long)blocks);
-    lookup_kernel<R, QU, LD><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    lookup_kernel<R, QU><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
     return check_launch("lookup_kernel");
 }
 
@@ -797,19 +605,11 @@ extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const 
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
-    static const int qu = [] { const char* e = getenv("FFCORR_LOOKUP_QU"); return e ? atoi(e) : 8; }();
     switch (radius) {
         case 1: return launch_lookup<1, 4>(p, s);
         case 2: return launch_lookup<2, 4>(p, s);
         case 3: return launch_lookup<3, 4>(p, s);
-        default: {
-            static const int ld = [] { const char* e = getenv("FFCORR_LOOKUP_LD"); return e ? atoi(e) : 0; }();
-            if (ld == 1) return launch_lookup<4, 8, 1>(p, s);
-            if (ld == 2) return launch_lookup<4, 8, 2>(p, s);
-            if (ld == 3) return launch_lookup<4, 8, 3>(p, s);
-            if (ld == 4) return launch_lookup<4, 8, 4>(p, s);
-            return qu == 4 ? launch_lookup<4, 4>(p, s) : (qu == 2 ? launch_lookup<4, 2>(p, s) : launch_lookup<4, 8>(p, s));
-        }
+        default: return launch_lookup<4, 8>(p, s);
     }
 }
 
@@ -868,19 +668,10 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
-    static const int variant = [] { const char* e = getenv("FFCORR_LOOKUP_TILED"); return e ? atoi(e) : 1; }();
-    if (variant == 1) {
-        switch (radius) {
-            case 1: return launch_lookup_tiled_stream<1>(p, s);
-            case 2: return launch_lookup_tiled_stream<2>(p, s);
-            case 3: return launch_lookup_tiled_stream<3>(p, s);
-            default: return launch_lookup_tiled_stream<4>(p, s);
-        }
-    }
     switch (radius) {
-        case 1: return launch_lookup_tiled<1>(p, s);
-        case 2: return launch_lookup_tiled<2>(p, s);
-        case 3: return launch_lookup_tiled<3>(p, s);
-        default: return launch_lookup_tiled<4>(p, s);
+        case 1: return launch_lookup_tiled_stream<1>(p, s);
+        case 2: return launch_lookup_tiled_stream<2>(p, s);
+        case 3: return launch_lookup_tiled_stream<3>(p, s);
+        default: return launch_lookup_tiled_stream<4>(p, s);
     }
 }

@@ -64,8 +64,8 @@ int ffcorr_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /*
  * Device-wide hint for the DRAM->L2 fetch size (cudaLimitMaxL2FetchGranularity: 32, 64 or 128).
- * The lookup is a gather of 40-byte window rows; with the default 64-byte granularity about
- * half of every fetched pair of sectors is never used.  The host code sets 32 once per process.
+ * Diagnostic only: on B200 the measured DRAM traffic of the lookup did not change with it
+ * (the fetch unit stays 64 bytes), so the host code leaves the driver default alone.
  */
 int ffcorr_set_l2_fetch_granularity(int bytes);
 int ffcorr_get_l2_fetch_granularity(int* bytes);

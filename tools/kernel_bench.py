@@ -64,7 +64,8 @@ def raft_shapes(config):
             6: (8, 256, 56, 128), 7: (8, 256, 48, 160)}[config]  # 6/7: tile-aligned shapes (diagnosis)
 
 
-def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, verbose=False, warmup=3):
+def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, verbose=False, warmup=3, smooth=False,
+                 only=None):
     import focusflow_official_b200 as ff
     from focusflow_official_b200 import _lib
 
@@ -84,7 +85,14 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     ptrs = _lib.ptr_array(levels)
     stream = _lib.current_stream()
-    coords = ff.coords_grid(b, h, w, dev) + torch.randn(b, 2, h, w, device=dev) * sigma
+    if smooth:
+        # a flow field like the model produces: a low-frequency displacement plus sub-pixel jitter
+        ys = torch.linspace(0, 3.14159, h, device=dev).view(1, 1, h, 1)
+        xs = torch.linspace(0, 6.28318, w, device=dev).view(1, 1, 1, w)
+        flow = torch.cat([5.3 * torch.sin(xs + ys), 2.7 * torch.cos(xs - ys)], 1).expand(b, 2, h, w)
+        coords = ff.coords_grid(b, h, w, dev) + flow + torch.randn(b, 2, h, w, device=dev) * 0.25
+    else:
+        coords = ff.coords_grid(b, h, w, dev) + torch.randn(b, 2, h, w, device=dev) * sigma
     out = torch.empty(b, nl * 81, h, w, device=dev)
     flush = L2Flusher(dev)
 
@@ -123,6 +131,12 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         todo += [("volume_tiled", k_volume_t, vol_bytes, vol_flops), ("pyramid_tiled", k_pyramid_t, pyr_bytes, 0.0),
                  ("lookup_tiled", k_lookup_t, look_bytes, 0.0)]
     for name, fn, byts, flops in todo:
+        if only and not any(o in name for o in only):
+            if name in ("volume_tiled", "pyramid_tiled") and any("tiled" in o for o in only):
+                fn()   # the tiled lookup needs a built tiled pyramid
+            elif name in ("volume", "pyramid"):
+                fn()
+            continue
         med, best = time_cuda(fn, iters=iters, warmup=warmup, flush=flush)
         gbs = byts / (med * 1e-3) / 1e9
         rec = {"kernel": name, "config": config, "ms": round(med, 4), "ms_min": round(best, 4),
@@ -184,14 +198,18 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--sigma", type=float, default=3.0)
+    ap.add_argument("--smooth", action="store_true", help="smooth synthetic flow instead of iid noise")
+    ap.add_argument("--only", default=None, help="comma-separated substrings of kernel names to time")
     ap.add_argument("--pwc", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--all-precisions", action="store_true")
     a = ap.parse_args()
     if a.all_precisions:
         for pr in ("fp16", "tf32", "bf16x3"):
-            time_kernels(a.config, a.iters, pr, sigma=a.sigma, verbose=True, warmup=a.warmup)
+            time_kernels(a.config, a.iters, pr, sigma=a.sigma, verbose=True, warmup=a.warmup, smooth=a.smooth,
+                         only=a.only.split(',') if a.only else None)
     else:
-        time_kernels(a.config, a.iters, a.precision, sigma=a.sigma, verbose=True, warmup=a.warmup)
+        time_kernels(a.config, a.iters, a.precision, sigma=a.sigma, verbose=True, warmup=a.warmup, smooth=a.smooth,
+                         only=a.only.split(',') if a.only else None)
     if a.pwc:
         time_pwc(a.iters, verbose=True, warmup=a.warmup)
