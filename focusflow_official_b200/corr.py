@@ -77,8 +77,12 @@ def tiled_supported(h: int, w: int, num_levels: int) -> bool:
     return bool(_lib.lib().ffcorr_tiled_supported(num_levels, h, w))
 
 
-def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, precision: int) -> List[torch.Tensor]:
-    """Volume + pyramid in the tiled layout: level i is [B*h*w, tiled_map_elems(h, w, i)]."""
+def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, precision: int,
+                              fused: bool = True) -> List[torch.Tensor]:
+    """Volume + pyramid in the tiled layout: level i is [B*h*w, tiled_map_elems(h, w, i)].
+
+    fused=True (default): one GEMM launch writes every level (ffcorr_build_tiled_f32); fused=False: the GEMM
+    writes level 0 and the standalone pooling kernel re-reads it (bit-identical results, kept for tests)."""
     b, d, h, w = fmap1.shape
     L = _lib.lib()
     levels = [torch.empty((b * h * w, _tiled_elems(h, w, i)), device=fmap1.device, dtype=torch.float32)
@@ -86,6 +90,10 @@ def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_leve
     ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
     ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
     stream = _lib.current_stream()
+    if fused:
+        _lib.check(L.ffcorr_build_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), _lib.ptr_array(levels), num_levels, b, d, h, w,
+                                            precision, ws.data_ptr(), ws_bytes, stream), "ffcorr_build_tiled_f32")
+        return levels
     _lib.check(L.ffcorr_volume_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), levels[0].data_ptr(), b, d, h, w, precision,
                                          ws.data_ptr(), ws_bytes, stream), "ffcorr_volume_tiled_f32")
     _lib.check(L.ffcorr_pyramid_tiled_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream),
@@ -127,10 +135,10 @@ def tile_levels(levels) -> List[torch.Tensor]:
     return out
 
 
-def tiled_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None) -> List[torch.Tensor]:
+def tiled_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None, fused: bool = True) -> List[torch.Tensor]:
     """Volume + pyramid in the tiled layout (inference only)."""
     fmap1, fmap2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
-    return _volume_pyramid_tiled_raw(fmap1, fmap2, num_levels, _precision_code(precision))
+    return _volume_pyramid_tiled_raw(fmap1, fmap2, num_levels, _precision_code(precision), fused)
 
 
 def lookup_tiled(tiled_levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None) -> torch.Tensor:

@@ -76,6 +76,11 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int
                  ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -150,7 +155,8 @@ constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 constexpr int SMEM_A_STAGE = BM * BK_BYTES;   // 16 KB
 constexpr int SMEM_B_STAGE = BN * BK_BYTES;   // 32 KB
 constexpr int SMEM_STORE_BUF = 32 * STORE_COLS * 4;  // 4 KB: 32 rows x 128 B
-constexpr int SMEM_STORE = EPI_WARPS * STORE_BUFS * SMEM_STORE_BUF;  // 64 KB
+constexpr int FUSED_BUFS = STORE_BUFS + 1; // fused build: + one level-1 box per epilogue warp
+constexpr int SMEM_STORE = EPI_WARPS * FUSED_BUFS * SMEM_STORE_BUF;  // 80 KB (the plain volume kernel uses 64 KB of it)
 constexpr int SMEM_OFF_A = SMEM_STORE;
 constexpr int SMEM_OFF_B = SMEM_OFF_A + STAGES * SMEM_A_STAGE;
 constexpr int SMEM_OFF_BAR = SMEM_OFF_B + STAGES * SMEM_B_STAGE;
@@ -181,10 +187,30 @@ struct GemmParams {
     float* out;     // only used by the non-TMA epilogue (N % 4 != 0)
 };
 
-template <bool TF32, bool TMA_STORE, bool DIV>
+// Fused pyramid build (ffcorr_build_tiled_f32): the GEMM's N order is made of 16x16-pixel SUPER-GROUPS
+// (4x4 tiles of 4x4 pixels; one 256-column UMMA tile each), chunk c of the epilogue = tile row c of the
+// super-group, so a thread (= one query) holds everything the 2x2 poolings of levels 1..3 need in registers:
+//   level 1: every level-0 tile pools to a 2x2 patch; two chunks complete two level-1 tiles (128 B)
+//   level 2: one value per level-0 tile; the four chunks complete one level-2 tile (64 B)
+//   level 3: one 2x2 patch per super-group (a quarter of a level-3 tile)
+// The memory layout of every level stays [tile row][tile column][4][4]; only the GEMM column order changes.
+struct FusedParams {
+    int levels;                 // levels written (2..4)
+    int sgw, sgh;               // super-groups per row / column of the level-0 map
+    int th0, tw0, th1, tw1;     // tiles of levels 0 and 1 (TMA clips, these only skip empty boxes)
+    int lh1, lw1, lh2, lw2, lh3, lw3;   // true level sizes (floor semantics of avg_pool2d)
+    int th2, tw2, th3, tw3;
+    int map2, map3;             // floats per query map, levels 2 and 3
+    float* l2;
+    float* l3;
+};
+
+template <bool TF32, bool TMA_STORE, bool DIV, bool FUSED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_c, const GemmParams p, const uint32_t idesc) {
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_l1,
+                   const GemmParams p, const FusedParams fp, const uint32_t idesc) {
+    static_assert(!FUSED || TMA_STORE, "the fused build stores through TMA");
     // Index the extern array directly: rounding the pointer up through uintptr_t loses the shared
     // address space (generic ST.E instead of STS in the epilogue).  128B-swizzle needs 1024-byte alignment.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -204,6 +230,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if (TMA_STORE) tma_prefetch_desc(&tmap_c);
+        if (FUSED) tma_prefetch_desc(&tmap_l1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -283,8 +310,11 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
         const int ew = warp - 2;                      // private store ring
-        uint8_t* my_bufs = smem + (size_t)ew * STORE_BUFS * SMEM_STORE_BUF;
-        const uint32_t my_bufs_u32 = smem_base + (uint32_t)(ew * STORE_BUFS * SMEM_STORE_BUF);
+        constexpr int MY_BUFS = FUSED ? FUSED_BUFS : STORE_BUFS;
+        uint8_t* my_bufs = smem + (size_t)ew * MY_BUFS * SMEM_STORE_BUF;
+        const uint32_t my_bufs_u32 = smem_base + (uint32_t)(ew * MY_BUFS * SMEM_STORE_BUF);
+        float pe[16];    // fused: level-1 values of the even chunk (rows 0-1 of the level-1 tiles being assembled)
+        float q2[16];    // fused: level-2 tile of this super-group, [chunk][tile]
         int pair = 0;   // store ring: 2 pairs of 32x32 boxes per warp
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -302,7 +332,119 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             // chunk c is scaled, staged (two 128B-swizzled 32x32 boxes, ONE proxy fence) and handed to TMA.
             auto process = [&](uint32_t (&v)[64], int c) {
                 const int col0 = n0 + c * 64;
-                if (TMA_STORE) {
+                if (FUSED) {
+                    if (row0 >= p.N) return;                      // warp-uniform
+                    const int nt = n0 / BN;
+                    const int sgy = nt / fp.sgw, sgx = nt - sgy * fp.sgw;
+                    const int ty = sgy * 4 + c;                   // level-0 tile row of this chunk
+                    float f[64];
+#pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        f[i] = DIV ? __fdiv_rn(__uint_as_float(v[i]), p.divisor) : __uint_as_float(v[i]) * p.scale;
+                    if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();
+                    __syncwarp();
+                    // ---- level 0: tiles (ty, 4 sgx .. 4 sgx + 3) = 256 contiguous bytes per query, two 32x32 boxes ----
+                    const bool l0_any = ty < fp.th0;
+                    if (l0_any) {
+                        uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int i0 = hlf * 32 + 4 * j;
+                                *reinterpret_cast<float4*>(dst + hlf * SMEM_STORE_BUF + ((j ^ (lane & 7)) << 4)) =
+                                    make_float4(f[i0], f[i0 + 1], f[i0 + 2], f[i0 + 3]);
+                            }
+                    }
+                    // ---- level 1: 2x2 means inside every tile; ATen's (((a+b)+c)+d)/4 order; zero beyond the floor size ----
+                    float p1[16];   // [tile t][py][px]
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int py = 0; py < 2; ++py)
+#pragma unroll
+                            for (int px = 0; px < 2; ++px) {
+                                const int i0 = t * 16 + py * 8 + px * 2;
+                                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(f[i0], f[i0 + 1]), f[i0 + 4]), f[i0 + 5]);
+                                const bool ok = (ty * 2 + py < fp.lh1) && ((sgx * 4 + t) * 2 + px < fp.lw1);
+                                p1[t * 4 + py * 2 + px] = ok ? __fmul_rn(sum, 0.25f) : 0.0f;
+                            }
+                    // ---- level 2: one value per level-0 tile ----
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float sum = __fadd_rn(__fadd_rn(__fadd_rn(p1[t * 4], p1[t * 4 + 1]), p1[t * 4 + 2]), p1[t * 4 + 3]);
+                        const bool ok = (ty < fp.lh2) && (sgx * 4 + t < fp.lw2);
+                        q2[c * 4 + t] = ok ? __fmul_rn(sum, 0.25f) : 0.0f;
+                    }
+                    const bool odd = c & 1;
+                    bool l1_any = false;
+                    if (odd) {
+                        // level-1 tiles (sgy*2 + c/2, sgx*2 .. +1): rows 0-1 from the even chunk, rows 2-3 from this one
+                        const int ty1 = sgy * 2 + (c >> 1);
+                        l1_any = (ty1 < fp.th1) && (sgx * 2 < fp.tw1);
+                        if (l1_any) {
+                            uint8_t* dst = my_bufs + (size_t)STORE_BUFS * SMEM_STORE_BUF + lane * 128;
+#pragma unroll
+                            for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+                                for (int rr = 0; rr < 4; ++rr) {
+                                    const float* src = (rr < 2) ? pe : p1;
+                                    const int py = rr & 1;
+                                    const float4 q = make_float4(src[(2 * tt) * 4 + py * 2], src[(2 * tt) * 4 + py * 2 + 1],
+                                                                 src[(2 * tt + 1) * 4 + py * 2], src[(2 * tt + 1) * 4 + py * 2 + 1]);
+                                    const int j = tt * 4 + rr;
+                                    *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = q;
+                                }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pe[i] = p1[i];
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (l0_any) {
+                            const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
+                            tma_store_4d(&tmap_c, src, sgx * 64, ty, row0, b);
+                            if (sgx * 4 + 2 < fp.tw0) tma_store_4d(&tmap_c, src + SMEM_STORE_BUF, sgx * 64 + 32, ty, row0, b);
+                        }
+                        if (l1_any)
+                            tma_store_4d(&tmap_l1, my_bufs_u32 + (uint32_t)(STORE_BUFS * SMEM_STORE_BUF), sgx * 32,
+                                         sgy * 2 + (c >> 1), row0, b);
+                        tma_store_commit();
+                    }
+                    pair = (pair + 1) % STORE_PAIRS;
+                    const int row = row0 + lane;
+                    // ---- level 3: a 2x2 patch per super-group, one row per chunk pair; written directly (8-byte pieces) ----
+                    if (odd && fp.levels >= 4 && row < p.N) {
+                        const int ty3 = sgy >> 1, tx3 = sgx >> 1;
+                        if (ty3 < fp.th3 && tx3 < fp.tw3) {
+                            const int ce = (c - 1) * 4, co = c * 4;
+                            float2 o;
+                            o.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q2[ce], q2[ce + 1]), q2[co]), q2[co + 1]), 0.25f);
+                            o.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q2[ce + 2], q2[ce + 3]), q2[co + 2]), q2[co + 3]), 0.25f);
+                            const int y3 = sgy * 2 + (c >> 1);
+                            if (!(y3 < fp.lh3 && sgx * 2 < fp.lw3)) o.x = 0.0f;
+                            if (!(y3 < fp.lh3 && sgx * 2 + 1 < fp.lw3)) o.y = 0.0f;
+                            float* d3 = fp.l3 + ((int64_t)b * p.N + row) * fp.map3 + (ty3 * fp.tw3 + tx3) * 16 +
+                                        ((sgy & 1) * 2 + (c >> 1)) * 4 + (sgx & 1) * 2;
+                            *reinterpret_cast<float2*>(d3) = o;
+                            // quarters of this level-3 tile whose super-group does not exist stay exact zeros
+                            const bool ghost_x = (sgx == fp.sgw - 1) && !(sgx & 1);
+                            const bool ghost_y = (sgy == fp.sgh - 1) && !(sgy & 1);
+                            const float2 z = make_float2(0.0f, 0.0f);
+                            if (ghost_x) *reinterpret_cast<float2*>(d3 + 2) = z;
+                            if (ghost_y) *reinterpret_cast<float2*>(d3 + 8) = z;
+                            if (ghost_x && ghost_y) *reinterpret_cast<float2*>(d3 + 10) = z;
+                        }
+                    }
+                    // ---- level 2: the complete 4x4 tile of this super-group, 64 contiguous bytes per query ----
+                    if (c == 3 && fp.levels >= 3 && row < p.N && sgy < fp.th2 && sgx < fp.tw2) {
+                        float4* d2 = reinterpret_cast<float4*>(fp.l2 + ((int64_t)b * p.N + row) * fp.map2 + (sgy * fp.tw2 + sgx) * 16);
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) d2[rr] = make_float4(q2[rr * 4], q2[rr * 4 + 1], q2[rr * 4 + 2], q2[rr * 4 + 3]);
+                    }
+                } else if (TMA_STORE) {
                     if (row0 >= p.N || col0 >= p.Ncols) return;   // warp-uniform: both boxes outside
                     if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();   // the pair used STORE_PAIRS groups ago has been read
                     __syncwarp();
@@ -394,11 +536,13 @@ __device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
 // Tiled ("T4") target order for the B operand: row n' of the staged operand is pixel
 // (y, x) = (4*ty + iy, 4*tx + ix) with n' = (ty*TW + tx)*16 + iy*4 + ix, zero rows for the padding up to
 // multiples of 4, so the GEMM writes every query's map directly as 4x4-pixel tiles of 64 contiguous bytes.
+// Super-group order (enabled == 2, fused pyramid build): n' = sg*256 + c*64 + t*16 + iy*4 + ix is pixel
+// (y, x) = (16*sgy + 4*c + iy, 16*sgx + 4*t + ix), sg = sgy*SGW + sgx; padding up to multiples of 16.
 struct TiledB {
-    int enabled;
+    int enabled;   // 0: row-major pixels, 1: 4x4 tiles in row-major tile order, 2: 16x16 super-groups of 4x4 tiles
     int h, w;      // feature-map size
-    int tw;        // tiles per row: ceil(w / 4)
-    int np;        // padded pixel count: ceil4(h) * ceil4(w)
+    int tw;        // enabled == 1: tiles per row, ceil(w / 4); enabled == 2: super-groups per row, ceil(w / 16)
+    int np;        // padded pixel count = rows of the staged operand
 };
 
 template <int MODE>
@@ -425,9 +569,18 @@ __global__ void __launch_bounds__(256) operand_prepass_kernel(const float* __res
         if (d < D && n < Nout) {
             int src_n = n, lim = N - n;            // source pixel of output row n, and how many of the 4 exist
             if (tiled) {                           // n is a multiple of 4: one row of one 4x4 tile
-                const int t = n >> 4, iy = (n >> 2) & 3;
-                const int ty = t / tb.tw, tx = t - ty * tb.tw;
-                const int y = 4 * ty + iy, x = 4 * tx;
+                int y, x;
+                if (tb.enabled == 2) {
+                    const int sg = n >> 8, c = (n >> 6) & 3, t = (n >> 4) & 3, iy = (n >> 2) & 3;
+                    const int sgy = sg / tb.tw, sgx = sg - sgy * tb.tw;
+                    y = 16 * sgy + 4 * c + iy;
+                    x = 16 * sgx + 4 * t;
+                } else {
+                    const int t = n >> 4, iy = (n >> 2) & 3;
+                    const int ty = t / tb.tw, tx = t - ty * tb.tw;
+                    y = 4 * ty + iy;
+                    x = 4 * tx;
+                }
                 src_n = y * tb.w + x;
                 lim = (y < tb.h) ? tb.w - x : 0;
             }
@@ -600,14 +753,19 @@ using namespace ffcorr;
 extern "C" size_t ffcorr_volume_workspace_bytes(int B, int D, int h, int w, int precision) {
     PrecInfo pi;
     if (!prec_info(precision, &pi) || B <= 0 || D <= 0 || h <= 0 || w <= 0) return 0;
-    const size_t Np = align_up((size_t)h, 4) * align_up((size_t)w, 4);   // >= h*w; covers the tiled layout too
+    const size_t Np = align_up((size_t)h, 16) * align_up((size_t)w, 16); // >= h*w; covers the tiled and super-group orders too
     const size_t Dp = align_up((size_t)D, pi.k_align);
     const size_t one = align_up((size_t)B * Np * Dp * pi.k_mult * pi.elem_bytes, 256);
     return 2 * one;
 }
 
+enum : int { OUT_ROWMAJOR = 0, OUT_TILED = 1, OUT_FUSED_PYRAMID = 2 };
+
 static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w, int precision,
-                       void* workspace, size_t workspace_bytes, void* stream, bool tiled) {
+                       void* workspace, size_t workspace_bytes, void* stream, int out_mode, float* const* lvl = nullptr,
+                       int num_levels = 1) {
+    const bool tiled = out_mode != OUT_ROWMAJOR;
+    const bool fused = out_mode == OUT_FUSED_PYRAMID;
     FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume: bad shape B=%d D=%d h=%d w=%d", B, D, h, w);
     FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "volume: h*w=%lld too large", (long long)h * w);
     if (B == 0) return FFCORR_OK;  // empty batch: pointers may legitimately be null
@@ -640,11 +798,11 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
 
     // ---- 1. operand pre-pass ----
     TiledB tlb{};
-    tlb.enabled = tiled ? 1 : 0;
+    tlb.enabled = fused ? 2 : (tiled ? 1 : 0);
     tlb.h = h;
     tlb.w = w;
-    tlb.tw = ceil_div(w, 4);
-    tlb.np = ceil_div(h, 4) * 4 * tlb.tw * 4;
+    tlb.tw = fused ? ceil_div(w, 16) : ceil_div(w, 4);
+    tlb.np = fused ? ceil_div(h, 16) * tlb.tw * 256 : ceil_div(h, 4) * 4 * tlb.tw * 4;
     const int Ncols = tiled ? tlb.np : N;       // columns of the volume == rows of the staged B operand
     {
         dim3 grid(ceil_div(Ncols, PP_N), Dp / PP_D, 2 * B);
@@ -659,7 +817,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     }
 
     // ---- 2. tensor maps ----
-    CUtensorMap ta, tb, tc;
+    CUtensorMap ta, tb, tc, tl1;
     const bool tf32 = precision == FFCORR_PREC_TF32;
     const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                         : (precision == FFCORR_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -669,7 +827,43 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     if (int rc = encode_3d(&ta, dt, pi.elem_bytes, opA, Kt, N, B, row_bytes, row_bytes * N, box_k, BM, "A")) return rc;
     if (int rc = encode_3d(&tb, dt, pi.elem_bytes, opB, Kt, Ncols, B, row_bytes, row_bytes * Ncols, box_k, BN, "B")) return rc;
     const bool tma_store = (Ncols % 4 == 0);
-    if (tma_store) {
+    FusedParams fp{};
+    if (fused) {
+        // 4-D views [B][N][tile row][tile-row floats] of levels 0 and 1; boxes of 32 queries x 128 bytes
+        const int th0 = ceil_div(h, 4), tw0 = ceil_div(w, 4);
+        const int lh1 = h >> 1, lw1 = w >> 1;
+        const int th1 = ceil_div(lh1, 4), tw1 = ceil_div(lw1, 4);
+        const uint32_t box[4] = {32, 1, 32, 1};
+        {
+            const uint64_t dims[4] = {(uint64_t)tw0 * 16, (uint64_t)th0, (uint64_t)N, (uint64_t)B};
+            const uint64_t map_b = (uint64_t)th0 * tw0 * 64;
+            const uint64_t strides[3] = {(uint64_t)tw0 * 64, map_b, map_b * N};
+            if (int rc = encode_tensor_map(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl[0], dims, strides, box,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, "L0"))
+                return rc;
+        }
+        {
+            const uint64_t dims[4] = {(uint64_t)tw1 * 16, (uint64_t)th1, (uint64_t)N, (uint64_t)B};
+            const uint64_t map_b = (uint64_t)th1 * tw1 * 64;
+            const uint64_t strides[3] = {(uint64_t)tw1 * 64, map_b, map_b * N};
+            if (int rc = encode_tensor_map(&tl1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl[1], dims, strides, box,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, "L1"))
+                return rc;
+        }
+        fp.levels = num_levels;
+        fp.sgw = tlb.tw;
+        fp.sgh = ceil_div(h, 16);
+        fp.th0 = th0; fp.tw0 = tw0; fp.th1 = th1; fp.tw1 = tw1;
+        fp.lh1 = lh1; fp.lw1 = lw1;
+        fp.lh2 = h >> 2; fp.lw2 = w >> 2;
+        fp.lh3 = h >> 3; fp.lw3 = w >> 3;
+        fp.th2 = ceil_div(fp.lh2, 4); fp.tw2 = ceil_div(fp.lw2, 4);
+        fp.th3 = ceil_div(fp.lh3, 4); fp.tw3 = ceil_div(fp.lw3, 4);
+        fp.map2 = fp.th2 * fp.tw2 * 16;
+        fp.map3 = fp.th3 * fp.tw3 * 16;
+        fp.l2 = num_levels >= 3 ? lvl[2] : nullptr;
+        fp.l3 = num_levels >= 4 ? lvl[3] : nullptr;
+    } else if (tma_store) {
         if (int rc = encode_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, Ncols, N, B, (uint64_t)Ncols * 4,
                                (uint64_t)N * Ncols * 4, STORE_COLS, 32, "C"))
             return rc;
@@ -697,33 +891,57 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     const int64_t num_tiles = (int64_t)p.tiles_m * p.tiles_n * B;
     FFCORR_REQUIRE(num_tiles < (1ll << 31), FFCORR_EINVAL, "volume: too many tiles");
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-#define FF_GEMM(TF, TS, DV)                                                                                  \
-    do {                                                                                                     \
-        if (int rc = set_smem(volume_gemm_kernel<TF, TS, DV>, SMEM_GEMM_TOTAL)) return rc;                   \
-        volume_gemm_kernel<TF, TS, DV><<<grid, GEMM_THREADS, SMEM_GEMM_TOTAL, s>>>(ta, tb, tc, p, idesc);    \
+#define FF_GEMM_F(TF, TS, DV, FU)                                                                                     \
+    do {                                                                                                              \
+        if (int rc = set_smem(volume_gemm_kernel<TF, TS, DV, FU>, SMEM_GEMM_TOTAL)) return rc;                        \
+        volume_gemm_kernel<TF, TS, DV, FU><<<grid, GEMM_THREADS, SMEM_GEMM_TOTAL, s>>>(ta, tb, tc, tl1, p, fp, idesc); \
     } while (0)
+#define FF_GEMM(TF, TS, DV) FF_GEMM_F(TF, TS, DV, false)
 #define FF_GEMM_DV(TF, TS)            \
     do {                              \
         if (p.use_div) FF_GEMM(TF, TS, true); \
         else FF_GEMM(TF, TS, false);  \
     } while (0)
-    if (tf32 && tma_store) FF_GEMM_DV(true, true);
+    if (fused) {
+        if (tf32) { if (p.use_div) FF_GEMM_F(true, true, true, true); else FF_GEMM_F(true, true, false, true); }
+        else      { if (p.use_div) FF_GEMM_F(false, true, true, true); else FF_GEMM_F(false, true, false, true); }
+    }
+    else if (tf32 && tma_store) FF_GEMM_DV(true, true);
     else if (tf32) FF_GEMM_DV(true, false);
     else if (tma_store) FF_GEMM_DV(false, true);
     else FF_GEMM_DV(false, false);
 #undef FF_GEMM_DV
 #undef FF_GEMM
+#undef FF_GEMM_F
     return check_launch("volume_gemm_kernel");
 }
 
 extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
                                  int precision, void* workspace, size_t workspace_bytes, void* stream) {
-    return volume_impl(fmap1, fmap2, lvl0, B, D, h, w, precision, workspace, workspace_bytes, stream, false);
+    return volume_impl(fmap1, fmap2, lvl0, B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_ROWMAJOR);
 }
 
 extern "C" int ffcorr_volume_tiled_f32(const float* fmap1, const float* fmap2, float* lvl0_tiled, int B, int D, int h, int w,
                                        int precision, void* workspace, size_t workspace_bytes, void* stream) {
-    return volume_impl(fmap1, fmap2, lvl0_tiled, B, D, h, w, precision, workspace, workspace_bytes, stream, true);
+    return volume_impl(fmap1, fmap2, lvl0_tiled, B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_TILED);
+}
+
+extern "C" int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, float* const* lvl, int num_levels, int B, int D,
+                                      int h, int w, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    FFCORR_REQUIRE(lvl != nullptr, FFCORR_EINVAL, "build_tiled: null level table");
+    if (int rc = check_levels(num_levels, h, w, "build_tiled")) return rc;
+    FFCORR_REQUIRE(ffcorr_tiled_supported(num_levels, h, w), FFCORR_EINVAL,
+                   "build_tiled: %dx%d with %d levels is outside the tiled path (use the row-major entry points)", h, w, num_levels);
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "build_tiled: B=%d", B);
+    if (B == 0) return FFCORR_OK;
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "build_tiled: lvl[%d] is null", i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "build_tiled: lvl[%d] must be 16-byte aligned", i);
+    }
+    if (num_levels == 1)
+        return volume_impl(fmap1, fmap2, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_TILED);
+    return volume_impl(fmap1, fmap2, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_FUSED_PYRAMID,
+                       lvl, num_levels);
 }
 
 extern "C" int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1, const float* fmap2, float* gfmap1,

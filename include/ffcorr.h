@@ -9,6 +9,7 @@
  *   ffcorr_volume_f32      core/models/ff-raft/FF_RAFT_Core/corr.py:52-60   CorrBlock.corr
  *                          (torch.matmul + separate "/ sqrt(D)" kernel)
  *   ffcorr_pyramid_f32     corr.py:24-27   3x F.avg_pool2d(corr, 2, stride=2)
+ *   ffcorr_build_tiled_f32 corr.py:13-27   CorrBlock.__init__ = volume + pyramid, fused (tiled layout)
  *   ffcorr_lookup_f32      corr.py:29-50   CorrBlock.__call__  +  utils/utils.py:57-71
  *                          bilinear_sampler (4x F.grid_sample + ~60 glue kernels)
  *   ffcorr_lookup_bwd_f32  autograd of the above w.r.t. the pyramid (coords are detached
@@ -118,6 +119,15 @@ int ffcorr_volume_tiled_f32(const float* fmap1, const float* fmap2, float* lvl0_
                             int B, int D, int h, int w, int precision,
                             void* workspace, size_t workspace_bytes, void* stream);
 int ffcorr_pyramid_tiled_f32(float* const* lvl, int num_levels, int64_t Q, int h, int w, void* stream);
+/*
+ * CorrBlock.__init__ (corr.py:13-27) in ONE GEMM launch: level 0 and the pooled levels 1..num_levels-1 are
+ * all written by the GEMM epilogue, so level 0 is never read back (the standalone pyramid re-reads it).
+ * `lvl` is a HOST array of num_levels device pointers to tiled levels; results are bit-identical to
+ * ffcorr_volume_tiled_f32 followed by ffcorr_pyramid_tiled_f32.  Same workspace as ffcorr_volume_f32.
+ */
+int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, float* const* lvl, int num_levels,
+                           int B, int D, int h, int w, int precision,
+                           void* workspace, size_t workspace_bytes, void* stream);
 int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
                             int B, int h, int w, int radius, void* stream);
 int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int h_level, int w_level, void* stream);

@@ -453,6 +453,31 @@ def test_lookup_tiled_vs_oracle(shape, radius, nl):
         assert max_rel(got, ref) <= 1e-5, (shape, name, max_rel(got, ref))
 
 
+@pytest.mark.parametrize("precision", ["fp16", "tf32", "bf16x3"])
+@pytest.mark.parametrize("shape,nl", [((1, 64, 47, 156), 4), ((2, 32, 33, 47), 4), ((1, 256, 46, 62), 4), ((2, 40, 17, 21), 4),
+                                      ((1, 32, 16, 16), 4), ((1, 32, 8, 8), 4), ((3, 16, 24, 40), 3), ((1, 48, 9, 35), 2),
+                                      ((1, 16, 50, 20), 4), ((2, 24, 12, 9), 1)])
+def test_fused_build_equals_volume_then_pyramid_bitwise(shape, nl, precision):
+    """ffcorr_build_tiled_f32 (pooling in the GEMM epilogue) == ffcorr_volume_tiled_f32 + ffcorr_pyramid_tiled_f32,
+    bit for bit, INCLUDING the zero padding of every tile (raw tiled buffers are compared)."""
+    m = ff()
+    torch.manual_seed(5)
+    f1 = torch.randn(shape, device=DEV) * 4.4
+    f2 = torch.randn(shape, device=DEV) * 4.4
+    b, d, h, w = shape
+    # poison the allocator's blocks so stale data would show up in unwritten padding
+    junk = [torch.full((b * h * w, int(m._lib.lib().ffcorr_tiled_map_elems(h, w, i))), float("nan"), device=DEV) for i in range(nl)]
+    del junk
+    fused = m.tiled_pyramid(f1, f2, nl, precision, fused=True)
+    junk = [torch.full_like(x, float("nan")) for x in fused]
+    del junk
+    plain = m.tiled_pyramid(f1, f2, nl, precision, fused=False)
+    torch.cuda.synchronize()
+    for i in range(nl):
+        assert torch.isfinite(fused[i]).all(), i
+        assert torch.equal(fused[i], plain[i]), (i, (fused[i] != plain[i]).sum().item())
+
+
 @pytest.mark.parametrize("shape", [(1, 256, 46, 62), (2, 64, 17, 21), (2, 32, 16, 24), (1, 40, 9, 13)])
 def test_tiled_and_rowmajor_blocks_agree_bitwise(shape):
     """Same kernels' arithmetic, two storage orders: pyramids and lookups must be identical."""

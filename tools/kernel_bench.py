@@ -117,6 +117,10 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     def k_pyramid_t():
         _lib.check(L.ffcorr_pyramid_tiled_f32(tptrs, nl, b * n, h, w, stream), "pyramid_tiled")
 
+    def k_build_t():
+        _lib.check(L.ffcorr_build_tiled_f32(f1.data_ptr(), f2.data_ptr(), tptrs, nl, b, d, h, w, code, ws.data_ptr(), ws_bytes,
+                                            stream), "build_tiled")
+
     def k_lookup_t():
         _lib.check(L.ffcorr_lookup_tiled_f32(tptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, stream), "lookup_tiled")
 
@@ -129,10 +133,11 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     todo = [("volume", k_volume, vol_bytes, vol_flops), ("pyramid", k_pyramid, pyr_bytes, 0.0), ("lookup", k_lookup, look_bytes, 0.0)]
     if tiled_ok:  # same algorithmic bytes: the padding of the tiled layout is overhead, not work
         todo += [("volume_tiled", k_volume_t, vol_bytes, vol_flops), ("pyramid_tiled", k_pyramid_t, pyr_bytes, 0.0),
+                 ("build_fused", k_build_t, vol_bytes + pyr_bytes - 4.0 * b * n * lv_elems[0], vol_flops),
                  ("lookup_tiled", k_lookup_t, look_bytes, 0.0)]
     for name, fn, byts, flops in todo:
         if only and not any(o in name for o in only):
-            if name in ("volume_tiled", "pyramid_tiled") and any("tiled" in o for o in only):
+            if name == "build_fused" and any("tiled" in o for o in only):
                 fn()   # the tiled lookup needs a built tiled pyramid
             elif name in ("volume", "pyramid"):
                 fn()
