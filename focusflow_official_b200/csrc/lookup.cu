@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     const int n = min(n0 + lane, N - 1);
     const int lh = p.lh[level], lw = p.lw[level];
     const int th = p.th[level], tw = p.tw[level];
+    const int twr = (lw + 3) >> 2;      // tile columns that hold pixels; the column that evens the pitch is never read
     const int map_elems = th * tw * 16;
     const float* __restrict__ lvl = p.lvl[level];
     const float inv_scale = __int_as_float((127 - level) << 23);
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         for (int tyi = 0; tyi < 4; ++tyi)
 #pragma unroll
             for (int txi = 0; txi < 4; ++txi)
-                if ((unsigned)(ty0 + tyi) < (unsigned)th && (unsigned)(tx0 + txi) < (unsigned)tw) tmask |= 1 << (tyi * 4 + txi);
+                if ((unsigned)(ty0 + tyi) < (unsigned)th && (unsigned)(tx0 + txi) < (unsigned)twr) tmask |= 1 << (tyi * 4 + txi);
         my_pack = (x_lo & 3) | ((y_lo & 3) << 2) | (tmask << 4);
     }
 
@@ -657,8 +658,8 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
         p.lvl[i] = lvl[i];
         p.lh[i] = h >> i;
         p.lw[i] = w >> i;
-        p.th[i] = ceil_div(p.lh[i], 4);
-        p.tw[i] = ceil_div(p.lw[i], 4);
+        p.th[i] = tiled_th(p.lh[i]);
+        p.tw[i] = tiled_tw(p.lw[i]);
     }
     p.coords = coords;
     p.out = out;

@@ -529,15 +529,15 @@ extern "C" int64_t ffcorr_tiled_map_elems(int h, int w, int level) {
     if (h < 1 || w < 1 || level < 0 || level >= FFCORR_MAX_LEVELS) return 0;
     const int hl = h >> level, wl = w >> level;
     if (hl < 1 || wl < 1) return 0;
-    return (int64_t)ceil_div(hl, 4) * ceil_div(wl, 4) * 16;
+    return (int64_t)tiled_th(hl) * tiled_tw(wl) * 16;
 }
 
 static int fill_tiled_params(TiledPyrParams* p, float* const* lvl, int num_levels, int h, int w) {
     for (int i = 0; i < num_levels; ++i) {
         p->h[i] = h >> i;
         p->w[i] = w >> i;
-        p->th[i] = ceil_div(p->h[i], 4);
-        p->tw[i] = ceil_div(p->w[i], 4);
+        p->th[i] = tiled_th(p->h[i]);
+        p->tw[i] = tiled_tw(p->w[i]);
         p->np[i] = p->th[i] * p->tw[i] * 16;
         p->out[i] = lvl[i];
         p->magic_tw[i] = (unsigned)((0x100000000ull + p->tw[i] - 1) / (unsigned)p->tw[i]);
@@ -586,8 +586,8 @@ extern "C" int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int 
     FFCORR_REQUIRE(Q >= 0 && h >= 1 && w >= 1, FFCORR_EINVAL, "untile: bad shape");
     if (Q == 0) return FFCORR_OK;
     FFCORR_REQUIRE(tiled && dst, FFCORR_EINVAL, "untile: null pointer");
-    const int tw = ceil_div(w, 4);
-    untile_kernel<<<grid_for(Q * h * w, 256), 256, 0, (cudaStream_t)stream>>>(tiled, dst, Q, h, w, tw, ceil_div(h, 4) * tw * 16);
+    const int tw = tiled_tw(w);
+    untile_kernel<<<grid_for(Q * h * w, 256), 256, 0, (cudaStream_t)stream>>>(tiled, dst, Q, h, w, tw, tiled_th(h) * tw * 16);
     return check_launch("untile_kernel");
 }
 
@@ -595,8 +595,8 @@ extern "C" int ffcorr_tile_f32(const float* src, float* tiled, int64_t Q, int h,
     FFCORR_REQUIRE(Q >= 0 && h >= 1 && w >= 1, FFCORR_EINVAL, "tile: bad shape");
     if (Q == 0) return FFCORR_OK;
     FFCORR_REQUIRE(tiled && src, FFCORR_EINVAL, "tile: null pointer");
-    const int tw = ceil_div(w, 4);
-    const int np = ceil_div(h, 4) * tw * 16;
+    const int tw = tiled_tw(w);
+    const int np = tiled_th(h) * tw * 16;
     tile_kernel<<<grid_for(Q * np, 256), 256, 0, (cudaStream_t)stream>>>(src, tiled, Q, h, w, tw, np);
     return check_launch("tile_kernel");
 }

@@ -801,8 +801,8 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     tlb.enabled = fused ? 2 : (tiled ? 1 : 0);
     tlb.h = h;
     tlb.w = w;
-    tlb.tw = fused ? ceil_div(w, 16) : ceil_div(w, 4);
-    tlb.np = fused ? ceil_div(h, 16) * tlb.tw * 256 : ceil_div(h, 4) * 4 * tlb.tw * 4;
+    tlb.tw = fused ? ceil_div(w, 16) : tiled_tw(w);
+    tlb.np = fused ? ceil_div(h, 16) * tlb.tw * 256 : tiled_th(h) * tlb.tw * 16;
     const int Ncols = tiled ? tlb.np : N;       // columns of the volume == rows of the staged B operand
     {
         dim3 grid(ceil_div(Ncols, PP_N), Dp / PP_D, 2 * B);
@@ -830,9 +830,9 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     FusedParams fp{};
     if (fused) {
         // 4-D views [B][N][tile row][tile-row floats] of levels 0 and 1; boxes of 32 queries x 128 bytes
-        const int th0 = ceil_div(h, 4), tw0 = ceil_div(w, 4);
+        const int th0 = tiled_th(h), tw0 = tiled_tw(w);
         const int lh1 = h >> 1, lw1 = w >> 1;
-        const int th1 = ceil_div(lh1, 4), tw1 = ceil_div(lw1, 4);
+        const int th1 = tiled_th(lh1), tw1 = tiled_tw(lw1);
         const uint32_t box[4] = {32, 1, 32, 1};
         {
             const uint64_t dims[4] = {(uint64_t)tw0 * 16, (uint64_t)th0, (uint64_t)N, (uint64_t)B};
@@ -857,8 +857,8 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
         fp.lh1 = lh1; fp.lw1 = lw1;
         fp.lh2 = h >> 2; fp.lw2 = w >> 2;
         fp.lh3 = h >> 3; fp.lw3 = w >> 3;
-        fp.th2 = ceil_div(fp.lh2, 4); fp.tw2 = ceil_div(fp.lw2, 4);
-        fp.th3 = ceil_div(fp.lh3, 4); fp.tw3 = ceil_div(fp.lw3, 4);
+        fp.th2 = tiled_th(fp.lh2); fp.tw2 = tiled_tw(fp.lw2);
+        fp.th3 = tiled_th(fp.lh3); fp.tw3 = tiled_tw(fp.lw3);
         fp.map2 = fp.th2 * fp.tw2 * 16;
         fp.map3 = fp.th3 * fp.tw3 * 16;
         fp.l2 = num_levels >= 3 ? lvl[2] : nullptr;

@@ -106,7 +106,9 @@ int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coor
 
 /*
  * Tiled ("T4") pyramid layout -- the inference fast path.  Every level is stored per query map as
- * [ceil(h_i/4)][ceil(w_i/4)][4][4] floats (ffcorr_tiled_map_elems() per map), padding = exact zeros.
+ * [ceil(h_i/4)][tw_i][4][4] floats with tw_i = ceil(w_i/4) rounded up to an even number, so that every tile
+ * row starts on a 128-byte line (ffcorr_tiled_map_elems() per map).  Pixels beyond the level size inside
+ * tiles that hold pixels are exact zeros; the extra tile column that evens the pitch is never read.
  * A 4x4 tile is 64 contiguous bytes, the granularity at which the memory system serves the lookup's
  * gathers.  The three entry points below are drop-ins for ffcorr_volume_f32 / ffcorr_pyramid_f32 /
  * ffcorr_lookup_f32 on that layout (same arguments, same results); ffcorr_untile_f32 / ffcorr_tile_f32

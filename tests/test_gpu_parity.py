@@ -412,7 +412,7 @@ def test_tile_untile_roundtrip_and_padding(shape):
     q, h, w = shape
     x = torch.randn(q, 1, h, w, device=DEV)
     (tl,) = m.tile_levels([x])
-    th, tw = (h + 3) // 4, (w + 3) // 4
+    th, tw = (h + 3) // 4, ((w + 3) // 4 + 1) & ~1      # tile-row pitch is even (128-byte aligned tile rows)
     assert tl.shape == (q, th * tw * 16)
     # padding is exact zero and the sum is preserved
     assert float(tl.double().sum()) == pytest.approx(float(x.double().sum()), rel=1e-9, abs=1e-9)
@@ -474,8 +474,13 @@ def test_fused_build_equals_volume_then_pyramid_bitwise(shape, nl, precision):
     plain = m.tiled_pyramid(f1, f2, nl, precision, fused=False)
     torch.cuda.synchronize()
     for i in range(nl):
-        assert torch.isfinite(fused[i]).all(), i
-        assert torch.equal(fused[i], plain[i]), (i, (fused[i] != plain[i]).sum().item())
+        hi, wi = h >> i, w >> i
+        th, twr = (hi + 3) // 4, (wi + 3) // 4
+        # the extra tile column that keeps the pitch even is never read (content unspecified); compare the rest raw
+        fa = fused[i].view(b * h * w, th, -1, 16)[:, :, :twr]
+        pa = plain[i].view(b * h * w, th, -1, 16)[:, :, :twr]
+        assert torch.isfinite(fa).all(), i
+        assert torch.equal(fa, pa), (i, (fa != pa).sum().item())
 
 
 @pytest.mark.parametrize("shape", [(1, 256, 46, 62), (2, 64, 17, 21), (2, 32, 16, 24), (1, 40, 9, 13)])

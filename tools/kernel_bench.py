@@ -136,10 +136,11 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
                  ("build_fused", k_build_t, vol_bytes + pyr_bytes - 4.0 * b * n * lv_elems[0], vol_flops),
                  ("lookup_tiled", k_lookup_t, look_bytes, 0.0)]
     for name, fn, byts, flops in todo:
-        if only and not any(o in name for o in only):
-            if name == "build_fused" and any("tiled" in o for o in only):
-                fn()   # the tiled lookup needs a built tiled pyramid
-            elif name in ("volume", "pyramid"):
+        if only and name not in only:
+            # run (untimed) only what a selected kernel reads
+            needs = {"pyramid": ["volume"], "lookup": ["volume", "pyramid"], "pyramid_tiled": ["volume_tiled"],
+                     "lookup_tiled": ["build_fused"]}
+            if any(name in needs.get(o, []) for o in only):
                 fn()
             continue
         med, best = time_cuda(fn, iters=iters, warmup=warmup, flush=flush)
