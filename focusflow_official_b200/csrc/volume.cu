@@ -145,25 +145,37 @@ constexpr int BM = 128;              // tile rows (queries i)     == UMMA M == T
 constexpr int BN = 256;              // tile cols (targets j)     == UMMA N == TMEM columns per accumulator
 constexpr int BK_BYTES = 128;        // one 128B swizzle atom along K per stage
 constexpr int UMMA_K_BYTES = 32;     // K extent of one tcgen05.mma: 16 x 16-bit or 8 x tf32
-constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr int STORE_COLS = 32;       // fp32 columns per store box (128 B rows)
-constexpr int STORE_BUFS = 4;        // per epilogue warp: 2 pairs = 2 TMA-store groups in flight
-constexpr int EPI_WARPS = 4;
-constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
-
 constexpr int SMEM_A_STAGE = BM * BK_BYTES;   // 16 KB
 constexpr int SMEM_B_STAGE = BN * BK_BYTES;   // 32 KB
 constexpr int SMEM_STORE_BUF = 32 * STORE_COLS * 4;  // 4 KB: 32 rows x 128 B
-constexpr int FUSED_BUFS = STORE_BUFS + 1; // fused build: + one level-1 box per epilogue warp
-constexpr int SMEM_STORE = EPI_WARPS * FUSED_BUFS * SMEM_STORE_BUF;  // 80 KB (the plain volume kernel uses 64 KB of it)
-constexpr int SMEM_OFF_A = SMEM_STORE;
-constexpr int SMEM_OFF_B = SMEM_OFF_A + STAGES * SMEM_A_STAGE;
-constexpr int SMEM_OFF_BAR = SMEM_OFF_B + STAGES * SMEM_B_STAGE;
-constexpr int SMEM_GEMM_TOTAL = SMEM_OFF_BAR + 128 + 1024;  // + barriers + alignment slack
-static_assert(SMEM_GEMM_TOTAL <= 227 * 1024, "shared memory budget");
-static_assert(BN == 256 && STORE_COLS == 32 && STORE_BUFS % 2 == 0, "the epilogue is written for 4 x 64-column chunks");
-constexpr int STORE_PAIRS = STORE_BUFS / 2;
+
+// Per-variant resources.
+//   plain volume : 4 epilogue warps (one per TMEM lane quarter, 4 chunks each), 2 store pairs per warp, 3 operand stages.
+//   fused build  : 8 epilogue warps -- two per lane quarter, chunks {0,1} and {2,3} -- each with one store pair + one
+//                  level-1 box, 2 operand stages.  The epilogue does ~2.3x the instructions per chunk (pooling of
+//                  three levels), so it gets two warps per scheduler; measured, this is no faster than the 4-warp
+//                  version (0.486 ms either way at config 2): the kernel runs at the speed of its WRITE PATTERN --
+//                  tools/mb/mb_scatter_write.cu reproduces 0.48 ms with plain stores and no GEMM at all (level 0
+//                  alone 0.31 ms; the 32-byte level-2 and 8-byte level-3 pieces cost 0.08 ms for 150 MB).
+template <bool FUSED>
+struct Cfg {
+    static constexpr int STAGES = FUSED ? 2 : 3;
+    static constexpr int EPI_WARPS = FUSED ? 8 : 4;
+    static constexpr int THREADS = (2 + EPI_WARPS) * 32;
+    static constexpr int STORE_BUFS = FUSED ? 2 : 4;            // level-0 boxes per epilogue warp
+    static constexpr int STORE_PAIRS = STORE_BUFS / 2;
+    static constexpr int WARP_BUFS = STORE_BUFS + (FUSED ? 1 : 0);   // + the level-1 box
+    static constexpr int SMEM_STORE = EPI_WARPS * WARP_BUFS * SMEM_STORE_BUF;
+    static constexpr int OFF_A = SMEM_STORE;
+    static constexpr int OFF_B = OFF_A + STAGES * SMEM_A_STAGE;
+    static constexpr int OFF_BAR = OFF_B + STAGES * SMEM_B_STAGE;
+    static constexpr int SMEM_TOTAL = OFF_BAR + 128;            // + barriers and the TMEM slot
+    static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+    static_assert((OFF_A % 1024) == 0, "operand stages must stay 1024-byte aligned (128B swizzle)");
+};
+static_assert(BN == 256 && STORE_COLS == 32, "the epilogue is written for 4 x 64-column chunks");
 
 // K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -206,22 +218,25 @@ struct FusedParams {
 };
 
 template <bool TF32, bool TMA_STORE, bool DIV, bool FUSED>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<FUSED>::THREADS, 1)
 volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_l1,
                    const GemmParams p, const FusedParams fp, const uint32_t idesc) {
     static_assert(!FUSED || TMA_STORE, "the fused build stores through TMA");
+    using C = Cfg<FUSED>;
+    constexpr int STAGES = C::STAGES;
+    constexpr int STORE_PAIRS = C::STORE_PAIRS;
     // Index the extern array directly: rounding the pointer up through uintptr_t loses the shared
     // address space (generic ST.E instead of STS in the epilogue).  128B-swizzle needs 1024-byte alignment.
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
     if (smem_base & 1023u) __trap();
-    const uint32_t bar_base = smem_base + SMEM_OFF_BAR;
+    const uint32_t bar_base = smem_base + C::OFF_BAR;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_OFF_BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 8 * (2 * STAGES + 2 * ACC_STAGES));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -237,7 +252,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         for (int s = 0; s < ACC_STAGES; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), EPI_WARPS);
+            mbar_init(tempty_bar(s), C::EPI_WARPS);
         }
         fence_barrier_init();
     } else if (warp == 1) {
@@ -271,8 +286,8 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_arrive_expect_tx(full_bar(stage), SMEM_A_STAGE + SMEM_B_STAGE);
                     const int k0 = kb * (TF32 ? BK_BYTES / 4 : BK_BYTES / 2);
-                    tma_load_3d(smem_base + SMEM_OFF_A + stage * SMEM_A_STAGE, &tmap_a, full_bar(stage), k0, m0, b);
-                    tma_load_3d(smem_base + SMEM_OFF_B + stage * SMEM_B_STAGE, &tmap_b, full_bar(stage), k0, n0, b);
+                    tma_load_3d(smem_base + C::OFF_A + stage * SMEM_A_STAGE, &tmap_a, full_bar(stage), k0, m0, b);
+                    tma_load_3d(smem_base + C::OFF_B + stage * SMEM_B_STAGE, &tmap_b, full_bar(stage), k0, n0, b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -292,8 +307,8 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_smem_desc(smem_base + SMEM_OFF_A + stage * SMEM_A_STAGE);
-                    const uint64_t bdesc = make_smem_desc(smem_base + SMEM_OFF_B + stage * SMEM_B_STAGE);
+                    const uint64_t adesc = make_smem_desc(smem_base + C::OFF_A + stage * SMEM_A_STAGE);
+                    const uint64_t bdesc = make_smem_desc(smem_base + C::OFF_B + stage * SMEM_B_STAGE);
 #pragma unroll
                     for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
                         // advance K inside the swizzle atom: +32 B == +2 in the (addr >> 4) field
@@ -310,80 +325,98 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
         const int ew = warp - 2;                      // private store ring
-        constexpr int MY_BUFS = FUSED ? FUSED_BUFS : STORE_BUFS;
-        uint8_t* my_bufs = smem + (size_t)ew * MY_BUFS * SMEM_STORE_BUF;
-        const uint32_t my_bufs_u32 = smem_base + (uint32_t)(ew * MY_BUFS * SMEM_STORE_BUF);
-        float pe[16];    // fused: level-1 values of the even chunk (rows 0-1 of the level-1 tiles being assembled)
-        float q2[16];    // fused: level-2 tile of this super-group, [chunk][tile]
-        int pair = 0;   // store ring: 2 pairs of 32x32 boxes per warp
+        uint8_t* my_bufs = smem + (size_t)ew * C::WARP_BUFS * SMEM_STORE_BUF;
+        const uint32_t my_bufs_u32 = smem_base + (uint32_t)(ew * C::WARP_BUFS * SMEM_STORE_BUF);
+        int pair = 0;   // store ring position
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int b = t / tiles_per_batch;
             const int r = t - b * tiles_per_batch;
             const int m0 = (r / p.tiles_n) * BM;
-            const int n0 = (r % p.tiles_n) * BN;
+            const int nt = r % p.tiles_n;
+            const int n0 = nt * BN;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             const int row0 = m0 + quarter * 32;
-            // 4 chunks of 64 columns, software pipelined: the TMEM load of chunk c+1 is in flight while
-            // chunk c is scaled, staged (two 128B-swizzled 32x32 boxes, ONE proxy fence) and handed to TMA.
-            auto process = [&](uint32_t (&v)[64], int c) {
-                const int col0 = n0 + c * 64;
-                if (FUSED) {
-                    if (row0 >= p.N) return;                      // warp-uniform
-                    const int nt = n0 / BN;
-                    const int sgy = nt / fp.sgw, sgx = nt - sgy * fp.sgw;
-                    const int ty = sgy * 4 + c;                   // level-0 tile row of this chunk
-                    float f[64];
+            // raw accumulators -> volume values, in place (fp32 bit patterns stay in the same registers)
+            auto scale_chunk = [&](uint32_t (&v)[64]) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i)
-                        f[i] = DIV ? __fdiv_rn(__uint_as_float(v[i]), p.divisor) : __uint_as_float(v[i]) * p.scale;
-                    if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();
-                    __syncwarp();
-                    // ---- level 0: tiles (ty, 4 sgx .. 4 sgx + 3) = 256 contiguous bytes per query, two 32x32 boxes ----
-                    const bool l0_any = ty < fp.th0;
-                    if (l0_any) {
-                        uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
+                for (int i = 0; i < 64; ++i)
+                    v[i] = __float_as_uint(DIV ? __fdiv_rn(__uint_as_float(v[i]), p.divisor) : __uint_as_float(v[i]) * p.scale);
+            };
+            auto scaled = [](uint32_t bits) { return __uint_as_float(bits); };
+            // stages one 64-column chunk as two 128B-swizzled 32x32 boxes in store pair `pair`
+            auto stage_pair = [&](const uint32_t (&v)[64]) {
+                uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
 #pragma unroll
-                        for (int hlf = 0; hlf < 2; ++hlf)
+                for (int hlf = 0; hlf < 2; ++hlf)
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int i0 = hlf * 32 + 4 * j;
-                                *reinterpret_cast<float4*>(dst + hlf * SMEM_STORE_BUF + ((j ^ (lane & 7)) << 4)) =
-                                    make_float4(f[i0], f[i0 + 1], f[i0 + 2], f[i0 + 3]);
-                            }
+                    for (int j = 0; j < 8; ++j) {
+                        const int i0 = hlf * 32 + 4 * j;
+                        *reinterpret_cast<float4*>(dst + hlf * SMEM_STORE_BUF + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(scaled(v[i0]), scaled(v[i0 + 1]), scaled(v[i0 + 2]), scaled(v[i0 + 3]));
                     }
-                    // ---- level 1: 2x2 means inside every tile; ATen's (((a+b)+c)+d)/4 order; zero beyond the floor size ----
+            };
+
+            if constexpr (FUSED) {
+                // ---- fused pyramid build: this warp owns chunks c0 (even) and c0 + 1 of its 32 queries ----
+                const int c0 = (ew >> 2) * 2;
+                const int sgy = nt / fp.sgw, sgx = nt - sgy * fp.sgw;
+                const bool rows_live = row0 < p.N;               // warp-uniform
+                const int row = row0 + lane;
+                float pe[16];                                    // level-1 values of the even chunk
+                float q2[8];                                     // level-2 values: [chunk parity][tile]
+                uint32_t v[64];
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci) {
+                    const int c = c0 + ci;
+                    const int ty = sgy * 4 + c;                   // level-0 tile row of this chunk
+                    tmem_ld_32x64(t_row + (uint32_t)(c * 64), v);
+                    tmem_ld_wait();
+                    if (ci == 1) {
+                        // both chunks are in registers: hand the TMEM stage back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
+                    if (!rows_live) continue;
+                    scale_chunk(v);
+                    // ---- level 1: 2x2 means inside every tile, ATen's (((a+b)+c)+d)/4 order, zero beyond the floor size ----
                     float p1[16];   // [tile t][py][px]
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
+                    for (int tt = 0; tt < 4; ++tt)
 #pragma unroll
                         for (int py = 0; py < 2; ++py)
 #pragma unroll
                             for (int px = 0; px < 2; ++px) {
-                                const int i0 = t * 16 + py * 8 + px * 2;
-                                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(f[i0], f[i0 + 1]), f[i0 + 4]), f[i0 + 5]);
-                                const bool ok = (ty * 2 + py < fp.lh1) && ((sgx * 4 + t) * 2 + px < fp.lw1);
-                                p1[t * 4 + py * 2 + px] = ok ? __fmul_rn(sum, 0.25f) : 0.0f;
+                                const int i0 = tt * 16 + py * 8 + px * 2;
+                                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(scaled(v[i0]), scaled(v[i0 + 1])), scaled(v[i0 + 4])),
+                                                            scaled(v[i0 + 5]));
+                                const bool ok = (ty * 2 + py < fp.lh1) && ((sgx * 4 + tt) * 2 + px < fp.lw1);
+                                p1[tt * 4 + py * 2 + px] = ok ? __fmul_rn(sum, 0.25f) : 0.0f;
                             }
                     // ---- level 2: one value per level-0 tile ----
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float sum = __fadd_rn(__fadd_rn(__fadd_rn(p1[t * 4], p1[t * 4 + 1]), p1[t * 4 + 2]), p1[t * 4 + 3]);
-                        const bool ok = (ty < fp.lh2) && (sgx * 4 + t < fp.lw2);
-                        q2[c * 4 + t] = ok ? __fmul_rn(sum, 0.25f) : 0.0f;
+                    for (int tt = 0; tt < 4; ++tt) {
+                        const float sum = __fadd_rn(__fadd_rn(__fadd_rn(p1[tt * 4], p1[tt * 4 + 1]), p1[tt * 4 + 2]), p1[tt * 4 + 3]);
+                        const bool ok = (ty < fp.lh2) && (sgx * 4 + tt < fp.lw2);
+                        q2[ci * 4 + tt] = ok ? __fmul_rn(sum, 0.25f) : 0.0f;
                     }
-                    const bool odd = c & 1;
+                    if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();   // this warp's previous group has left smem
+                    __syncwarp();
+                    // ---- level 0: tiles (ty, 4 sgx .. 4 sgx + 3) = 256 contiguous bytes per query ----
+                    const bool l0_any = ty < fp.th0;
+                    if (l0_any) stage_pair(v);
                     bool l1_any = false;
-                    if (odd) {
-                        // level-1 tiles (sgy*2 + c/2, sgx*2 .. +1): rows 0-1 from the even chunk, rows 2-3 from this one
+                    if (ci == 1) {
+                        // level-1 tiles (2 sgy + c/2, 2 sgx .. + 1): rows 0-1 from the even chunk, rows 2-3 from this one
                         const int ty1 = sgy * 2 + (c >> 1);
                         l1_any = (ty1 < fp.th1) && (sgx * 2 < fp.tw1);
                         if (l1_any) {
-                            uint8_t* dst = my_bufs + (size_t)STORE_BUFS * SMEM_STORE_BUF + lane * 128;
+                            uint8_t* dst = my_bufs + (size_t)C::STORE_BUFS * SMEM_STORE_BUF + lane * 128;
 #pragma unroll
                             for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
@@ -409,20 +442,25 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                             if (sgx * 4 + 2 < fp.tw0) tma_store_4d(&tmap_c, src + SMEM_STORE_BUF, sgx * 64 + 32, ty, row0, b);
                         }
                         if (l1_any)
-                            tma_store_4d(&tmap_l1, my_bufs_u32 + (uint32_t)(STORE_BUFS * SMEM_STORE_BUF), sgx * 32,
+                            tma_store_4d(&tmap_l1, my_bufs_u32 + (uint32_t)(C::STORE_BUFS * SMEM_STORE_BUF), sgx * 32,
                                          sgy * 2 + (c >> 1), row0, b);
                         tma_store_commit();
                     }
                     pair = (pair + 1) % STORE_PAIRS;
-                    const int row = row0 + lane;
-                    // ---- level 3: a 2x2 patch per super-group, one row per chunk pair; written directly (8-byte pieces) ----
-                    if (odd && fp.levels >= 4 && row < p.N) {
+                    if (ci == 1 && row < p.N) {
+                        // ---- level 2: rows c0, c0 + 1 of this super-group's tile, 32 contiguous bytes per query ----
+                        if (fp.levels >= 3 && sgy < fp.th2 && sgx < fp.tw2) {
+                            float4* d2 = reinterpret_cast<float4*>(fp.l2 + ((int64_t)b * p.N + row) * fp.map2 +
+                                                                   (sgy * fp.tw2 + sgx) * 16 + c0 * 4);
+                            d2[0] = make_float4(q2[0], q2[1], q2[2], q2[3]);
+                            d2[1] = make_float4(q2[4], q2[5], q2[6], q2[7]);
+                        }
+                        // ---- level 3: one row of the super-group's 2x2 patch, 8 bytes per query ----
                         const int ty3 = sgy >> 1, tx3 = sgx >> 1;
-                        if (ty3 < fp.th3 && tx3 < fp.tw3) {
-                            const int ce = (c - 1) * 4, co = c * 4;
+                        if (fp.levels >= 4 && ty3 < fp.th3 && tx3 < fp.tw3) {
                             float2 o;
-                            o.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q2[ce], q2[ce + 1]), q2[co]), q2[co + 1]), 0.25f);
-                            o.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q2[ce + 2], q2[ce + 3]), q2[co + 2]), q2[co + 3]), 0.25f);
+                            o.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q2[0], q2[1]), q2[4]), q2[5]), 0.25f);
+                            o.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q2[2], q2[3]), q2[6]), q2[7]), 0.25f);
                             const int y3 = sgy * 2 + (c >> 1);
                             if (!(y3 < fp.lh3 && sgx * 2 < fp.lw3)) o.x = 0.0f;
                             if (!(y3 < fp.lh3 && sgx * 2 + 1 < fp.lw3)) o.y = 0.0f;
@@ -438,68 +476,56 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                             if (ghost_x && ghost_y) *reinterpret_cast<float2*>(d3 + 10) = z;
                         }
                     }
-                    // ---- level 2: the complete 4x4 tile of this super-group, 64 contiguous bytes per query ----
-                    if (c == 3 && fp.levels >= 3 && row < p.N && sgy < fp.th2 && sgx < fp.tw2) {
-                        float4* d2 = reinterpret_cast<float4*>(fp.l2 + ((int64_t)b * p.N + row) * fp.map2 + (sgy * fp.tw2 + sgx) * 16);
-#pragma unroll
-                        for (int rr = 0; rr < 4; ++rr) d2[rr] = make_float4(q2[rr * 4], q2[rr * 4 + 1], q2[rr * 4 + 2], q2[rr * 4 + 3]);
-                    }
-                } else if (TMA_STORE) {
-                    if (row0 >= p.N || col0 >= p.Ncols) return;   // warp-uniform: both boxes outside
-                    if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();   // the pair used STORE_PAIRS groups ago has been read
-                    __syncwarp();
-                    uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
-#pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 q;
-                            const int i0 = hlf * 32 + 4 * j;
-                            q.x = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 0]), p.divisor) : __uint_as_float(v[i0 + 0]) * p.scale;
-                            q.y = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 1]), p.divisor) : __uint_as_float(v[i0 + 1]) * p.scale;
-                            q.z = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 2]), p.divisor) : __uint_as_float(v[i0 + 2]) * p.scale;
-                            q.w = DIV ? __fdiv_rn(__uint_as_float(v[i0 + 3]), p.divisor) : __uint_as_float(v[i0 + 3]) * p.scale;
-                            *reinterpret_cast<float4*>(dst + hlf * SMEM_STORE_BUF + ((j ^ (lane & 7)) << 4)) = q;  // 128B swizzle
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
-                        tma_store_3d(&tmap_c, src, col0, row0, b);
-                        if (col0 + 32 < p.Ncols) tma_store_3d(&tmap_c, src + SMEM_STORE_BUF, col0 + 32, row0, b);
-                        tma_store_commit();
-                    }
-                    pair = (pair + 1) % STORE_PAIRS;
-                } else {
-                    const int row = row0 + lane;
-                    if (row < p.N) {
-                        float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.Ncols + col0;
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) {
-                            const float a = __uint_as_float(v[i]);
-                            if (col0 + i < p.Ncols) o[i] = DIV ? __fdiv_rn(a, p.divisor) : a * p.scale;
-                        }
-                    }
                 }
-            };
-            uint32_t va[64], vb[64];
-            tmem_ld_32x64(t_row, va);
-            tmem_ld_wait();
-            tmem_ld_32x64(t_row + 64u, vb);
-            process(va, 0);
-            tmem_ld_wait();
-            tmem_ld_32x64(t_row + 128u, va);
-            process(vb, 1);
-            tmem_ld_wait();
-            tmem_ld_32x64(t_row + 192u, vb);
-            process(va, 2);
-            tmem_ld_wait();
-            // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            process(vb, 3);
+            } else {
+                // ---- plain volume: 4 chunks of 64 columns, software pipelined: the TMEM load of chunk c+1 is in
+                // flight while chunk c is scaled, staged (two boxes, ONE proxy fence) and handed to TMA ----
+                auto process = [&](uint32_t (&v)[64], int c) {
+                    const int col0 = n0 + c * 64;
+                    if (TMA_STORE) {
+                        if (row0 >= p.N || col0 >= p.Ncols) return;   // warp-uniform: both boxes outside
+                        if (lane == 0) tma_store_wait_read<STORE_PAIRS - 1>();   // the pair used STORE_PAIRS groups ago has been read
+                        __syncwarp();
+                        scale_chunk(v);
+                        stage_pair(v);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
+                            tma_store_3d(&tmap_c, src, col0, row0, b);
+                            if (col0 + 32 < p.Ncols) tma_store_3d(&tmap_c, src + SMEM_STORE_BUF, col0 + 32, row0, b);
+                            tma_store_commit();
+                        }
+                        pair = (pair + 1) % STORE_PAIRS;
+                    } else {
+                        const int row = row0 + lane;
+                        if (row < p.N) {
+                            scale_chunk(v);
+                            float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.Ncols + col0;
+#pragma unroll
+                            for (int i = 0; i < 64; ++i)
+                                if (col0 + i < p.Ncols) o[i] = scaled(v[i]);
+                        }
+                    }
+                };
+                uint32_t va[64], vb[64];
+                tmem_ld_32x64(t_row, va);
+                tmem_ld_wait();
+                tmem_ld_32x64(t_row + 64u, vb);
+                process(va, 0);
+                tmem_ld_wait();
+                tmem_ld_32x64(t_row + 128u, va);
+                process(vb, 1);
+                tmem_ld_wait();
+                tmem_ld_32x64(t_row + 192u, vb);
+                process(va, 2);
+                tmem_ld_wait();
+                // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                process(vb, 3);
+            }
         }
         if (TMA_STORE && lane == 0) tma_store_wait_all();
     }
@@ -893,8 +919,9 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
 #define FF_GEMM_F(TF, TS, DV, FU)                                                                                     \
     do {                                                                                                              \
-        if (int rc = set_smem(volume_gemm_kernel<TF, TS, DV, FU>, SMEM_GEMM_TOTAL)) return rc;                        \
-        volume_gemm_kernel<TF, TS, DV, FU><<<grid, GEMM_THREADS, SMEM_GEMM_TOTAL, s>>>(ta, tb, tc, tl1, p, fp, idesc); \
+        if (int rc = set_smem(volume_gemm_kernel<TF, TS, DV, FU>, Cfg<FU>::SMEM_TOTAL)) return rc;                    \
+        volume_gemm_kernel<TF, TS, DV, FU><<<grid, Cfg<FU>::THREADS, Cfg<FU>::SMEM_TOTAL, s>>>(ta, tb, tc, tl1, p, fp, \
+                                                                                             idesc);                  \
     } while (0)
 #define FF_GEMM(TF, TS, DV) FF_GEMM_F(TF, TS, DV, false)
 #define FF_GEMM_DV(TF, TS)            \

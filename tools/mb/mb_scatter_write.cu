@@ -12,7 +12,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-struct P { int B, N, tiles_m, tiles_n, sgw, tw0; long long map_floats; int mode; };
+struct P { int B, N, tiles_m, tiles_n, sgw, tw0; long long map_floats; int mode; float *l1, *l2, *l3; int extra; };
 
 __global__ void __launch_bounds__(128) wr(float* __restrict__ out, P p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,6 +33,25 @@ __global__ void __launch_bounds__(128) wr(float* __restrict__ out, P p) {
         }
         for (int c = 0; c < 4; ++c) {
             long long col;   // float offset inside the query map of this chunk's 64 floats
+            if (p.extra && p.mode == 2) {
+                // the other pyramid levels, written like the fused build does: L1 128 B per chunk pair, L2 32 B per
+                // chunk pair, L3 8 B per chunk pair (tw1 = 20, tw2 = 10, tw3 = 6 tiles; maps 1920 / 480 / 192 floats)
+                const int sgy = nt / p.sgw, sgx = nt - sgy * p.sgw;
+                if (c & 1) {
+                    for (int rr = 0; rr < 32; rr += 4) {
+                        const int row = row0 + rr + (lane >> 3);
+                        if (row < p.N && (p.extra & 1))
+                            *reinterpret_cast<float4*>(p.l1 + ((long long)b * p.N + row) * 1920 + ((sgy * 2 + (c >> 1)) * 20 + sgx * 2) * 16 + (lane & 7) * 4) = val;
+                    }
+                    const int row = row0 + lane;
+                    if (row < p.N && (p.extra & 2) && sgy < 3) {
+                        float4* d2 = reinterpret_cast<float4*>(p.l2 + ((long long)b * p.N + row) * 480 + (sgy * 10 + sgx) * 16 + (c - 1) * 4);
+                        d2[0] = val; d2[1] = val;
+                    }
+                    if (row < p.N && (p.extra & 4))
+                        *reinterpret_cast<float2*>(p.l3 + ((long long)b * p.N + row) * 192 + ((sgy >> 1) * 6 + (sgx >> 1)) * 16 + ((sgy & 1) * 2 + (c >> 1)) * 4 + (sgx & 1) * 2) = make_float2(1.f, 2.f);
+                }
+            }
             if (p.mode == 4) {
                 const int sy = nt / p.sgw, sx = nt - sy * p.sgw;      // sgw = n-tiles per row (32 px wide)
                 col = ((long long)(sy * 2 + (c & 1)) * p.tw0 + sx * 8 + (c >> 1) * 4) * 16;
@@ -60,7 +79,7 @@ __global__ void __launch_bounds__(128) wr(float* __restrict__ out, P p) {
 }
 
 int main() {
-    P p; p.B = 8; p.N = 7332; p.tiles_m = 58; p.tw0 = 39; p.map_floats = 7488;
+    P p; p.extra = 0; p.B = 8; p.N = 7332; p.tiles_m = 58; p.tw0 = 39; p.map_floats = 7488;
     float* out; size_t bytes = (size_t)p.B * p.N * 7680 * 4 + (64 << 20);
     cudaMalloc(&out, bytes);
     cudaMemset(out, 0, bytes);
@@ -93,6 +112,25 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         double gb = (double)p.B * p.N * 7680 * 4 / 1e9;
         printf("tw0=40: %-28s %7.3f ms  %7.0f GB/s\n", names[mode], ms, gb / ms * 1e3);
+    }
+    {
+        size_t n = (size_t)p.B * p.N;
+        cudaMalloc(&p.l1, n * 1920 * 4); cudaMalloc(&p.l2, n * 480 * 4); cudaMalloc(&p.l3, n * 192 * 4);
+        const char* en[4] = {"L0 only", "L0+L1", "L0+L1+L2", "L0+L1+L2+L3"};
+        const int ex[4] = {0, 1, 3, 7};
+        const double fl[4] = {7680, 7680 + 1920, 7680 + 1920 + 480, 7680 + 1920 + 480 + 160};
+        for (int k = 0; k < 4; ++k) {
+            p.mode = 2; p.tw0 = 40; p.map_floats = 7680; p.sgw = 10; p.tiles_n = 30; p.extra = ex[k];
+            for (int rep = 0; rep < 2; ++rep) {
+                cudaEventRecord(e0);
+                wr<<<148, 128>>>(out, p);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+            }
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double gb = (double)p.B * p.N * fl[k] * 4 / 1e9;
+            printf("fused pattern %-14s            %7.3f ms  %7.0f GB/s  %s\n", en[k], ms, gb / ms * 1e3, cudaGetErrorString(cudaGetLastError()));
+        }
+        p.extra = 0;
     }
     p.tw0 = 39; p.map_floats = 7488;
     // more CTAs per SM for the linear case (LSU-issue bound with 4 warps/SM?)
