@@ -157,6 +157,56 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     return res
 
 
+def time_stock_aten(config=2, iters=5, dev="cuda:0", sigma=3.0, verbose=False, tf32=True):
+    """The same operations through stock PyTorch CUDA ops (what the reference's corr.py / utils.py run on a GPU):
+    torch.matmul + divide, 3x avg_pool2d, and per level meshgrid + grid_sample.  Measurement only."""
+    import torch.nn.functional as F
+
+    b, d, h, w = raft_shapes(config)
+    n = h * w
+    torch.manual_seed(1234)
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    f1 = torch.randn(b, d, h, w, device=dev) * 4.4
+    f2 = torch.randn(b, d, h, w, device=dev) * 4.4
+    coords = torch.stack(torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")[::-1], 0).float()
+    coords = coords[None].repeat(b, 1, 1, 1) + torch.randn(b, 2, h, w, device=dev) * sigma
+    flush = L2Flusher(dev)
+    state = {}
+
+    def build():
+        corr = torch.matmul(f1.view(b, d, n).transpose(1, 2), f2.view(b, d, n)).view(b, h, w, 1, h, w)
+        corr = (corr / torch.sqrt(torch.tensor(d).float())).reshape(b * n, 1, h, w)
+        pyr = [corr]
+        for _ in range(3):
+            corr = F.avg_pool2d(corr, 2, stride=2)
+            pyr.append(corr)
+        state["pyr"] = pyr
+
+    def lookup():
+        r = 4
+        c = coords.permute(0, 2, 3, 1)
+        out = []
+        for i, corr in enumerate(state["pyr"]):
+            dx = torch.linspace(-r, r, 2 * r + 1, device=dev)
+            dy = torch.linspace(-r, r, 2 * r + 1, device=dev)
+            delta = torch.stack(torch.meshgrid(dy, dx, indexing="ij"), axis=-1)
+            cl = c.reshape(b * n, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+            hh, ww = corr.shape[-2:]
+            xg, yg = cl.split([1, 1], dim=-1)
+            grid = torch.cat([2 * xg / (ww - 1) - 1, 2 * yg / (hh - 1) - 1], dim=-1)
+            out.append(F.grid_sample(corr, grid, align_corners=True).view(b, h, w, -1))
+        return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+
+    res = []
+    for name, fn in (("stock_aten_build", build), ("stock_aten_lookup", lookup)):
+        med, best = time_cuda(fn, iters=iters, warmup=2, flush=flush)
+        rec = {"kernel": name, "config": config, "ms": round(med, 4), "ms_min": round(best, 4), "tf32_matmul": tf32}
+        res.append(rec)
+        if verbose:
+            print(json.dumps(rec), flush=True)
+    return res
+
+
 def time_pwc(iters=10, dev="cuda:0", batch=16, verbose=False, warmup=3):
     import focusflow_official_b200 as ff
 
@@ -207,6 +257,7 @@ if __name__ == "__main__":
     ap.add_argument("--smooth", action="store_true", help="smooth synthetic flow instead of iid noise")
     ap.add_argument("--only", default=None, help="comma-separated substrings of kernel names to time")
     ap.add_argument("--pwc", action="store_true")
+    ap.add_argument("--stock", action="store_true", help="also time the same ops through stock PyTorch CUDA kernels")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--all-precisions", action="store_true")
     a = ap.parse_args()
@@ -217,5 +268,7 @@ if __name__ == "__main__":
     else:
         time_kernels(a.config, a.iters, a.precision, sigma=a.sigma, verbose=True, warmup=a.warmup, smooth=a.smooth,
                          only=a.only.split(',') if a.only else None)
+    if a.stock:
+        time_stock_aten(a.config, sigma=a.sigma, verbose=True)
     if a.pwc:
         time_pwc(a.iters, verbose=True, warmup=a.warmup)
