@@ -160,27 +160,68 @@ def _lookup_raw(levels, level_ptrs, coords: torch.Tensor, radius: int) -> torch.
 # autograd wrappers (reference: ATen autograd of corr.py:26,45,58; coords never need a
 # gradient because the caller detaches them, raft.py:216-217)
 # ------------------------------------------------------------------------------------
+class _GradSink:
+    """Gradient of the pyramid of ONE CorrBlock, shared by all its lookups.
+
+    The reference's autograd materialises a pyramid-sized gradient per lookup and sums them (12-32 adds of
+    ~345 MB each at config 5).  Here every lookup's backward scatters straight into one zero-initialised
+    buffer (``ffcorr_lookup_bwd_f32`` accumulates), and ``_VolumePyramid.backward`` -- which autograd runs after
+    all lookups because they all consume its ``anchor`` output -- turns it into the fmap gradients."""
+
+    def __init__(self, shapes, device):
+        self.shapes = shapes
+        self.device = device
+        self.levels = None
+        self.zero = None
+
+    def buffers(self):
+        if self.levels is None:
+            self.levels = [torch.zeros(s, device=self.device, dtype=torch.float32) for s in self.shapes]
+        return self.levels
+
+    def take(self):
+        lv, self.levels = self.levels, None     # a second backward (retain_graph) starts from zero again
+        return lv
+
+    def anchor_grad(self):
+        if self.zero is None:
+            self.zero = torch.zeros(1, device=self.device, dtype=torch.float32)
+        return self.zero
+
+
 class _VolumePyramid(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, fmap1, fmap2, num_levels, precision):
+    def forward(ctx, fmap1, fmap2, num_levels, precision, sink):
         levels = _volume_pyramid_raw(fmap1, fmap2, num_levels, precision)
         ctx.save_for_backward(fmap1, fmap2)
         ctx.num_levels = num_levels
-        return tuple(levels)
+        ctx.sink = sink
+        ctx.set_materialize_grads(False)
+        if sink is None:
+            return tuple(levels)
+        return (*levels, torch.zeros(1, device=fmap1.device, dtype=torch.float32))   # + the anchor
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, *grads):
         fmap1, fmap2 = ctx.saved_tensors
         b, d, h, w = fmap1.shape
         L = _lib.lib()
         shapes = _level_shapes(b, h, w, ctx.num_levels)
-        g = []
-        for i, (gi, s) in enumerate(zip(grads, shapes)):
-            if gi is None:
-                g.append(torch.zeros(s, device=fmap1.device, dtype=torch.float32))
-            else:
-                gi = gi.contiguous().float()
-                g.append(gi.clone() if i < ctx.num_levels - 1 else gi)  # finer levels are updated in place
+        g = ctx.sink.take() if ctx.sink is not None else None
+        direct = grads[:ctx.num_levels]              # gradients of levels used directly (corr_pyramid[i] in a loss)
+        if g is None:
+            g = []
+            for i, (gi, s) in enumerate(zip(direct, shapes)):
+                if gi is None:
+                    g.append(torch.zeros(s, device=fmap1.device, dtype=torch.float32))
+                else:
+                    gi = gi.contiguous().float()
+                    g.append(gi.clone() if i < ctx.num_levels - 1 else gi)  # finer levels are updated in place
+        else:
+            for gl, gi in zip(g, direct):
+                if gi is not None:
+                    gl.add_(gi.reshape(gl.shape))
         stream = _lib.current_stream()
         _lib.check(L.ffcorr_pyramid_bwd_f32(_lib.ptr_array(g), ctx.num_levels, b * h * w, h, w, stream),
                    "ffcorr_pyramid_bwd_f32")
@@ -190,27 +231,32 @@ class _VolumePyramid(torch.autograd.Function):
                                            g1.data_ptr() if g1 is not None else None,
                                            g2.data_ptr() if g2 is not None else None, b, d, h, w, stream),
                    "ffcorr_volume_bwd_f32")
-        return g1, g2, None, None
+        return g1, g2, None, None, None
 
 
 class _Lookup(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, coords, radius, *levels):
+    def forward(ctx, coords, radius, sink, anchor, *levels):
         out = _lookup_raw(levels, _lib.ptr_array(levels), coords, radius)
         ctx.save_for_backward(coords)
         ctx.radius = radius
+        ctx.sink = sink
         ctx.shapes = [tuple(l.shape) for l in levels]
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         (coords,) = ctx.saved_tensors
         b, _, h, w = coords.shape
         gout = gout.contiguous().float()
-        glv = [torch.zeros(s, device=coords.device, dtype=torch.float32) for s in ctx.shapes]
+        shared = ctx.sink is not None
+        glv = ctx.sink.buffers() if shared else [torch.zeros(s, device=coords.device, dtype=torch.float32) for s in ctx.shapes]
         _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), len(glv), coords.data_ptr(), gout.data_ptr(),
                                                     b, h, w, ctx.radius, _lib.current_stream()), "ffcorr_lookup_bwd_f32")
-        return (None, None, *glv)
+        if shared:   # the gradient reaches _VolumePyramid through the sink; the anchor only orders the two
+            return (None, None, None, ctx.sink.anchor_grad(), *([None] * len(glv)))
+        return (None, None, None, None, *glv)
 
 
 def _prep(fmap: torch.Tensor, name: str) -> torch.Tensor:
@@ -236,7 +282,7 @@ def correlation_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None) -> Li
         raise ValueError(f"fmap shapes differ: {tuple(fmap1.shape)} vs {tuple(fmap2.shape)}")
     code = _precision_code(precision)
     if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
-        return list(_VolumePyramid.apply(fmap1, fmap2, num_levels, code))
+        return list(_VolumePyramid.apply(fmap1, fmap2, num_levels, code, None))
     return _volume_pyramid_raw(fmap1, fmap2, num_levels, code)
 
 
@@ -250,7 +296,7 @@ def lookup(levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None) -> to
     _require_cuda(coords, "coords")
     coords = coords.float().contiguous()
     if torch.is_grad_enabled() and any(l.requires_grad for l in levels):
-        return _Lookup.apply(coords, radius, *levels)
+        return _Lookup.apply(coords, radius, None, None, *levels)
     return _lookup_raw(levels, level_ptrs if level_ptrs is not None else _lib.ptr_array(levels), coords, radius)
 
 
@@ -261,6 +307,7 @@ class CorrBlock:
         self.radius = radius
         b, _, h, w = fmap1.shape
         self._shape = (b, h, w)
+        self._sink = None
         layout = layout or DEFAULT_LAYOUT
         if layout not in ("tiled", "rowmajor"):
             raise ValueError(f"layout must be 'tiled' or 'rowmajor', got {layout!r}")
@@ -276,6 +323,14 @@ class CorrBlock:
                 raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
             self._levels = _volume_pyramid_tiled_raw(f1, f2, num_levels, code)
             self._rowmajor = None                      # materialised on first access of .corr_pyramid
+        elif needs_grad:
+            f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
+            if f1.shape != f2.shape:
+                raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
+            self._sink = _GradSink(_level_shapes(b, h, w, num_levels), f1.device)
+            outs = _VolumePyramid.apply(f1, f2, num_levels, code, self._sink)
+            self._levels, self._anchor = list(outs[:-1]), outs[-1]
+            self._rowmajor = self._levels
         else:
             self._levels = correlation_pyramid(fmap1, fmap2, num_levels, precision)
             self._rowmajor = self._levels
@@ -296,6 +351,9 @@ class CorrBlock:
             raise ValueError(f"coords {tuple(coords.shape)} does not match the volume built for B,h,w={self._shape}")
         if self._tiled:
             return lookup_tiled(self._levels, coords, self.radius, self._ptrs)
+        if self._sink is not None and torch.is_grad_enabled():
+            _require_cuda(coords, "coords")
+            return _Lookup.apply(coords.float().contiguous(), self.radius, self._sink, self._anchor, *self._levels)
         return lookup(self._levels, coords, self.radius, self._ptrs)
 
     @staticmethod

@@ -298,6 +298,55 @@ def test_corrblock_gradients_match_torch_autograd():
     assert float((g2 - f2.grad).norm() / f2.grad.norm()) <= 1e-4
 
 
+def test_corrblock_gradients_many_lookups_and_direct_level_use():
+    """12 lookups share one gradient buffer (_GradSink); a level used directly in the loss adds to it; a second
+    backward through the retained graph starts from zero again."""
+    m = ff()
+    torch.manual_seed(6)
+    b, d, h, w = 1, 16, 16, 24
+    n = h * w
+    f1 = torch.randn(b, d, h, w, device=DEV, requires_grad=True)
+    f2 = torch.randn(b, d, h, w, device=DEV, requires_grad=True)
+    coords = [m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 2 for _ in range(12)]
+    wgt = [torch.randn(b, 324, h, w, device=DEV) for _ in range(12)]
+    wl1 = torch.randn(b * n, 1, h // 2, w // 2, device=DEV)
+
+    def ref_loss():
+        corr = torch.matmul(f1.view(b, d, n).transpose(1, 2), f2.view(b, d, n)) / torch.sqrt(torch.tensor(float(d)))
+        cur = corr.reshape(b * n, 1, h, w)
+        pyr = [cur]
+        for _ in range(3):
+            cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+            pyr.append(cur)
+        dd = torch.linspace(-4, 4, 9, device=DEV)
+        delta = torch.stack(torch.meshgrid(dd, dd, indexing="ij"), dim=-1).view(1, 9, 9, 2)
+        loss = (pyr[1] * wl1).sum()
+        for cds, wg in zip(coords, wgt):
+            c = cds.permute(0, 2, 3, 1).reshape(b * n, 1, 1, 2)
+            outs = []
+            for i, lv in enumerate(pyr):
+                cl = c / 2 ** i + delta
+                hh, ww = lv.shape[-2:]
+                grid = torch.stack([2 * cl[..., 0] / (ww - 1) - 1, 2 * cl[..., 1] / (hh - 1) - 1], -1)
+                outs.append(torch.nn.functional.grid_sample(lv, grid, align_corners=True).view(b, h, w, -1))
+            loss = loss + (torch.cat(outs, -1).permute(0, 3, 1, 2) * wg).sum()
+        return loss
+
+    blk = m.CorrBlock(f1, f2, precision="fp32")
+    loss = (blk.corr_pyramid[1] * wl1).sum()
+    for cds, wg in zip(coords, wgt):
+        loss = loss + (blk(cds) * wg).sum()
+    loss.backward(retain_graph=True)
+    g1, g2 = f1.grad.clone(), f2.grad.clone()
+    f1.grad = f2.grad = None
+    loss.backward()                      # second pass through the same graph: same gradients, not doubled
+    assert torch.allclose(f1.grad, g1, rtol=1e-5, atol=1e-5) and torch.allclose(f2.grad, g2, rtol=1e-5, atol=1e-5)
+    f1.grad = f2.grad = None
+    ref_loss().backward()
+    assert float((g1 - f1.grad).norm() / f1.grad.norm()) <= 1e-4
+    assert float((g2 - f2.grad).norm() / f2.grad.norm()) <= 1e-4
+
+
 def test_lookup_backward_vs_oracle_adjoint():
     from focusflow_official_b200 import _lib
 
