@@ -44,7 +44,7 @@ _PROTOS = {
     "ffcorr_tile_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_lookup_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ffcorr_pyramid_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
-    "ffcorr_volume_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_volume_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_pwc81_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]),
     "ffcorr_pwc81_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }

@@ -195,6 +195,7 @@ class _VolumePyramid(torch.autograd.Function):
         levels = _volume_pyramid_raw(fmap1, fmap2, num_levels, precision)
         ctx.save_for_backward(fmap1, fmap2)
         ctx.num_levels = num_levels
+        ctx.precision = precision
         ctx.sink = sink
         ctx.set_materialize_grads(False)
         if sink is None:
@@ -217,7 +218,7 @@ class _VolumePyramid(torch.autograd.Function):
                     g.append(torch.zeros(s, device=fmap1.device, dtype=torch.float32))
                 else:
                     gi = gi.contiguous().float()
-                    g.append(gi.clone() if i < ctx.num_levels - 1 else gi)  # finer levels are updated in place
+                    g.append(gi.clone())     # updated in place below (pooling adjoint, in-place transpose)
         else:
             for gl, gi in zip(g, direct):
                 if gi is not None:
@@ -229,7 +230,7 @@ class _VolumePyramid(torch.autograd.Function):
         g2 = torch.empty_like(fmap2) if ctx.needs_input_grad[1] else None
         _lib.check(L.ffcorr_volume_bwd_f32(g[0].data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(),
                                            g1.data_ptr() if g1 is not None else None,
-                                           g2.data_ptr() if g2 is not None else None, b, d, h, w, stream),
+                                           g2.data_ptr() if g2 is not None else None, b, d, h, w, ctx.precision, stream),
                    "ffcorr_volume_bwd_f32")
         return g1, g2, None, None, None
 

@@ -196,7 +196,9 @@ struct GemmParams {
     float scale;    // 1/sqrt(D) (exact when D is a power of 4) or 1 when divide != 0
     float divisor;  // sqrt(D)
     int use_div;    // 1: fp32 divide like the reference; 0: multiply by the exact reciprocal
-    float* out;     // only used by the non-TMA epilogue (N % 4 != 0)
+    float* out;     // only used by the non-TMA epilogue (N % 4 != 0, backward GEMMs)
+    int out_transposed;   // non-TMA epilogue: write C^T, i.e. out[b][col][row] with row pitch ldc (backward GEMMs)
+    int64_t ldc;
 };
 
 // Fused pyramid build (ffcorr_build_tiled_f32): the GEMM's N order is made of 16x16-pixel SUPER-GROUPS
@@ -501,10 +503,18 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         const int row = row0 + lane;
                         if (row < p.N) {
                             scale_chunk(v);
-                            float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.Ncols + col0;
+                            if (p.out_transposed) {
+                                // 32 lanes = 32 consecutive rows -> every store instruction writes one 128-byte line
+                                float* o = p.out + ((int64_t)b * p.Ncols + col0) * p.ldc + row;
 #pragma unroll
-                            for (int i = 0; i < 64; ++i)
-                                if (col0 + i < p.Ncols) o[i] = scaled(v[i]);
+                                for (int i = 0; i < 64; ++i)
+                                    if (col0 + i < p.Ncols) o[(int64_t)i * p.ldc] = scaled(v[i]);
+                            } else {
+                                float* o = p.out + ((int64_t)b * p.N + row) * (int64_t)p.Ncols + col0;
+#pragma unroll
+                                for (int i = 0; i < 64; ++i)
+                                    if (col0 + i < p.Ncols) o[i] = scaled(v[i]);
+                            }
                         }
                     }
                 };
@@ -755,6 +765,36 @@ int set_smem(K kernel, int bytes) {
     return FFCORR_OK;
 }
 
+// In-place transpose of B square [n x n] fp32 matrices (the level-0 gradient before the second backward GEMM):
+// block (ti, tj), ti <= tj, swaps tiles (ti, tj) and (tj, ti) through shared memory.
+__global__ void __launch_bounds__(256) transpose_inplace_kernel(float* __restrict__ g, int n, int tiles) {
+    __shared__ float ta[32][33], tb[32][33];
+    // linear block index -> (ti <= tj) of the upper triangle
+    int k = blockIdx.x, ti = 0;
+    while (k >= tiles - ti) { k -= tiles - ti; ++ti; }
+    const int tj = ti + k;
+    float* m = g + (size_t)blockIdx.y * n * n;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int ia = ti * 32 + r, ja = tj * 32 + tx;          // element of tile (ti, tj)
+        const int ib = tj * 32 + r, jb = ti * 32 + tx;          // element of tile (tj, ti)
+        ta[r][tx] = (ia < n && ja < n) ? m[(size_t)ia * n + ja] : 0.f;
+        tb[r][tx] = (ib < n && jb < n) ? m[(size_t)ib * n + jb] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int ia = ti * 32 + r, ja = tj * 32 + tx;
+        const int ib = tj * 32 + r, jb = ti * 32 + tx;
+        if (ia < n && ja < n) m[(size_t)ia * n + ja] = tb[tx][r];
+        if (ti != tj && ib < n && jb < n) m[(size_t)ib * n + jb] = ta[tx][r];
+    }
+}
+
+// C^T[b][n][m] = (sum_k A[b][m][k] * Bm[b][n][k]) / divisor on the tensor cores (kind::tf32 straight from the fp32
+// arrays: both operands are K-major as they lie in memory, so there is no pre-pass).  K*4 must be a multiple of 16.
+int launch_gemm_nt_tf32(const float* A, const float* Bm, float* Ct, int M, int Nn, int K, int batches, float divisor,
+                        cudaStream_t s);
+
 int launch_sgemm(bool a_mcontig, bool b_ncontig, const float* A, const float* Bm, float* C, int M, int Nn, int K,
                  int64_t a_sm, int64_t a_sk, int64_t b_sk, int64_t b_sn, int64_t c_ld, int64_t a_batch, int64_t b_batch,
                  int64_t c_batch, int batches, float divisor, cudaStream_t s) {
@@ -943,6 +983,48 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     return check_launch("volume_gemm_kernel");
 }
 
+namespace ffcorr {
+namespace {
+int launch_gemm_nt_tf32(const float* A, const float* Bm, float* Ct, int M, int Nn, int K, int batches, float divisor,
+                        cudaStream_t s) {
+    CUtensorMap ta, tb;
+    const uint64_t row_bytes = (uint64_t)K * 4;
+    if (int rc = encode_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(A), K, M, batches, row_bytes,
+                           row_bytes * M, BK_BYTES / 4, BM, "bwd A")) return rc;
+    if (int rc = encode_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(Bm), K, Nn, batches, row_bytes,
+                           row_bytes * Nn, BK_BYTES / 4, BN, "bwd B")) return rc;
+    GemmParams p{};
+    p.N = M;
+    p.Ncols = Nn;
+    p.B = batches;
+    p.num_kb = (int)((row_bytes + BK_BYTES - 1) / BK_BYTES);   // the K tail is zero-filled by TMA
+    p.tiles_m = ceil_div(M, BM);
+    p.tiles_n = ceil_div(Nn, BN);
+    p.divisor = divisor;
+    int e = 0;
+    const float mant = frexpf(divisor, &e);
+    p.use_div = (mant == 0.5f) ? 0 : 1;
+    p.scale = 1.0f / divisor;
+    p.out = Ct;
+    p.out_transposed = 1;
+    p.ldc = M;
+    FusedParams fp{};
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const int64_t num_tiles = (int64_t)p.tiles_m * p.tiles_n * batches;
+    FFCORR_REQUIRE(num_tiles < (1ll << 31), FFCORR_EINVAL, "volume_bwd: too many tiles");
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    if (p.use_div) {
+        if (int rc = set_smem(volume_gemm_kernel<true, false, true, false>, Cfg<false>::SMEM_TOTAL)) return rc;
+        volume_gemm_kernel<true, false, true, false><<<grid, Cfg<false>::THREADS, Cfg<false>::SMEM_TOTAL, s>>>(ta, tb, ta, ta, p, fp, idesc);
+    } else {
+        if (int rc = set_smem(volume_gemm_kernel<true, false, false, false>, Cfg<false>::SMEM_TOTAL)) return rc;
+        volume_gemm_kernel<true, false, false, false><<<grid, Cfg<false>::THREADS, Cfg<false>::SMEM_TOTAL, s>>>(ta, tb, ta, ta, p, fp, idesc);
+    }
+    return check_launch("volume_gemm_kernel (backward)");
+}
+}  // namespace
+}  // namespace ffcorr
+
 extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
                                  int precision, void* workspace, size_t workspace_bytes, void* stream) {
     return volume_impl(fmap1, fmap2, lvl0, B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_ROWMAJOR);
@@ -971,8 +1053,8 @@ extern "C" int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, fl
                        lvl, num_levels);
 }
 
-extern "C" int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1, const float* fmap2, float* gfmap1,
-                                     float* gfmap2, int B, int D, int h, int w, void* stream) {
+extern "C" int ffcorr_volume_bwd_f32(float* grad_lvl0, const float* fmap1, const float* fmap2, float* gfmap1,
+                                     float* gfmap2, int B, int D, int h, int w, int precision, void* stream) {
     FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume_bwd: bad shape");
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(grad_lvl0 && fmap1 && fmap2, FFCORR_EINVAL, "volume_bwd: null pointer");
@@ -980,6 +1062,22 @@ extern "C" int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1,
     const int N = h * w;
     const float sqrt_d = sqrtf((float)D);
     const int64_t fb = (int64_t)D * N, gb = (int64_t)N * N;
+    const bool aligned = ((uintptr_t)grad_lvl0 % 16 == 0) && ((uintptr_t)fmap1 % 16 == 0) && ((uintptr_t)fmap2 % 16 == 0);
+    if (precision != FFCORR_PREC_FP32 && N % 4 == 0 && aligned && N >= 32) {
+        // tensor-core path (tf32 operands, fp32 accumulate -- what the reference's cuBLAS backward does under
+        // ALLOW_TF32).  gf1^T[i,d] = sum_j g[i,j] f2[d,j]: both operands K-major in place.  gf2^T[j,d] = sum_i
+        // g[i,j] f1[d,i] needs g^T: the gradient is dead after this call, so it is transposed in place.
+        if (gfmap1)
+            if (int rc = launch_gemm_nt_tf32(grad_lvl0, fmap2, gfmap1, N, D, N, B, sqrt_d, s)) return rc;
+        if (gfmap2) {
+            const int tiles = ceil_div(N, 32);
+            FFCORR_REQUIRE(B < 65536, FFCORR_EINVAL, "volume_bwd: B=%d too large", B);
+            transpose_inplace_kernel<<<dim3((unsigned)((int64_t)tiles * (tiles + 1) / 2), B), 256, 0, s>>>(grad_lvl0, N, tiles);
+            if (int rc = check_launch("transpose_inplace_kernel")) return rc;
+            if (int rc = launch_gemm_nt_tf32(grad_lvl0, fmap1, gfmap2, N, D, N, B, sqrt_d, s)) return rc;
+        }
+        return FFCORR_OK;
+    }
     if (gfmap1) {
         // gf1[d,i] = sum_j f2[d,j] g[i,j]: A[m=d,k=j] = f2 (k contiguous), B[k=j,n=i] = g[i*N+j] (k contiguous)
         if (int rc = launch_sgemm(false, false, fmap2, grad_lvl0, gfmap1, D, N, N, N, 1, 1, N, N, fb, gb, fb, B, sqrt_d, s))

@@ -151,10 +151,13 @@ int ffcorr_pyramid_bwd_f32(float* const* grad_lvl, int num_levels, int64_t Q, in
 /*
  * Adjoint of the volume: gfmap1[b,d,i] = sum_j g[b,i,j] fmap2[b,d,j] / sqrt(D),
  *                         gfmap2[b,d,j] = sum_i g[b,i,j] fmap1[b,d,i] / sqrt(D).
- * fp32 CUDA-core path.  Either gradient pointer may be NULL.
+ * precision FFCORR_PREC_FP32: exact CUDA-core path.  Any other precision: tcgen05 kind::tf32 straight from the
+ * fp32 arrays (what the reference's cuBLAS backward does under ALLOW_TF32; needs h*w % 4 == 0, else the
+ * CUDA-core path runs).  grad_lvl0 is SCRATCH: the tensor-core path transposes it in place for the second
+ * product, so its content is unspecified afterwards.  Either gradient pointer may be NULL.
  */
-int ffcorr_volume_bwd_f32(const float* grad_lvl0, const float* fmap1, const float* fmap2,
-                          float* gfmap1, float* gfmap2, int B, int D, int h, int w, void* stream);
+int ffcorr_volume_bwd_f32(float* grad_lvl0, const float* fmap1, const float* fmap2,
+                          float* gfmap1, float* gfmap2, int B, int D, int h, int w, int precision, void* stream);
 
 /*
  * PWC local cost volume, max displacement 4 (81 channels).

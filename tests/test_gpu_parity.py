@@ -298,6 +298,31 @@ def test_corrblock_gradients_match_torch_autograd():
     assert float((g2 - f2.grad).norm() / f2.grad.norm()) <= 1e-4
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 16, 20), (1, 256, 46, 62), (1, 24, 9, 13), (2, 40, 8, 8)])
+@pytest.mark.parametrize("precision", ["fp16", "tf32"])
+def test_tensor_core_backward_gemms(shape, precision):
+    """precision != fp32: the two backward GEMMs run on tcgen05 (tf32 operands) when h*w % 4 == 0; they must agree
+    with the exact CUDA-core path to tf32 accuracy, for the volume gradient alone and through a lookup."""
+    m = ff()
+    torch.manual_seed(9)
+    b, d, h, w = shape
+    f1 = (torch.randn(shape, device=DEV) * 2).requires_grad_(True)
+    f2 = (torch.randn(shape, device=DEV) * 2).requires_grad_(True)
+    nl = 4 if min(h, w) >= 8 else 1
+    coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 2
+    wgt = torch.randn(b, nl * 81, h, w, device=DEV)
+    wl0 = torch.randn(b * h * w, 1, h, w, device=DEV)
+    grads = {}
+    for prec in (precision, "fp32"):
+        f1.grad = f2.grad = None
+        blk = m.CorrBlock(f1, f2, num_levels=nl, precision=prec)
+        ((blk(coords) * wgt).sum() + (blk.corr_pyramid[0] * wl0).sum()).backward()
+        grads[prec] = (f1.grad.clone(), f2.grad.clone())
+    for got, ref in zip(grads[precision], grads["fp32"]):
+        assert torch.isfinite(got).all()
+        assert float((got - ref).norm() / ref.norm()) <= 2e-3, float((got - ref).norm() / ref.norm())
+
+
 def test_corrblock_gradients_many_lookups_and_direct_level_use():
     """12 lookups share one gradient buffer (_GradSink); a level used directly in the loss adds to it; a second
     backward through the retained graph starts from zero again."""
