@@ -523,41 +523,174 @@ struct LookupBwdParams {
     int B, N, num_levels, radius;
 };
 
-__global__ void __launch_bounds__(256) lookup_bwd_kernel(const LookupBwdParams p) {
-    const int K = 2 * p.radius + 1;
-    const int KK = K * K;
-    const int CT = p.num_levels * KK;
-    const int64_t total = (int64_t)p.B * CT * p.N;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(idx % p.N);
-        const int64_t t = idx / p.N;
-        const int ch = (int)(t % CT);
-        const int b = (int)(t / CT);
-        const int level = ch / KK;
-        const int k = ch - level * KK;
-        const int a = k / K, bb = k - a * K;
-        const float g = __ldg(p.gout + idx);
-        if (g == 0.0f) continue;
-        const int lh = p.lh[level], lw = p.lw[level];
-        const float inv_scale = __int_as_float((127 - level) << 23);
-        const float cx = __ldg(p.coords + (size_t)b * 2 * p.N + n) * inv_scale;
-        const float cy = __ldg(p.coords + (size_t)b * 2 * p.N + p.N + n) * inv_scale;
-        const float ix = source_index(__fadd_rn(cx, (float)(a - p.radius)), (float)(lw - 1));
-        const float iy = source_index(__fadd_rn(cy, (float)(bb - p.radius)), (float)(lh - 1));
-        if (!(fabsf(ix) < kWildLimit) || !(fabsf(iy) < kWildLimit)) continue;
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = (int)fx, y0 = (int)fy;
-        const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
-        const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
-        float* m = p.glvl[level] + ((int64_t)b * p.N + n) * ((int64_t)lh * lw);
-        const bool xa = (unsigned)x0 < (unsigned)lw, xb = (unsigned)(x0 + 1) < (unsigned)lw;
-        const bool ya = (unsigned)y0 < (unsigned)lh, yb = (unsigned)(y0 + 1) < (unsigned)lh;
-        if (ya && xa) atomicAdd(m + y0 * lw + x0, g * (wx0 * wy0));
-        if (ya && xb) atomicAdd(m + y0 * lw + x0 + 1, g * (wx1 * wy0));
-        if (yb && xa) atomicAdd(m + (y0 + 1) * lw + x0, g * (wx0 * wy1));
-        if (yb && xb) atomicAdd(m + (y0 + 1) * lw + x0 + 1, g * (wx1 * wy1));
+// Mirror image of lookup_kernel.  Phase A (lane = query) as in the forward; then every lane builds the gradient
+// of ITS window in shared memory -- no atomics, the window is private -- using the same separable form: the 81
+// output gradients are folded along x into 9 horizontal rows, and window row r = wy0[r] * hrow[r] +
+// wy1[r-1] * hrow[r-1]; finally the warp flushes the 32 windows cooperatively, 32 consecutive window elements
+// per instruction, with red.global.add (the pyramid gradient accumulates over the lookups of all iterations).
+// ~100 reductions per (query, level) in row-contiguous runs instead of 324 scattered ones.
+template <int R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_bwd_kernel(const LookupBwdParams p, const int tiles_per_batch,
+                                                                         const int blocks_per_batch) {
+    constexpr int K = 2 * R + 1;
+    constexpr int W2 = K + 2;
+    constexpr int WIN = W2 * W2;
+    constexpr int NLOAD = (WIN + 31) / 32;
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    float* swin = smem + warp * (kTile * WIN);
+
+    int bid = blockIdx.x;
+    const int per_level = p.B * blocks_per_batch;
+    const int level = bid / per_level;
+    bid -= level * per_level;
+    const int b = bid / blocks_per_batch;
+    const int tile = (bid - b * blocks_per_batch) * kWarpsPerBlock + warp;
+    if (tile >= tiles_per_batch) return;
+
+    const int N = p.N;
+    const int n0 = tile * kTile;
+    const int n = n0 + lane;
+    const bool valid = n < N;
+    const int lh = p.lh[level], lw = p.lw[level];
+    const float inv_scale = __int_as_float((127 - level) << 23);
+
+    // ---------------- phase A: window origin and in-bounds masks (as lookup_kernel) ----------------
+    float cx = 0.f, cy = 0.f;
+    if (valid) {
+        const float* c = p.coords + (size_t)b * 2 * N + n;
+        cx = __ldg(c) * inv_scale;
+        cy = __ldg(c + N) * inv_scale;
     }
+    const float sx = (float)(lw - 1), sy = (float)(lh - 1);
+    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
+    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
+    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
+    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
+    const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
+                      !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
+    const int map_elems = lh * lw;
+    int x_lo = 0, y_lo = 0;
+    int my_mask = 0, my_qoff = 0;
+    if (valid && !wild) {
+        x_lo = (int)floorf(ixf);
+        y_lo = (int)floorf(iyf);
+        const int ncols = min((int)floorf(ixl) + 2 - x_lo, W2);
+        const int nrows = min((int)floorf(iyl) + 2 - y_lo, W2);
+        const int rlo = max(0, -y_lo), rhi = min(nrows, lh - y_lo);
+        const int clo = max(0, -x_lo), chi = min(ncols, lw - x_lo);
+        const int rm = (rhi > rlo) ? (((1 << rhi) - 1) & ~((1 << rlo) - 1)) : 0;
+        const int cm = (chi > clo) ? (((1 << chi) - 1) & ~((1 << clo) - 1)) : 0;
+        my_mask = (rm && cm) ? (rm | (cm << 16)) : 0;
+        my_qoff = lane * map_elems + y_lo * lw + x_lo;
+    }
+
+    int rx[K], ry[K];
+    float wx0[K], wx1[K], wy0[K], wy1[K];
+    bool deviated = false;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
+        const float fx = floorf(ix);
+        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
+        const float fy = floorf(iy);
+        const bool dead = wild || !valid;
+        wx1[a] = dead ? 0.f : __fsub_rn(ix, fx);
+        wx0[a] = dead ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+        wy1[a] = dead ? 0.f : __fsub_rn(iy, fy);
+        wy0[a] = dead ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+        rx[a] = dead ? a : min(max((int)fx - x_lo, 0), W2 - 2);
+        ry[a] = dead ? a : min(max((int)fy - y_lo, 0), W2 - 2);
+        deviated |= (rx[a] != a) | (ry[a] != a);
+    }
+
+    // ---------------- per-lane window gradient in shared memory ----------------
+    float* sq = swin + lane * WIN;
+    const int CT = p.num_levels * K * K;
+    const float* __restrict__ gp = p.gout + ((int64_t)b * CT + (int64_t)level * K * K) * N + min(n, N - 1);
+    if (!__any_sync(0xffffffffu, deviated)) {
+        float hprev[K + 1];
+#pragma unroll
+        for (int c = 0; c <= K; ++c) hprev[c] = 0.f;
+#pragma unroll
+        for (int r = 0; r <= K; ++r) {
+            float hcur[K + 1];
+#pragma unroll
+            for (int c = 0; c <= K; ++c) hcur[c] = 0.f;
+            if (r < K) {
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    const float g = __ldg(gp + (int64_t)(a * K + r) * N);
+                    hcur[a] = fmaf(g, wx0[a], hcur[a]);
+                    hcur[a + 1] = fmaf(g, wx1[a], hcur[a + 1]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c <= K; ++c) {
+                float v = (r > 0) ? wy1[r > 0 ? r - 1 : 0] * hprev[c] : 0.f;
+                if (r < K) v = fmaf(wy0[r < K ? r : 0], hcur[c], v);
+                sq[r * W2 + c] = v;
+            }
+            sq[r * W2 + K + 1] = 0.f;
+#pragma unroll
+            for (int c = 0; c <= K; ++c) hprev[c] = hcur[c];
+        }
+#pragma unroll
+        for (int c = 0; c < W2; ++c) sq[(K + 1) * W2 + c] = 0.f;
+    } else {
+        for (int e = 0; e < WIN; ++e) sq[e] = 0.f;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+#pragma unroll
+            for (int bb = 0; bb < K; ++bb) {
+                const float g = __ldg(gp + (int64_t)(a * K + bb) * N);
+                float* s = sq + ry[bb] * W2 + rx[a];
+                s[0] = fmaf(g, wx0[a] * wy0[bb], s[0]);
+                s[1] = fmaf(g, wx1[a] * wy0[bb], s[1]);
+                s[W2] = fmaf(g, wx0[a] * wy1[bb], s[W2]);
+                s[W2 + 1] = fmaf(g, wx1[a] * wy1[bb], s[W2 + 1]);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---------------- cooperative flush: red.global.add of the in-bounds window elements ----------------
+    float* __restrict__ tile_base = p.glvl[level] + ((int64_t)b * N + n0) * (int64_t)map_elems;
+    int poff[NLOAD], bits[NLOAD];
+#pragma unroll
+    for (int j = 0; j < NLOAD; ++j) {
+        const int e = lane + 32 * j;
+        const int er = e / W2, ec = e - er * W2;
+        poff[j] = er * lw + ec;
+        bits[j] = (e < WIN) ? ((1 << er) | (1 << (16 + ec))) : 0x80008000;  // never matches
+    }
+#pragma unroll 4
+    for (int q = 0; q < kTile; ++q) {
+        const int qoff = __shfl_sync(0xffffffffu, my_qoff, q);
+        const int msk = __shfl_sync(0xffffffffu, my_mask, q);
+#pragma unroll
+        for (int j = 0; j < NLOAD; ++j) {
+            if ((msk & bits[j]) == bits[j]) {
+                const float v = swin[q * WIN + lane + 32 * j];
+                if (v != 0.f) atomicAdd(tile_base + (poff[j] + qoff), v);
+            }
+        }
+    }
+}
+
+template <int R>
+int launch_lookup_bwd(const LookupBwdParams& p, cudaStream_t stream) {
+    constexpr int K = 2 * R + 1;
+    constexpr int WIN = (K + 2) * (K + 2);
+    const size_t smem = (size_t)kWarpsPerBlock * kTile * WIN * sizeof(float);
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_per_batch = ceil_div(p.N, kTile);
+    const int blocks_per_batch = ceil_div(tiles_per_batch, kWarpsPerBlock);
+    const int64_t blocks = (int64_t)p.num_levels * p.B * blocks_per_batch;
+    FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_bwd: grid too large");
+    lookup_bwd_kernel<R><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p, tiles_per_batch, blocks_per_batch);
+    return check_launch("lookup_bwd_kernel");
 }
 
 template <int R, int QU>
@@ -635,12 +768,14 @@ extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, con
     p.N = h * w;
     p.num_levels = num_levels;
     p.radius = radius;
-    const int K = 2 * radius + 1;
-    const int64_t total = (int64_t)B * num_levels * K * K * p.N;
-    const int64_t want = ceil_div64(total, 256);
-    const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
-    lookup_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    return check_launch("lookup_bwd_kernel");
+    FFCORR_REQUIRE((int64_t)(h) * w < (1ll << 24), FFCORR_EINVAL, "lookup_bwd: h*w too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (radius) {
+        case 1: return launch_lookup_bwd<1>(p, s);
+        case 2: return launch_lookup_bwd<2>(p, s);
+        case 3: return launch_lookup_bwd<3>(p, s);
+        default: return launch_lookup_bwd<4>(p, s);
+    }
 }
 
 

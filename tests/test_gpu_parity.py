@@ -393,6 +393,35 @@ def test_lookup_backward_vs_oracle_adjoint():
         assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), i
 
 
+@pytest.mark.parametrize("shape,radius,nl", [((1, 46, 62), 4, 4), ((2, 17, 21), 4, 4), ((2, 12, 9), 2, 3), ((1, 9, 33), 1, 2),
+                                             ((1, 24, 40), 3, 4)])
+def test_lookup_backward_is_the_adjoint_of_the_forward(shape, radius, nl):
+    """<lookup(P, c), G> == <P, lookup_bwd(G, c)> for integer (exact per-tap path), half-integer, noisy and far
+    out-of-bounds / non-finite coordinates; accumulation over two calls doubles the gradient."""
+    from focusflow_official_b200 import _lib
+
+    m = ff()
+    b, h, w = shape
+    rng = np.random.default_rng(31)
+    q = b * h * w
+    k2 = (2 * radius + 1) ** 2
+    pyr = [t(rng.standard_normal((q, 1, h >> i, w >> i)).astype(np.float32)) for i in range(nl)]
+    for name, c in _coords_cases(rng, b, h, w).items():
+        c_dev = t(c)
+        gout = t(rng.standard_normal((b, nl * k2, h, w)).astype(np.float32))
+        out = m.lookup(pyr, c_dev, radius)
+        lhs = float((out.double() * gout.double()).sum())
+        glv = [torch.zeros_like(p) for p in pyr]
+        for _ in range(2):
+            _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), nl, c_dev.data_ptr(), gout.data_ptr(), b, h, w,
+                                                        radius, _lib.current_stream()), "bwd")
+        torch.cuda.synchronize()
+        rhs = sum(float((p.double() * g.double()).sum()) for p, g in zip(pyr, glv)) / 2
+        scale = float(out.double().abs().mul(gout.double().abs()).sum()) + 1e-30
+        assert all(torch.isfinite(g).all() for g in glv), name
+        assert abs(lhs - rhs) <= 1e-5 * scale, (name, lhs, rhs)
+
+
 # ---------------------------------------------------------------- PWC cost volume
 PWC_SHAPES = [(2, 32, 28, 64), (1, 64, 56, 128), (2, 96, 28, 64), (2, 128, 14, 32), (2, 196, 7, 16),
               (1, 3, 5, 5), (2, 40, 9, 13), (1, 17, 33, 70)]
