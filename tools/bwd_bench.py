@@ -72,6 +72,35 @@ res = {"config": 5, "iters": iters, "stock_aten_tf32_ms": round(timeit(stock), 3
 for p in ("fp16", "fp32"):
     res[f"ffcorr_{p}_ms"] = round(timeit(lambda: ours(p)), 3)
 print(json.dumps(res))
+if "--pwc" in sys.argv:
+    # PWC cost volume forward + backward at the five config-3 level shapes
+    for c, hh, ww in [(32, 112, 256), (64, 56, 128), (96, 28, 64), (128, 14, 32), (196, 7, 16)]:
+        one = torch.randn(16, c, hh, ww, device=dev, requires_grad=True)
+        two = torch.randn(16, c, hh, ww, device=dev, requires_grad=True)
+        go = torch.randn(16, 81, hh, ww, device=dev)
+
+        def fb():
+            one.grad = two.grad = None
+            ff.FunctionCorrelation(one, two).backward(go)
+
+        def fwd():
+            with torch.no_grad():
+                ff.FunctionCorrelation(one, two)
+
+        for _ in range(2):
+            fb()
+        torch.cuda.synchronize()
+        ts = []
+        for fn in (fwd, fb):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / 5)
+        print(json.dumps({"kernel": "pwc81 fwd / fwd+bwd", "C": c, "H": hh, "W": ww, "fwd_ms": round(ts[0], 4),
+                          "fwd_bwd_ms": round(ts[1], 4)}))
 if "--profile" in sys.argv:
     from torch.profiler import profile, ProfilerActivity
     f1.grad = f2.grad = None
