@@ -7,6 +7,9 @@
 // [h_i, w_i] correlation map is read once, (2r+1)^2 bilinear samples are written.
 // Algorithmic bytes per query (r = 4, L = 4): 4*100*4 read + 324*4 write + 8 = 2904 B.
 //
+// Three kernels: lookup_kernel (row-major pyramid, described below), lookup_tiled_stream_kernel (tiled pyramid,
+// the inference default, described at its definition) and lookup_bwd_kernel (adjoint w.r.t. the pyramid).
+//
 // Work decomposition
 //   unit   = (level, tile of 32 consecutive queries of one batch item), one warp each;
 //   block  = 4 warps = 4 consecutive tiles; blocks are ordered level-major so the

@@ -1,22 +1,27 @@
-// All-pairs correlation volume (level 0 of the pyramid) for sm_100a.
+// All-pairs correlation volume (level 0 of the pyramid) for sm_100a, optionally with the whole avg-pool
+// pyramid fused into the GEMM epilogue, and the two backward GEMMs.
 //
 // Replaces torch.matmul(fmap1^T, fmap2) followed by a separate "/ sqrt(D)" pass
-// (FF_RAFT_Core/corr.py:52-60).  C[b,i,j] = sum_d f1[b,d,i] f2[b,d,j] / sqrt(D).
+// (FF_RAFT_Core/corr.py:52-60) -- and, in the fused build, the three avg_pool2d passes of corr.py:24-27.
+// C[b,i,j] = sum_d f1[b,d,i] f2[b,d,j] / sqrt(D).
 //
 // Tensor-core path (default):
 //   1. operand pre-pass: [B, D, N] fp32 (MN-major, as the encoder hands it over) ->
-//      [B, N, Dp] K-major fp16 / bf16-split / fp32(tf32), zero padded along K.
+//      [B, N, Dp] K-major fp16 / bf16-split / fp32(tf32), zero padded along K; the B operand's rows are
+//      permuted into the storage order of the output (row-major pixels, 4x4 tiles, or 16x16 super-groups).
 //      Traffic: 2*B*N*D*(4 + e) bytes, ~2% of the volume write.
 //   2. persistent warp-specialised GEMM, one CTA per SM, tile 128 x 256:
-//        warp 0    TMA producer   (cp.async.bulk.tensor, 128B swizzle, 3-stage mbarrier ring)
+//        warp 0    TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier ring)
 //        warp 1    MMA issuer     (tcgen05.mma cta_group::1, M=128 N=256, fp32 accumulators in
 //                                  TMEM, 2 x 256 columns so tile t+1 overlaps the epilogue of t)
-//        warps 2-5 epilogue       (tcgen05.ld -> scale by 1/sqrt(D) -> swizzled smem -> TMA store,
-//                                  each warp owns its 32 TMEM lanes and its own 4-deep store ring)
+//        warps 2.. epilogue       (tcgen05.ld -> scale by 1/sqrt(D) [-> pool levels 1..3] -> swizzled smem ->
+//                                  TMA store; each warp owns 32 TMEM lanes and a private store ring)
 //   The kernel is HBM-WRITE bound, not tensor bound: per tile 128 KB of fp32 leave the SM for
 //   2*128*256*D flop (AI ~ 120 flop/B at D=256 < B200 ridge ~215), so the design spends shared
-//   memory on store buffering rather than on a deep operand pipeline.
-// Exact path: FFCORR_PREC_FP32, a CUDA-core SGEMM (also serves the two backward GEMMs).
+//   memory on store buffering rather than on a deep operand pipeline.  See Cfg<> and DESIGN.md 3.1-3.2.
+// Exact path: FFCORR_PREC_FP32, a CUDA-core SGEMM (also the exact backward).
+// Backward: gf1 = g * f2^T, gf2 = g^T * f1 on the same tcgen05 kernel with kind::tf32 reading the fp32 arrays
+// in place (both operands are K-major as they lie; g is transposed in place for the second product).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
