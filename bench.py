@@ -292,7 +292,7 @@ def run_gpu_arm(args, rank, world, local):
     device = torch.device("cuda", local)
     _lib.lib()  # fail loudly if the extension is missing
     # reference run settings: ALLOW_TF32 true, cudnn benchmark (common.py:20-27)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
 
@@ -414,6 +414,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cudnn-benchmark", dest="no_cudnn_benchmark", action="store_true", default=False,
+                    help="heuristic cuDNN algorithm choice instead of timing-based autotuning (profiler runs: the "
+                         "autotuner mis-times kernels under ncu and picks different engines)")
     ap.add_argument("--channels-last", dest="channels_last", action="store_true", default=False)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--update-nchw", dest="update_cl", action="store_false", default=True,

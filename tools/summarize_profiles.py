@@ -25,7 +25,7 @@ for r in rows[1:]:
 tot = sum(sum(v) for v in acc.values())
 mine = {k: v for k, v in acc.items() if "ffcorr" in k or any(s in k for s in ("lookup_kernel", "volume_gemm", "pyramid_", "operand_prepass", "pwc81"))}
 with open(os.path.join(out, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none" + (" -k <this repo's kernels only>" if only_ffcorr else "") + " python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none" + (" -k <this repo's kernels only>" if only_ffcorr else "") + " python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-cudnn-benchmark\n")
     f.write(f"# {n_launch} launches (warm-up step + timed step, + e2e steps), total {tot/1e3:.2f} ms of kernel time (cold-cache, serialised)\n")
     f.write(f"# share of this repo's kernels: {100*sum(sum(v) for v in mine.values())/tot:.2f}%\n")
     f.write(f"{'kernel':72s} {'n':>6s} {'mean_us':>10s} {'total_ms':>10s} {'share%':>8s}\n")
