@@ -405,7 +405,144 @@ pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_consta
     }
 }
 
-// Gradients (correlation.py:104-232).  One thread per input element, 81 taps each.
+// ------------------------------------------------------------------------------------------
+// Gradients (correlation.py:104-232, 331-380) on the forward's machinery.  Both have the form
+//   R[c, p] = (1/C) sum_k G_k[p] * T[c, p + s * d_k],      k = (dy, dx), d_k = (dy, dx):
+//   grad_one:  T = two, s = +1, G_k[p] = g[k, p]
+//   grad_two:  T = one, s = -1, G_k[p] = g[k, p - d_k]      (the gradient plane shifted by its displacement)
+// A block owns an 8x32-pixel tile of one batch item and 32 channels: the 32 T planes (+4-pixel halo) are loaded
+// once by TMA (4 boxes of 8 channels, zero fill = zero padding), the gradient planes stream through a 2-slot
+// ring, 9 planes (one dy) per slot.  For grad_two every plane is fetched with its own row shift; the column shift
+// cannot be put into the TMA coordinate (an inner coordinate that is not a multiple of 16 bytes faults), so the
+// planes carry a 4-pixel halo and the shift is applied when the registers are filled.  Warp w owns channels 4w..4w+3, lane = 8-pixel strip (as in the forward): per dy a
+// thread reads 4 x 16 floats of T and 9 x 8 floats of G (34 LDS.128) for 288 FMAs into 32 accumulators.
+// ------------------------------------------------------------------------------------------
+constexpr int BW_CH = 32;                         // channels per block
+constexpr int BW_CT = 4;                          // channels per thread
+constexpr int BW_THREADS = (BW_CH / BW_CT) * 32;  // 256
+constexpr int BW_T_BYTES = BW_CH * S2 * 4;        // 90112
+constexpr int BW_G_PITCH = PITCH2;                // 44: tile + 4-pixel halo left and right, conflict-free LDS.128
+constexpr int BW_G_PLANE = PT_Y * BW_G_PITCH;     // 352 floats
+constexpr int BW_G_BYTES = 9 * BW_G_PLANE * 4;    // 12672 per dy
+constexpr size_t PWC_BWD_SMEM = (size_t)BW_T_BYTES + 2 * BW_G_BYTES + 64;
+static_assert(BW_T_BYTES % 128 == 0 && BW_G_BYTES % 128 == 0 && (BW_G_PLANE * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+
+template <bool NEG, bool POW2>
+__global__ void __launch_bounds__(BW_THREADS, 2)
+pwc81_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_g,
+                     float* __restrict__ out, int C, int H, int W, int cstages, float inv_c) {
+    extern __shared__ __align__(1024) uint8_t base[];
+    const uint32_t base_u32 = (uint32_t)__cvta_generic_to_shared(base);
+    if (base_u32 & 127u) __trap();
+    const uint32_t g_u32 = base_u32 + BW_T_BYTES;
+    const uint32_t bar_t = g_u32 + 2 * BW_G_BYTES;
+    const uint32_t bar_g = bar_t + 8;             // two barriers
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * PT_Y;
+    const int x0 = (blockIdx.x / cstages) * PT_X;
+    const int cbase = (blockIdx.x % cstages) * BW_CH;
+    const int tid = threadIdx.x;
+    const int cg = tid >> 5;                      // warp = channel group
+    const int lane = tid & 31;
+    const int row = lane >> 2;
+    const int c8 = (lane & 3) * 8;
+
+    auto issue_g = [&](int dyi) {                 // thread 0 only: the 9 gradient planes of displacement row dyi
+        const uint32_t bar = bar_g + 8u * (dyi & 1);
+        const uint32_t dst = g_u32 + (uint32_t)((dyi & 1) * BW_G_BYTES);
+        pw_mbar_expect_tx(bar, BW_G_BYTES);
+#pragma unroll 1
+        for (int dxi = 0; dxi < 9; ++dxi) {
+            const int gy = NEG ? y0 - (dyi - 4) : y0;
+            pw_tma_load_4d(dst + (uint32_t)(dxi * BW_G_PLANE * 4), &tm_g, bar, x0 - PHALO, gy, dyi * 9 + dxi, b);
+        }
+    };
+
+    if (tid == 0) {
+        pw_mbar_init(bar_t, 1);
+        pw_mbar_init(bar_g, 1);
+        pw_mbar_init(bar_g + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pw_mbar_expect_tx(bar_t, BW_T_BYTES);
+#pragma unroll 1
+        for (int i = 0; i < BW_CH / PCC; ++i)
+            pw_tma_load_4d(base_u32 + (uint32_t)(i * PCC * S2 * 4), &tm_t, bar_t, x0 - PHALO, y0 - PHALO, cbase + i * PCC, b);
+        issue_g(0);
+        issue_g(1);
+    }
+
+    float acc[BW_CT][8];
+#pragma unroll
+    for (int j = 0; j < BW_CT; ++j)
+#pragma unroll
+        for (int px = 0; px < 8; ++px) acc[j][px] = 0.0f;
+
+    pw_mbar_wait(bar_t, 0);
+    const float* Ts = reinterpret_cast<const float*>(base) + (size_t)(cg * BW_CT) * S2 + c8;
+#pragma unroll 1
+    for (int dyi = 0; dyi < 9; ++dyi) {
+        pw_mbar_wait(bar_g + 8u * (dyi & 1), (uint32_t)((dyi >> 1) & 1));
+        const float* Gs = reinterpret_cast<const float*>(base + BW_T_BYTES + (dyi & 1) * BW_G_BYTES) + row * BW_G_PITCH + c8;
+        const int trow = row + (NEG ? 8 - dyi : dyi);
+        float t[BW_CT][16];
+#pragma unroll
+        for (int j = 0; j < BW_CT; ++j) {
+            const float* tp = Ts + j * S2 + trow * PITCH2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(tp + 4 * q);
+                t[j][4 * q] = v.x; t[j][4 * q + 1] = v.y; t[j][4 * q + 2] = v.z; t[j][4 * q + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int dxi = 0; dxi < 9; ++dxi) {
+            // plane column of pixel px: c8 + px + 4 (halo) - dx for grad_two, c8 + px + 4 for grad_one
+            const int gs = NEG ? 8 - dxi : PHALO;                 // compile-time after unrolling
+            const float* gp = Gs + dxi * BW_G_PLANE + (gs & ~3);
+            const float4 w0 = *reinterpret_cast<const float4*>(gp);
+            const float4 w1 = *reinterpret_cast<const float4*>(gp + 4);
+            float4 w2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gs & 3) w2 = *reinterpret_cast<const float4*>(gp + 8);
+            const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+            float g8[8];
+#pragma unroll
+            for (int px = 0; px < 8; ++px) g8[px] = wv[(gs & 3) + px];
+            const int sh = NEG ? 8 - dxi : dxi;
+#pragma unroll
+            for (int j = 0; j < BW_CT; ++j)
+#pragma unroll
+                for (int px = 0; px < 8; ++px) acc[j][px] = fmaf(g8[px], t[j][px + sh], acc[j][px]);
+        }
+        __syncthreads();                           // everyone is done with this gradient slot
+        if (tid == 0 && dyi + 2 < 9) issue_g(dyi + 2);
+    }
+
+    const int gy = y0 + row, gx = x0 + c8;
+    if (gy >= H || gx >= W) return;
+    const float fc = (float)C;
+#pragma unroll
+    for (int j = 0; j < BW_CT; ++j) {
+        const int c = cbase + cg * BW_CT + j;
+        if (c >= C) break;
+        float r[8];
+#pragma unroll
+        for (int px = 0; px < 8; ++px) r[px] = POW2 ? acc[j][px] * inv_c : __fdiv_rn(acc[j][px], fc);
+        float* od = out + (((size_t)b * C + c) * H + gy) * W + gx;
+        if (gx + 7 < W) {
+            reinterpret_cast<float4*>(od)[0] = make_float4(r[0], r[1], r[2], r[3]);
+            reinterpret_cast<float4*>(od)[1] = make_float4(r[4], r[5], r[6], r[7]);
+        } else {
+#pragma unroll
+            for (int px = 0; px < 8; ++px)
+                if (gx + px < W) od[px] = r[px];
+        }
+    }
+}
+
+// Fallback gradients (W % 4 != 0 or unaligned bases).  One thread per input element, 81 taps each.
 //   gone[b,c,y,x] = (1/C) sum_{p,o} g[b,(p,o),y,x]       * two[b,c,y+p,x+o]
 //   gtwo[b,c,y,x] = (1/C) sum_{p,o} g[b,(p,o),y-p,x-o]   * one[b,c,y-p,x-o]
 __global__ void __launch_bounds__(256) pwc81_bwd_kernel(const float* __restrict__ one, const float* __restrict__ two,
@@ -516,6 +653,45 @@ extern "C" int ffcorr_pwc81_bwd_f32(const float* one, const float* two, const fl
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(one && two && grad_out, FFCORR_EINVAL, "pwc81_bwd: null pointer");
     if (B == 0 || (!grad_one && !grad_two)) return FFCORR_OK;
+    const int tiles_x = ceil_div(W, PT_X), tiles_y = ceil_div(H, PT_Y);
+    const int cstages = ceil_div(C, BW_CH);
+    const bool aligned = (W % 4 == 0) && ((uintptr_t)one % 16 == 0) && ((uintptr_t)two % 16 == 0) &&
+                         ((uintptr_t)grad_out % 16 == 0) && (!grad_one || (uintptr_t)grad_one % 16 == 0) &&
+                         (!grad_two || (uintptr_t)grad_two % 16 == 0);
+    if (aligned && tiles_y < 65536 && B < 65536 && (int64_t)tiles_x * cstages < (1ll << 31)) {
+        CUtensorMap tm_one, tm_two, tm_g;
+        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)C * H * W * 4};
+        const uint64_t gdims[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
+        const uint64_t gstrides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)81 * H * W * 4};
+        const uint32_t box_t[4] = {PITCH2, PH2, PCC, 1};
+        const uint32_t box_g[4] = {BW_G_PITCH, PT_Y, 1, 1};
+        if (int rc = encode_tensor_map(&tm_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, grad_out, gdims, gstrides, box_g,
+                                       CU_TENSOR_MAP_SWIZZLE_NONE, "pwc grad_out")) return rc;
+        const bool pow2 = (C & (C - 1)) == 0;
+        const float inv_c = 1.0f / (float)C;
+        const dim3 grid((unsigned)(tiles_x * cstages), (unsigned)tiles_y, (unsigned)B);
+        cudaStream_t s = (cudaStream_t)stream;
+#define FF_PWC_BWD(NEG, P2, TM, OUT)                                                                                       \
+    do {                                                                                                                   \
+        FFCORR_CUDA(cudaFuncSetAttribute(pwc81_bwd_tma_kernel<NEG, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int)PWC_BWD_SMEM));                                                              \
+        pwc81_bwd_tma_kernel<NEG, P2><<<grid, BW_THREADS, PWC_BWD_SMEM, s>>>(TM, tm_g, OUT, C, H, W, cstages, inv_c);      \
+        if (int rc = check_launch("pwc81_bwd_tma_kernel")) return rc;                                                      \
+    } while (0)
+        if (grad_one) {
+            if (int rc = encode_tensor_map(&tm_two, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, two, dims, strides, box_t,
+                                           CU_TENSOR_MAP_SWIZZLE_NONE, "pwc two")) return rc;
+            if (pow2) FF_PWC_BWD(false, true, tm_two, grad_one); else FF_PWC_BWD(false, false, tm_two, grad_one);
+        }
+        if (grad_two) {
+            if (int rc = encode_tensor_map(&tm_one, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, one, dims, strides, box_t,
+                                           CU_TENSOR_MAP_SWIZZLE_NONE, "pwc one")) return rc;
+            if (pow2) FF_PWC_BWD(true, true, tm_one, grad_two); else FF_PWC_BWD(true, false, tm_one, grad_two);
+        }
+#undef FF_PWC_BWD
+        return FFCORR_OK;
+    }
     const int64_t total = (int64_t)B * C * H * W;
     const int64_t want = ceil_div64(total, 256);
     const int64_t cap = (int64_t)sm_count() * 16;

@@ -464,13 +464,17 @@ def test_pwc_full_size_level2_properties():
     assert float((lhs - rhs).abs().max()) <= 1e-5
 
 
-def test_pwc_backward_vs_oracle():
+@pytest.mark.parametrize("shape", [(2, 20, 11, 14),      # W % 4 != 0: per-element fallback kernel
+                                   (2, 20, 11, 16),      # TMA kernel, one partial channel stage, image < tile
+                                   (1, 70, 19, 40),      # three channel stages (32+32+6), several tiles, ragged rows
+                                   (2, 32, 8, 32),       # exactly one tile, power-of-two C (reciprocal multiply)
+                                   (1, 196, 7, 16)])     # config-3 level 6
+def test_pwc_backward_vs_oracle(shape):
     m = ff()
     rng = np.random.default_rng(4)
-    shape = (2, 20, 11, 14)
     one = rng.standard_normal(shape).astype(np.float32)
     two = rng.standard_normal(shape).astype(np.float32)
-    g = rng.standard_normal((2, 81, 11, 14)).astype(np.float32)
+    g = rng.standard_normal((shape[0], 81, shape[2], shape[3])).astype(np.float32)
     a = t(one).requires_grad_(True)
     bb = t(two).requires_grad_(True)
     m.ModuleCorrelation()(a, bb).backward(t(g))
