@@ -39,6 +39,9 @@ _PROTOS = {
     "ffcorr_volume_tiled_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_pyramid_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_build_tiled_f32": (_i, [_vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "ffcorr_stage_operands_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "ffcorr_build_tiled_chunk_f32": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "ffcorr_lookup_tiled_chunk_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_lookup_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ffcorr_untile_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_tile_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),

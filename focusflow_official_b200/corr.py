@@ -360,3 +360,61 @@ class CorrBlock:
     @staticmethod
     def corr(fmap1, fmap2, precision: Optional[str] = None):
         return correlation_volume(fmap1, fmap2, precision)
+
+
+class AlternateCorrBlock:
+    """Memory-bounded drop-in for the reference's ``AlternateCorrBlock`` (``corr.py:63-91``): same constructor, same
+    ``__call__(coords)``, same values as :class:`CorrBlock` (bit-identical), but the pyramid is never stored -- every
+    lookup recomputes it for ``chunk`` queries at a time with the fused tensor-core build and throws it away, so
+    memory is O(chunk * h*w) instead of O((h*w)^2).  Inference only (the reference's version has no backward
+    either: ``alt_cuda_corr`` is forward-only in every shipped config)."""
+
+    def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4, precision: Optional[str] = None,
+                 chunk: Optional[int] = None, max_pyramid_bytes: int = 512 << 20):
+        self.num_levels = num_levels
+        self.radius = radius
+        f1, f2 = _prep(fmap1, "fmap1").detach(), _prep(fmap2, "fmap2").detach()
+        if f1.shape != f2.shape:
+            raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
+        b, d, h, w = f1.shape
+        self._shape = (b, d, h, w)
+        self._code = _precision_code(precision)
+        if self._code == _lib.PREC_FP32 or not tiled_supported(h, w, num_levels):
+            raise ValueError("AlternateCorrBlock needs a tensor-core precision (fp16 / tf32 / bf16x3) and a shape the "
+                             "tiled kernels support")
+        n = h * w
+        per_query = 4 * sum(_tiled_elems(h, w, i) for i in range(num_levels))
+        if chunk is None:   # as many queries as fit the budget, in whole GEMM row tiles
+            chunk = max(128, (max_pyramid_bytes // max(1, b * per_query)) // 128 * 128)
+        # whole 32-query lookup units: the lookup picks its separable / exact-per-tap path per unit, so only then is
+        # every query evaluated exactly like in CorrBlock (the two paths differ by ~1e-7 relative)
+        self.chunk = int(min(max(32, chunk // 32 * 32), (n + 31) // 32 * 32))
+        L = _lib.lib()
+        self._ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, self._code)
+        self._ws = torch.empty(max(self._ws_bytes, 1), device=f1.device, dtype=torch.uint8)
+        _lib.check(L.ffcorr_stage_operands_f32(f1.data_ptr(), f2.data_ptr(), num_levels, b, d, h, w, self._code,
+                                               self._ws.data_ptr(), self._ws_bytes, _lib.current_stream()),
+                   "ffcorr_stage_operands_f32")
+        self._levels = [torch.empty((b * self.chunk, _tiled_elems(h, w, i)), device=f1.device, dtype=torch.float32)
+                        for i in range(num_levels)]
+        self._ptrs = _lib.ptr_array(self._levels)
+
+    def __call__(self, coords: torch.Tensor) -> torch.Tensor:
+        b, d, h, w = self._shape
+        _require_cuda(coords, "coords")
+        if tuple(coords.shape) != (b, 2, h, w):
+            raise ValueError(f"coords {tuple(coords.shape)} does not match B,h,w={(b, h, w)}")
+        coords = coords.detach().float().contiguous()
+        k = 2 * self.radius + 1
+        out = torch.empty((b, self.num_levels * k * k, h, w), device=coords.device, dtype=torch.float32)
+        L = _lib.lib()
+        stream = _lib.current_stream()
+        n = h * w
+        for q0 in range(0, n, self.chunk):
+            nq = min(self.chunk, n - q0)            # q0 stays a multiple of 32
+            _lib.check(L.ffcorr_build_tiled_chunk_f32(self._ptrs, self.num_levels, b, d, h, w, q0, nq, self._code,
+                                                      self._ws.data_ptr(), self._ws_bytes, stream),
+                       "ffcorr_build_tiled_chunk_f32")
+            _lib.check(L.ffcorr_lookup_tiled_chunk_f32(self._ptrs, self.num_levels, coords.data_ptr(), out.data_ptr(),
+                                                       b, h, w, q0, nq, self.radius, stream), "ffcorr_lookup_tiled_chunk_f32")
+        return out

@@ -247,6 +247,8 @@ struct LookupTiledParams {
     int B, N, num_levels;
     int tiles_per_batch;
     int blocks_per_batch;
+    int64_t coords_stride;   // floats between the x and y planes of coords (N, or the full map size for a query chunk)
+    int64_t out_stride;      // floats between output channels (N, or the full map size for a query chunk)
 };
 
 // ---------------------------------------------------------------------------------
@@ -311,9 +313,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     const float inv_scale = __int_as_float((127 - level) << 23);
 
     // ---------------- phase A (lane = query) ----------------
-    const float* cptr = p.coords + (size_t)b * 2 * N + n;
+    const float* cptr = p.coords + (size_t)b * 2 * p.coords_stride + n;
     const float cx = __ldg(cptr) * inv_scale;
-    const float cy = __ldg(cptr + N) * inv_scale;
+    const float cy = __ldg(cptr + p.coords_stride) * inv_scale;
     const float sx = (float)(lw - 1), sy = (float)(lh - 1);
     const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
     const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
@@ -422,8 +424,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     };
 
     const int CT = p.num_levels * K * K;
-    float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
-    const int64_t stride_a = (int64_t)K * N;
+    const int64_t ostride = p.out_stride;
+    float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * ostride + n;
+    const int64_t stride_a = (int64_t)K * ostride;
     const int my_row = slot_of(lane) * kRowPitch + (x_lo & 3);
 
 #pragma unroll
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
                     *o_ptr = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
                     o_ptr += stride_a;
                 }
-                o_row += N;
+                o_row += ostride;
             }
 #pragma unroll
             for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
                         o = __fmaf_rn(v01, ne, o);
                         o = __fmaf_rn(v10, sw, o);
                         o = __fmaf_rn(v11, se, o);
-                        op[(int64_t)(a * K + bb) * N] = o;
+                        op[(int64_t)(a * K + bb) * ostride] = o;
                     }
                 }
             }
@@ -782,17 +785,18 @@ extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, con
 }
 
 
-extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
-                                       int B, int h, int w, int radius, void* stream) {
-    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup_tiled: B=%d", B);
+static int lookup_tiled_impl(const float* const* lvl, int num_levels, const float* coords, float* out, int B, int h, int w,
+                             int nq, int64_t coords_stride, int64_t out_stride, int radius, void* stream, const char* who) {
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "%s: B=%d", who, B);
     if (B == 0) return FFCORR_OK;
-    FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "lookup_tiled: null pointer");
-    FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup_tiled: radius=%d outside [1,4]", radius);
-    if (int rc = check_levels(num_levels, h, w, "lookup_tiled")) return rc;
+    FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "%s: null pointer", who);
+    FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "%s: radius=%d outside [1,4]", who, radius);
+    if (int rc = check_levels(num_levels, h, w, who)) return rc;
+    FFCORR_REQUIRE(nq >= 1 && nq <= h * w, FFCORR_EINVAL, "%s: %d queries for a %dx%d map", who, nq, h, w);
     LookupTiledParams p{};
     for (int i = 0; i < num_levels; ++i) {
-        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "lookup_tiled: lvl[%d] is null", i);
-        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "lookup_tiled: lvl[%d] must be 16-byte aligned", i);
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "%s: lvl[%d] is null", who, i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "%s: lvl[%d] must be 16-byte aligned", who, i);
         p.lvl[i] = lvl[i];
         p.lh[i] = h >> i;
         p.lw[i] = w >> i;
@@ -802,7 +806,9 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
     p.coords = coords;
     p.out = out;
     p.B = B;
-    p.N = h * w;
+    p.N = nq;
+    p.coords_stride = coords_stride;
+    p.out_stride = out_stride;
     p.num_levels = num_levels;
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
@@ -813,4 +819,21 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
         case 3: return launch_lookup_tiled_stream<3>(p, s);
         default: return launch_lookup_tiled_stream<4>(p, s);
     }
+}
+
+extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                                       int B, int h, int w, int radius, void* stream) {
+    return lookup_tiled_impl(lvl, num_levels, coords, out, B, h, w, h * w, (int64_t)h * w, (int64_t)h * w, radius, stream,
+                             "lookup_tiled");
+}
+
+extern "C" int ffcorr_lookup_tiled_chunk_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                                             int B, int h, int w, int q0, int nq, int radius, void* stream) {
+    FFCORR_REQUIRE(q0 >= 0 && nq >= 1 && (int64_t)q0 + nq <= (int64_t)h * w, FFCORR_EINVAL,
+                   "lookup_tiled_chunk: query range [%d, %d) outside the %dx%d map", q0, q0 + nq, h, w);
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(coords && out, FFCORR_EINVAL, "lookup_tiled_chunk: null pointer");
+    // coords / out are the FULL [B, 2, h*w] / [B, L*K*K, h*w] tensors; the chunk reads and writes its slice in place
+    return lookup_tiled_impl(lvl, num_levels, coords + q0, out + q0, B, h, w, nq, (int64_t)h * w, (int64_t)h * w, radius, stream,
+                             "lookup_tiled_chunk");
 }

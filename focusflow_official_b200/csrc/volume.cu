@@ -202,6 +202,7 @@ struct GemmParams {
     float divisor;  // sqrt(D)
     int use_div;    // 1: fp32 divide like the reference; 0: multiply by the exact reciprocal
     float* out;     // only used by the non-TMA epilogue (N % 4 != 0, backward GEMMs)
+    int row_offset;       // first A row (query) of this launch: the chunked build computes rows [row_offset, row_offset + N)
     int out_transposed;   // non-TMA epilogue: write C^T, i.e. out[b][col][row] with row pitch ldc (backward GEMMs)
     int64_t ldc;
 };
@@ -293,7 +294,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_arrive_expect_tx(full_bar(stage), SMEM_A_STAGE + SMEM_B_STAGE);
                     const int k0 = kb * (TF32 ? BK_BYTES / 4 : BK_BYTES / 2);
-                    tma_load_3d(smem_base + C::OFF_A + stage * SMEM_A_STAGE, &tmap_a, full_bar(stage), k0, m0, b);
+                    tma_load_3d(smem_base + C::OFF_A + stage * SMEM_A_STAGE, &tmap_a, full_bar(stage), k0, m0 + p.row_offset, b);
                     tma_load_3d(smem_base + C::OFF_B + stage * SMEM_B_STAGE, &tmap_b, full_bar(stage), k0, n0, b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -831,18 +832,23 @@ extern "C" size_t ffcorr_volume_workspace_bytes(int B, int D, int h, int w, int 
 }
 
 enum : int { OUT_ROWMAJOR = 0, OUT_TILED = 1, OUT_FUSED_PYRAMID = 2 };
+enum : int { PHASE_ALL = 0, PHASE_STAGE = 1, PHASE_GEMM = 2 };
 
 static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w, int precision,
                        void* workspace, size_t workspace_bytes, void* stream, int out_mode, float* const* lvl = nullptr,
-                       int num_levels = 1) {
+                       int num_levels = 1, int q0 = 0, int nq = -1, int phase = PHASE_ALL) {
+    // q0 / nq: only the queries [q0, q0 + nq) are computed (chunked build); phase: stage the operands, run the
+    // GEMM on already staged operands, or both.
     const bool tiled = out_mode != OUT_ROWMAJOR;
     const bool fused = out_mode == OUT_FUSED_PYRAMID;
     FFCORR_REQUIRE(B >= 0 && D >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "volume: bad shape B=%d D=%d h=%d w=%d", B, D, h, w);
     FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "volume: h*w=%lld too large", (long long)h * w);
     if (B == 0) return FFCORR_OK;  // empty batch: pointers may legitimately be null
-    FFCORR_REQUIRE(fmap1 && fmap2 && lvl0, FFCORR_EINVAL, "volume: null pointer");
+    FFCORR_REQUIRE((phase == PHASE_GEMM || (fmap1 && fmap2)) && (phase == PHASE_STAGE || lvl0), FFCORR_EINVAL, "volume: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const int N = h * w;
+    const int Nq = nq < 0 ? N : nq;               // queries computed by this call
+    FFCORR_REQUIRE(q0 >= 0 && Nq >= 1 && q0 + Nq <= N, FFCORR_EINVAL, "volume: query range [%d, %d) outside [0, %d)", q0, q0 + Nq, N);
     const float sqrt_d = sqrtf((float)D);
 
     FFCORR_REQUIRE(!(tiled && precision == FFCORR_PREC_FP32), FFCORR_EINVAL,
@@ -859,7 +865,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     FFCORR_REQUIRE(workspace != nullptr && workspace_bytes >= need, FFCORR_EWORKSPACE,
                    "volume: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
     FFCORR_REQUIRE((uintptr_t)workspace % 256 == 0, FFCORR_EALIGN, "volume: workspace must be 256-byte aligned");
-    FFCORR_REQUIRE((uintptr_t)lvl0 % 16 == 0, FFCORR_EALIGN, "volume: lvl0 must be 16-byte aligned");
+    FFCORR_REQUIRE(phase == PHASE_STAGE || (uintptr_t)lvl0 % 16 == 0, FFCORR_EALIGN, "volume: lvl0 must be 16-byte aligned");
 
     const int Dp = (int)align_up((size_t)D, pi.k_align);
     const int Kt = Dp * pi.k_mult;  // total K in elements
@@ -875,7 +881,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     tlb.tw = fused ? ceil_div(w, 16) : tiled_tw(w);
     tlb.np = fused ? ceil_div(h, 16) * tlb.tw * 256 : tiled_th(h) * tlb.tw * 16;
     const int Ncols = tiled ? tlb.np : N;       // columns of the volume == rows of the staged B operand
-    {
+    if (phase != PHASE_GEMM) {
         dim3 grid(ceil_div(Ncols, PP_N), Dp / PP_D, 2 * B);
         FFCORR_REQUIRE(grid.y < 65536 && grid.z < 65536, FFCORR_EINVAL, "volume: pre-pass grid too large");
         if (precision == FFCORR_PREC_FP16)
@@ -886,6 +892,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
             operand_prepass_kernel<CVT_BF16X3_A><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         if (int rc = check_launch("operand_prepass_kernel")) return rc;
     }
+    if (phase == PHASE_STAGE) return FFCORR_OK;
 
     // ---- 2. tensor maps ----
     CUtensorMap ta, tb, tc, tl1;
@@ -906,17 +913,17 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
         const int th1 = tiled_th(lh1), tw1 = tiled_tw(lw1);
         const uint32_t box[4] = {32, 1, 32, 1};
         {
-            const uint64_t dims[4] = {(uint64_t)tw0 * 16, (uint64_t)th0, (uint64_t)N, (uint64_t)B};
+            const uint64_t dims[4] = {(uint64_t)tw0 * 16, (uint64_t)th0, (uint64_t)Nq, (uint64_t)B};
             const uint64_t map_b = (uint64_t)th0 * tw0 * 64;
-            const uint64_t strides[3] = {(uint64_t)tw0 * 64, map_b, map_b * N};
+            const uint64_t strides[3] = {(uint64_t)tw0 * 64, map_b, map_b * Nq};
             if (int rc = encode_tensor_map(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl[0], dims, strides, box,
                                            CU_TENSOR_MAP_SWIZZLE_128B, "L0"))
                 return rc;
         }
         {
-            const uint64_t dims[4] = {(uint64_t)tw1 * 16, (uint64_t)th1, (uint64_t)N, (uint64_t)B};
+            const uint64_t dims[4] = {(uint64_t)tw1 * 16, (uint64_t)th1, (uint64_t)Nq, (uint64_t)B};
             const uint64_t map_b = (uint64_t)th1 * tw1 * 64;
-            const uint64_t strides[3] = {(uint64_t)tw1 * 64, map_b, map_b * N};
+            const uint64_t strides[3] = {(uint64_t)tw1 * 64, map_b, map_b * Nq};
             if (int rc = encode_tensor_map(&tl1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl[1], dims, strides, box,
                                            CU_TENSOR_MAP_SWIZZLE_128B, "L1"))
                 return rc;
@@ -935,8 +942,8 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
         fp.l2 = num_levels >= 3 ? lvl[2] : nullptr;
         fp.l3 = num_levels >= 4 ? lvl[3] : nullptr;
     } else if (tma_store) {
-        if (int rc = encode_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, Ncols, N, B, (uint64_t)Ncols * 4,
-                               (uint64_t)N * Ncols * 4, STORE_COLS, 32, "C"))
+        if (int rc = encode_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, Ncols, Nq, B, (uint64_t)Ncols * 4,
+                               (uint64_t)Nq * Ncols * 4, STORE_COLS, 32, "C"))
             return rc;
     } else {
         tc = ta;  // unused by the kernel
@@ -944,11 +951,12 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
 
     // ---- 3. GEMM ----
     GemmParams p{};
-    p.N = N;
+    p.N = Nq;
+    p.row_offset = q0;
     p.Ncols = Ncols;
     p.B = B;
     p.num_kb = Kt * pi.elem_bytes / BK_BYTES;
-    p.tiles_m = ceil_div(N, BM);
+    p.tiles_m = ceil_div(Nq, BM);
     p.tiles_n = ceil_div(Ncols, BN);
     p.divisor = sqrt_d;
     int e = 0;
@@ -1056,6 +1064,30 @@ extern "C" int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, fl
         return volume_impl(fmap1, fmap2, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_TILED);
     return volume_impl(fmap1, fmap2, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_FUSED_PYRAMID,
                        lvl, num_levels);
+}
+
+extern "C" int ffcorr_stage_operands_f32(const float* fmap1, const float* fmap2, int num_levels, int B, int D, int h, int w,
+                                         int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_levels(num_levels, h, w, "stage_operands")) return rc;
+    FFCORR_REQUIRE(ffcorr_tiled_supported(num_levels, h, w), FFCORR_EINVAL, "stage_operands: shape outside the tiled path");
+    float dummy = 0.f;   // PHASE_STAGE never touches the output
+    return volume_impl(fmap1, fmap2, &dummy, B, D, h, w, precision, workspace, workspace_bytes, stream,
+                       num_levels == 1 ? OUT_TILED : OUT_FUSED_PYRAMID, nullptr, num_levels, 0, -1, PHASE_STAGE);
+}
+
+extern "C" int ffcorr_build_tiled_chunk_f32(float* const* lvl, int num_levels, int B, int D, int h, int w, int q0, int nq,
+                                            int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    FFCORR_REQUIRE(lvl != nullptr, FFCORR_EINVAL, "build_tiled_chunk: null level table");
+    if (int rc = check_levels(num_levels, h, w, "build_tiled_chunk")) return rc;
+    FFCORR_REQUIRE(ffcorr_tiled_supported(num_levels, h, w), FFCORR_EINVAL, "build_tiled_chunk: shape outside the tiled path");
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "build_tiled_chunk: B=%d", B);
+    if (B == 0) return FFCORR_OK;
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "build_tiled_chunk: lvl[%d] is null", i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "build_tiled_chunk: lvl[%d] must be 16-byte aligned", i);
+    }
+    return volume_impl(nullptr, nullptr, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream,
+                       num_levels == 1 ? OUT_TILED : OUT_FUSED_PYRAMID, lvl, num_levels, q0, nq, PHASE_GEMM);
 }
 
 extern "C" int ffcorr_volume_bwd_f32(float* grad_lvl0, const float* fmap1, const float* fmap2, float* gfmap1,

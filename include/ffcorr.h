@@ -10,6 +10,7 @@
  *                          (torch.matmul + separate "/ sqrt(D)" kernel)
  *   ffcorr_pyramid_f32     corr.py:24-27   3x F.avg_pool2d(corr, 2, stride=2)
  *   ffcorr_build_tiled_f32 corr.py:13-27   CorrBlock.__init__ = volume + pyramid, fused (tiled layout)
+ *   ffcorr_*_chunk_f32     corr.py:63-91   AlternateCorrBlock: memory-bounded, recomputed per lookup
  *   ffcorr_lookup_f32      corr.py:29-50   CorrBlock.__call__  +  utils/utils.py:57-71
  *                          bilinear_sampler (4x F.grid_sample + ~60 glue kernels)
  *   ffcorr_lookup_bwd_f32  autograd of the above w.r.t. the pyramid (coords are detached
@@ -132,6 +133,22 @@ int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, float* const*
                            void* workspace, size_t workspace_bytes, void* stream);
 int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
                             int B, int h, int w, int radius, void* stream);
+
+/*
+ * Query-chunked build + lookup: AlternateCorrBlock semantics (corr.py:63-91) -- the same lookup values with
+ * O(nq * h*w) instead of O((h*w)^2) pyramid memory, recomputed per lookup.  Stage the GEMM operands once per
+ * image pair (ffcorr_stage_operands_f32, same workspace as ffcorr_volume_f32), then per lookup and per chunk of
+ * queries [q0, q0+nq): ffcorr_build_tiled_chunk_f32 writes the tiled pyramid of those queries only
+ * (lvl[i] = [B*nq, ffcorr_tiled_map_elems(h, w, i)]), ffcorr_lookup_tiled_chunk_f32 reads the chunk's slice of the
+ * FULL coords [B, 2, h, w] and writes its slice of the FULL out [B, L*(2r+1)^2, h, w] in place.  Values are
+ * bit-identical to ffcorr_build_tiled_f32 + ffcorr_lookup_tiled_f32.  num_levels must agree between the calls.
+ */
+int ffcorr_stage_operands_f32(const float* fmap1, const float* fmap2, int num_levels, int B, int D, int h, int w,
+                              int precision, void* workspace, size_t workspace_bytes, void* stream);
+int ffcorr_build_tiled_chunk_f32(float* const* lvl, int num_levels, int B, int D, int h, int w, int q0, int nq,
+                                 int precision, void* workspace, size_t workspace_bytes, void* stream);
+int ffcorr_lookup_tiled_chunk_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                                  int B, int h, int w, int q0, int nq, int radius, void* stream);
 int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int h_level, int w_level, void* stream);
 int ffcorr_tile_f32(const float* src, float* tiled, int64_t Q, int h_level, int w_level, void* stream);
 

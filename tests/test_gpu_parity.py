@@ -255,6 +255,29 @@ def test_full_size_config2_properties():
     assert max_rel(got_r, ref_r) <= 1e-5
 
 
+# ---------------------------------------------------------------- AlternateCorrBlock
+@pytest.mark.parametrize("shape,nl,radius,chunk", [((2, 64, 24, 40), 4, 4, 128), ((1, 32, 17, 21), 4, 4, 100), ((2, 48, 16, 16), 3, 3, 37),
+                                                   ((1, 256, 46, 62), 4, 4, None), ((1, 16, 9, 13), 1, 2, 50), ((1, 32, 33, 47), 4, 4, 1551)])
+def test_alternate_corrblock_equals_corrblock_bitwise(shape, nl, radius, chunk):
+    """Memory-bounded, recomputed-per-lookup block (chunks of queries) == the stored-pyramid block, bit for bit,
+    for chunk sizes that are / are not multiples of the GEMM row tile (the class rounds to whole 32-query lookup units)."""
+    m = ff()
+    torch.manual_seed(12)
+    b, d, h, w = shape
+    f1 = torch.randn(shape, device=DEV) * 4.4
+    f2 = torch.randn(shape, device=DEV) * 4.4
+    ref = m.CorrBlock(f1, f2, num_levels=nl, radius=radius)
+    alt = m.AlternateCorrBlock(f1, f2, num_levels=nl, radius=radius, chunk=chunk)
+    assert alt.chunk % 32 == 0
+    for sigma in (0.0, 2.5, 30.0):
+        coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * sigma
+        a, r = alt(coords), ref(coords)
+        assert a.shape == r.shape and torch.isfinite(a).all()
+        assert torch.equal(a, r), (sigma, (a != r).sum().item())
+    with pytest.raises(ValueError):
+        m.AlternateCorrBlock(f1, f2, num_levels=nl, precision="fp32")
+
+
 # ---------------------------------------------------------------- gradients (SURVEY 8f N1)
 def test_corrblock_gradients_match_torch_autograd():
     m = ff()

@@ -135,6 +135,16 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         todo += [("volume_tiled", k_volume_t, vol_bytes, vol_flops), ("pyramid_tiled", k_pyramid_t, pyr_bytes, 0.0),
                  ("build_fused", k_build_t, vol_bytes + pyr_bytes - 4.0 * b * n * lv_elems[0], vol_flops),
                  ("lookup_tiled", k_lookup_t, look_bytes, 0.0)]
+    if tiled_ok and (not only or "alt_lookup" in only):
+        # memory-bounded AlternateCorrBlock: the pyramid of a 512 MiB query chunk is rebuilt for every lookup
+        alt = ff.AlternateCorrBlock(f1, f2, num_levels=nl, radius=r, precision=precision)
+        med, best = time_cuda(lambda: alt(coords), iters=iters, warmup=warmup, flush=flush)
+        rec = {"kernel": "alt_lookup", "config": config, "ms": round(med, 4), "ms_min": round(best, 4), "chunk_queries": alt.chunk,
+               "pyramid_buffer_MiB": round(sum(l.numel() for l in alt._levels) * 4 / 2 ** 20, 1), "precision": precision}
+        res.append(rec)
+        if verbose:
+            print(json.dumps(rec), flush=True)
+        del alt
     for name, fn, byts, flops in todo:
         if only and name not in only:
             # run (untimed) only what a selected kernel reads
