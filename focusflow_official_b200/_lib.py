@@ -32,6 +32,7 @@ _PROTOS = {
     "ffcorr_get_l2_fetch_granularity": (_i, [ctypes.POINTER(_i)]),
     "ffcorr_volume_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
     "ffcorr_volume_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "ffcorr_volume_scaled_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_float, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_pyramid_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_lookup_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ffcorr_tiled_map_elems": (ctypes.c_int64, [_i, _i, _i]),

@@ -836,7 +836,7 @@ enum : int { PHASE_ALL = 0, PHASE_STAGE = 1, PHASE_GEMM = 2 };
 
 static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w, int precision,
                        void* workspace, size_t workspace_bytes, void* stream, int out_mode, float* const* lvl = nullptr,
-                       int num_levels = 1, int q0 = 0, int nq = -1, int phase = PHASE_ALL) {
+                       int num_levels = 1, int q0 = 0, int nq = -1, int phase = PHASE_ALL, float divisor = 0.0f) {
     // q0 / nq: only the queries [q0, q0 + nq) are computed (chunked build); phase: stage the operands, run the
     // GEMM on already staged operands, or both.
     const bool tiled = out_mode != OUT_ROWMAJOR;
@@ -849,7 +849,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     const int N = h * w;
     const int Nq = nq < 0 ? N : nq;               // queries computed by this call
     FFCORR_REQUIRE(q0 >= 0 && Nq >= 1 && q0 + Nq <= N, FFCORR_EINVAL, "volume: query range [%d, %d) outside [0, %d)", q0, q0 + Nq, N);
-    const float sqrt_d = sqrtf((float)D);
+    const float sqrt_d = divisor > 0.0f ? divisor : sqrtf((float)D);   // the value every dot product is divided by
 
     FFCORR_REQUIRE(!(tiled && precision == FFCORR_PREC_FP32), FFCORR_EINVAL,
                    "volume: the tiled layout is produced by the tensor-core paths only");
@@ -1041,6 +1041,13 @@ int launch_gemm_nt_tf32(const float* A, const float* Bm, float* Ct, int M, int N
 extern "C" int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
                                  int precision, void* workspace, size_t workspace_bytes, void* stream) {
     return volume_impl(fmap1, fmap2, lvl0, B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_ROWMAJOR);
+}
+
+extern "C" int ffcorr_volume_scaled_f32(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w,
+                                        int precision, float divisor, void* workspace, size_t workspace_bytes, void* stream) {
+    FFCORR_REQUIRE(divisor > 0.0f && divisor < 3.0e38f, FFCORR_EINVAL, "volume_scaled: divisor=%g must be positive and finite", (double)divisor);
+    return volume_impl(fmap1, fmap2, lvl0, B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_ROWMAJOR, nullptr, 1,
+                       0, -1, PHASE_ALL, divisor);
 }
 
 extern "C" int ffcorr_volume_tiled_f32(const float* fmap1, const float* fmap2, float* lvl0_tiled, int B, int D, int h, int w,

@@ -86,6 +86,14 @@ int ffcorr_volume_f32(const float* fmap1, const float* fmap2, float* lvl0,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Same contraction with an explicit divisor instead of sqrt(D): FlowFormer's cost volume
+ * (FF_FlowFormer_Core/FlowFormer/LatentCostFormer/encoder.py:335-347, one head) is the unscaled one, divisor = 1.
+ */
+int ffcorr_volume_scaled_f32(const float* fmap1, const float* fmap2, float* lvl0,
+                             int B, int D, int h, int w, int precision, float divisor,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Average-pool pyramid.  lvl[0] is the input [Q, h, w]; lvl[i] (i >= 1) is written,
  * [Q, h>>i, w>>i] with floor semantics and the ((a+b)+c+d)/4 summation order of
  * ATen avg_pool2d, so the result is bit-identical to the reference given the same lvl[0].

@@ -278,6 +278,38 @@ def test_alternate_corrblock_equals_corrblock_bitwise(shape, nl, radius, chunk):
         m.AlternateCorrBlock(f1, f2, num_levels=nl, precision="fp32")
 
 
+@pytest.mark.parametrize("shape,heads", [((2, 64, 16, 24), 1), ((1, 128, 17, 21), 1), ((1, 96, 12, 16), 2)])
+def test_flowformer_cost_volume_and_flow_token(shape, heads):
+    """FlowFormer's unscaled multi-head volume (encoder.py:335-347) and single-level token lookup (decoder.py:185-203)
+    against their literal torch formulas."""
+    from focusflow_official_b200 import flowformer as fl
+
+    torch.manual_seed(3)
+    b, dim, h, w = shape
+    f1 = torch.randn(shape, device=DEV)
+    f2 = torch.randn(shape, device=DEV)
+    d = dim // heads
+    a = f1.view(b, heads, d, h * w).permute(0, 1, 3, 2).double()
+    c = f2.view(b, heads, d, h * w).permute(0, 1, 3, 2).double()
+    ref = torch.einsum("bhid,bhjd->bhij", a, c).view(b, heads, h, w, h, w)
+    for prec, tol in (("fp16", 1e-3), ("fp32", 2e-6)):
+        got = fl.cost_volume(f1, f2, heads=heads, precision=prec)
+        assert got.shape == ref.shape
+        assert float((got.double() - ref).norm() / ref.norm()) <= tol, prec
+    # token lookup on the reference layout [B*h*w, heads, h, w]
+    vol = fl.cost_volume(f1, f2, heads=heads, precision="fp32")
+    cost_maps = vol.permute(0, 2, 3, 1, 4, 5).reshape(b * h * w, heads, h, w).contiguous()
+    coords = ff().coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 2
+    got = fl.encode_flow_token(cost_maps, coords)
+    dd = torch.linspace(-4, 4, 9, device=DEV)
+    delta = torch.stack(torch.meshgrid(dd, dd, indexing="ij"), dim=-1).view(1, 9, 9, 2)
+    cl = coords.permute(0, 2, 3, 1).reshape(b * h * w, 1, 1, 2) + delta
+    grid = torch.stack([2 * cl[..., 0] / (w - 1) - 1, 2 * cl[..., 1] / (h - 1) - 1], -1)
+    want = torch.nn.functional.grid_sample(cost_maps, grid, align_corners=True).view(b, h, w, -1).permute(0, 3, 1, 2)
+    assert got.shape == want.shape == (b, heads * 81, h, w)
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
 # ---------------------------------------------------------------- gradients (SURVEY 8f N1)
 def test_corrblock_gradients_match_torch_autograd():
     m = ff()
