@@ -554,9 +554,13 @@ static size_t tiled_pyramid_smem(const TiledPyrParams& p) {
 extern "C" int ffcorr_tiled_supported(int num_levels, int h, int w) {
     if (num_levels < 1 || num_levels > kFusedLevels || h < 1 || w < 1 || h > 16384 || w > 16384) return 0;
     if ((h >> (num_levels - 1)) < 1 || (w >> (num_levels - 1)) < 1) return 0;
-    TiledPyrParams p{};
-    float* dummy[kFusedLevels] = {nullptr, nullptr, nullptr, nullptr};
-    fill_tiled_params(&p, dummy, num_levels, h, w);
+    // limits of the fused build + tiled lookup: <= 4 levels (pooled in the GEMM epilogue), 32 query maps addressed
+    // with 32-bit element offsets, h*w < 2^24 (volume.cu).  The standalone ffcorr_pyramid_tiled_f32 is narrower:
+    // it stages whole maps in shared memory (see tiled_pyramid_standalone_ok).
+    return (int64_t)h * w < (1ll << 24) && (int64_t)tiled_th(h) * tiled_tw(w) * 16 < (1ll << 25);
+}
+
+static bool tiled_pyramid_standalone_ok(const TiledPyrParams& p) {
     return tiled_pyramid_smem(p) <= 200 * 1024 && (uint64_t)p.np[0] * 4 < (1u << 20);
 }
 
@@ -573,6 +577,9 @@ extern "C" int ffcorr_pyramid_tiled_f32(float* const* lvl, int num_levels, int64
     }
     TiledPyrParams p{};
     fill_tiled_params(&p, lvl, num_levels, h, w);
+    FFCORR_REQUIRE(tiled_pyramid_standalone_ok(p), FFCORR_EINVAL,
+                   "pyramid_tiled: a %dx%d map does not fit the standalone kernel's shared-memory staging; "
+                   "use ffcorr_build_tiled_f32 (pyramid fused into the GEMM)", h, w);
     const size_t smem = tiled_pyramid_smem(p);
     const int per_sm = smem <= 100 * 1024 ? 2 : 1;
     const int64_t want = (int64_t)per_sm * sm_count();

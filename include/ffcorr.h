@@ -122,7 +122,8 @@ int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coor
  * gathers.  The three entry points below are drop-ins for ffcorr_volume_f32 / ffcorr_pyramid_f32 /
  * ffcorr_lookup_f32 on that layout (same arguments, same results); ffcorr_untile_f32 / ffcorr_tile_f32
  * convert a level to / from the reference's row-major [Q, h_i, w_i] (CorrBlock.corr_pyramid, tests).
- * ffcorr_tiled_supported() tells whether a shape fits the tiled kernels (<= 4 levels, map <= ~48 KB).
+ * ffcorr_tiled_supported() tells whether a shape fits ffcorr_build_tiled_f32 + ffcorr_lookup_tiled_f32 (<= 4 levels);
+ * the standalone ffcorr_pyramid_tiled_f32 additionally needs the level-0 map to fit its shared-memory staging (~48 KB).
  */
 int64_t ffcorr_tiled_map_elems(int h, int w, int level);
 int ffcorr_tiled_supported(int num_levels, int h, int w);

@@ -645,7 +645,8 @@ def test_fused_build_equals_volume_then_pyramid_bitwise(shape, nl, precision):
         assert torch.equal(fa, pa), (i, (fa != pa).sum().item())
 
 
-@pytest.mark.parametrize("shape", [(1, 256, 46, 62), (2, 64, 17, 21), (2, 32, 16, 24), (1, 40, 9, 13)])
+@pytest.mark.parametrize("shape", [(1, 256, 46, 62), (2, 64, 17, 21), (2, 32, 16, 24), (1, 40, 9, 13),
+                                   (1, 32, 100, 160)])   # 64 KB maps: beyond the standalone tiled pyramid, fused build only
 def test_tiled_and_rowmajor_blocks_agree_bitwise(shape):
     """Same kernels' arithmetic, two storage orders: pyramids and lookups must be identical."""
     m = ff()
