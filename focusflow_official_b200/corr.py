@@ -1,4 +1,4 @@
-"""CorrBlock: drop-in for ``FF_RAFT_Core/corr.py:12-60`` backed by libffcorr (sm_100a).
+"""CorrBlock / AlternateCorrBlock: drop-ins for ``FF_RAFT_Core/corr.py:12-91`` backed by libffcorr (sm_100a).
 
 Same surface as the reference: ``CorrBlock(fmap1, fmap2, num_levels=4, radius=4)`` builds the
 all-pairs volume and its average-pool pyramid once (reference ``corr.py:13-27``), and
@@ -11,20 +11,23 @@ Differences, all deliberate:
   * the contraction runs on tcgen05 tensor cores with fp16-rounded operands and fp32
     accumulation by default (the reference uses TF32 cuBLAS, ``common.py:25-27``);
     ``precision="fp32" | "bf16x3" | "tf32"`` select the other operand modes.
-  * one kernel per call instead of ~60 (lookup) / 4 (pyramid) / 2 (volume).
+  * one kernel per call instead of ~60 (lookup); volume + pyramid are ONE GEMM launch (plus the operand pre-pass)
+    when no gradient is needed -- the pyramid is then stored as 4x4-pixel tiles (``layout="tiled"``) and
+    ``corr_pyramid`` is converted lazily; under autograd the reference's row-major layout is kept and all lookups
+    of a block share one gradient buffer (``_GradSink``).
+  * range: fp16 operands need |fmap| < 65504 (and lose precision below ~6e-5); feature maps of the trained
+    networks are O(1-10).  Use ``precision="tf32"`` / ``"bf16x3"`` for unbounded activations.
 """
 from __future__ import annotations
 
-import ctypes
+import os
 from typing import List, Optional
 
 import torch
 
 from . import _lib
 
-import os
-
-__all__ = ["CorrBlock", "coords_grid", "correlation_volume", "correlation_pyramid", "lookup",
+__all__ = ["CorrBlock", "AlternateCorrBlock", "coords_grid", "correlation_volume", "correlation_pyramid", "lookup",
            "tiled_pyramid", "lookup_tiled", "tile_levels", "untile_levels"]
 
 DEFAULT_PRECISION = "fp16"
