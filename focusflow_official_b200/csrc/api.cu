@@ -49,6 +49,14 @@ int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const vo
                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle, const char* what) {
     PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
     FFCORR_REQUIRE(fn != nullptr, FFCORR_EDEVICE, "cuTensorMapEncodeTiled is not available from the driver");
+    // The encoder is a DRIVER call and needs a current context.  A thread that has only been handed a device by
+    // the runtime (PyTorch's autograd worker running a backward as its first CUDA work) has none bound yet, and the
+    // call fails with CUDA_ERROR_INVALID_CONTEXT; cudaFree(nullptr) binds the primary context (once per thread).
+    static thread_local bool context_bound = false;
+    if (!context_bound) {
+        FFCORR_CUDA(cudaFree(nullptr));
+        context_bound = true;
+    }
     FFCORR_REQUIRE(rank >= 1 && rank <= 5, FFCORR_EINVAL, "tensor map rank %d", rank);
     cuuint64_t d[5], st[4];
     cuuint32_t bx[5], es[5];

@@ -664,3 +664,69 @@ def test_tiled_and_rowmajor_blocks_agree_bitwise(shape):
     assert torch.equal(a(coords), r(coords))
     grid = m.coords_grid(b, h, w, DEV)
     assert torch.equal(a(grid), r(grid))
+
+
+# ---------------------------------------------------------------- randomized shape sweep
+def test_random_shapes_tiled_rowmajor_alternate_agree():
+    """40 random (B, D, h, w, levels, radius): fused tiled block == row-major block == chunked alternate block bit for
+    bit, level 0 within the fp16-operand bar of an fp64 contraction, lookups within 1e-5 of the numpy oracle on the
+    block's own pyramid (spot-checked on a subset of queries)."""
+    m = ff()
+    rng = np.random.default_rng(2024)
+    for it in range(40):
+        h, w = int(rng.integers(8, 72)), int(rng.integers(8, 72))
+        nl = int(rng.integers(1, 5))
+        while (h >> (nl - 1)) < 1 or (w >> (nl - 1)) < 1:
+            nl -= 1
+        b = int(rng.integers(1, 4))
+        d = int(rng.choice([8, 24, 64, 100, 256]))
+        radius = int(rng.integers(1, 5))
+        torch.manual_seed(it)
+        f1 = torch.randn(b, d, h, w, device=DEV) * 3
+        f2 = torch.randn(b, d, h, w, device=DEV) * 3
+        coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * float(rng.choice([0.0, 1.5, 12.0]))
+        tag = (it, b, d, h, w, nl, radius)
+        tl = m.CorrBlock(f1, f2, num_levels=nl, radius=radius, layout="tiled")
+        rm = m.CorrBlock(f1, f2, num_levels=nl, radius=radius, layout="rowmajor")
+        assert tl._tiled and not rm._tiled, tag
+        out_t, out_r = tl(coords), rm(coords)
+        assert torch.equal(out_t, out_r), tag
+        for i in range(nl):
+            assert torch.equal(tl.corr_pyramid[i], rm.corr_pyramid[i]), (tag, i)
+        alt = m.AlternateCorrBlock(f1, f2, num_levels=nl, radius=radius, chunk=int(rng.choice([32, 96, 128, 1000])))
+        assert torch.equal(alt(coords), out_t), tag
+        n = h * w
+        ref0 = torch.matmul(f1.view(b, d, n).transpose(1, 2).double(), f2.view(b, d, n).double()) / np.sqrt(d)
+        got0 = rm.corr_pyramid[0].view(b, n, n).double()
+        assert float((got0 - ref0).norm() / ref0.norm()) <= 1e-3, tag
+        if it % 4 == 0:
+            sel = np.arange(0, n, max(1, n // 24))
+            pyr = [lv.view(b, n, lv.shape[2], lv.shape[3])[0, sel].cpu().numpy() for lv in rm.corr_pyramid]
+            cxy = coords.view(b, 2, n)[0][:, sel].cpu().numpy()
+            ref = np.concatenate([co.lookup_level(pyr[i], cxy[0] / np.float32(2 ** i), cxy[1] / np.float32(2 ** i), radius)
+                                  for i in range(nl)], axis=1)
+            got = out_r.view(b, -1, n)[0][:, sel].t().cpu().numpy()
+            assert max_rel(got, ref) <= 1e-5, tag
+
+
+def test_random_shapes_pwc_forward_backward():
+    """Random PWC shapes (aligned and W % 4 != 0, C around the 8 / 32 channel stage sizes) against the C restatement."""
+    m = ff()
+    rng = np.random.default_rng(77)
+    for it in range(12):
+        b = int(rng.integers(1, 3))
+        c = int(rng.choice([3, 8, 31, 32, 33, 70]))
+        h = int(rng.integers(3, 30))
+        w = int(rng.integers(3, 50)) if it % 3 else int(rng.integers(1, 12)) * 4
+        one = rng.standard_normal((b, c, h, w)).astype(np.float32)
+        two = rng.standard_normal((b, c, h, w)).astype(np.float32)
+        g = rng.standard_normal((b, 81, h, w)).astype(np.float32)
+        a, bb = t(one).requires_grad_(True), t(two).requires_grad_(True)
+        out = m.FunctionCorrelation(a, bb)
+        out.backward(t(g))
+        ref = po.forward_c(one, two)
+        r1, r2 = po.backward_c(one, two, g)
+        tag = (it, b, c, h, w)
+        assert np.abs(out.detach().cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), tag
+        assert np.abs(a.grad.cpu().numpy() - r1).max() <= 1e-5 * max(1.0, np.abs(r1).max()), tag
+        assert np.abs(bb.grad.cpu().numpy() - r2).max() <= 1e-5 * max(1.0, np.abs(r2).max()), tag
