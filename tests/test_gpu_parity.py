@@ -730,3 +730,27 @@ def test_random_shapes_pwc_forward_backward():
         assert np.abs(out.detach().cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), tag
         assert np.abs(a.grad.cpu().numpy() - r1).max() <= 1e-5 * max(1.0, np.abs(r1).max()), tag
         assert np.abs(bb.grad.cpu().numpy() - r2).max() <= 1e-5 * max(1.0, np.abs(r2).max()), tag
+
+
+def test_kernels_run_on_the_current_stream():
+    """Everything is enqueued on torch's CURRENT stream (the reference's CuPy kernels ignore it): producing the
+    inputs on a side stream and consuming the results there must be correct without any extra synchronisation."""
+    m = ff()
+    torch.manual_seed(8)
+    b, d, h, w = 2, 64, 24, 32
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        f1 = torch.randn(b, d, h, w, device=DEV) * 3
+        f2 = torch.randn(b, d, h, w, device=DEV) * 3
+        for _ in range(20):                       # keep the side stream busy so a default-stream launch would race ahead
+            f1 = f1 * 1.0001
+            f2 = f2 * 0.9999
+        coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 2
+        blk = m.CorrBlock(f1, f2)
+        out_side = blk(coords)
+        cv_side = m.FunctionCorrelation(f1[:, :32], f2[:, :32])
+    side.synchronize()
+    ref = m.CorrBlock(f1, f2)
+    assert torch.equal(out_side, ref(coords))
+    assert torch.equal(cv_side, m.FunctionCorrelation(f1[:, :32], f2[:, :32]))

@@ -49,8 +49,21 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert L.ffcorr_tiled_map_elems(47, 156, 3) == 2 * 6 * 16
     assert L.ffcorr_volume_workspace_bytes(8, 256, 47, 156, 1) == 0            # fp32 path needs none
     assert L.ffcorr_pwc81_f32(1, 1, 1, 1, 0, 4, 4, -1.0, None) == -1
+    # the tiled / fused / chunked / scaled entry points validate before touching the device too
+    assert L.ffcorr_tiled_supported(4, 47, 156) == 1 and L.ffcorr_tiled_supported(5, 47, 156) == 0
+    assert L.ffcorr_tiled_supported(4, 100, 160) == 1                           # fused build: no shared-memory map limit
+    assert L.ffcorr_build_tiled_f32(1, 1, None, 4, 1, 256, 16, 16, 0, None, 0, None) == -1          # null level table
+    assert L.ffcorr_build_tiled_f32(1, 1, ptrs, 5, 1, 256, 64, 64, 0, None, 0, None) == -1          # > 4 levels
+    assert L.ffcorr_build_tiled_chunk_f32(ptrs, 4, 1, 256, 16, 16, 0, 32, 0, None, 0, None) == -1   # null level pointers
+    assert L.ffcorr_lookup_tiled_chunk_f32(ptrs, 4, 1, 1, 1, 16, 16, 250, 32, 4, None) == -1        # chunk beyond the map
+    assert b"query range" in L.ffcorr_last_error()
+    assert L.ffcorr_volume_scaled_f32(1, 1, 1, 1, 8, 8, 8, 0, ctypes.c_float(0.0), None, 0, None) == -1
+    assert b"divisor" in L.ffcorr_last_error()
+    assert L.ffcorr_stage_operands_f32(1, 1, 9, 1, 8, 8, 8, 0, None, 0, None) == -1                 # 9 levels
     # empty batches are a no-op, even with null pointers
     assert L.ffcorr_lookup_f32(None, 4, None, None, 0, 16, 16, 4, None) == 0
+    assert L.ffcorr_build_tiled_f32(None, None, ptrs, 4, 0, 256, 16, 16, 0, None, 0, None) == 0
+    assert L.ffcorr_lookup_tiled_chunk_f32(ptrs, 4, None, None, 0, 16, 16, 0, 32, 4, None) == 0
     with pytest.raises(RuntimeError):
         _lib.check(-1, "x")
 
