@@ -754,3 +754,26 @@ def test_kernels_run_on_the_current_stream():
     ref = m.CorrBlock(f1, f2)
     assert torch.equal(out_side, ref(coords))
     assert torch.equal(cv_side, m.FunctionCorrelation(f1[:, :32], f2[:, :32]))
+
+
+def test_config4_on_one_gpu_batch64():
+    """SURVEY config 4 on ONE GPU: B = 64 Sintel-shaped pairs, a 16.7 GB pyramid (3.2 G elements: 64-bit offsets,
+    blockIdx.z = 2B in the pre-pass, 14 k lookup blocks).  The last batch item must equal the same pair run alone."""
+    m = ff()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~25 GB of free HBM")
+    torch.manual_seed(64)
+    b, d, h, w = 64, 256, 55, 128
+    f1 = torch.randn(b, d, h, w, device=DEV) * 4.4
+    f2 = torch.randn(b, d, h, w, device=DEV) * 4.4
+    coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 3
+    blk = m.CorrBlock(f1, f2)
+    assert blk._tiled and sum(l.numel() for l in blk._levels) > 3_000_000_000
+    out = blk(coords)
+    torch.cuda.synchronize()
+    for j in (0, 37, 63):
+        one = m.CorrBlock(f1[j:j + 1], f2[j:j + 1])
+        assert torch.equal(one(coords[j:j + 1]), out[j:j + 1]), j
+    del blk, out
+    torch.cuda.empty_cache()
