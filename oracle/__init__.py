@@ -9,9 +9,11 @@ Pinning status: the reference ships no tests or golden vectors,
 so the oracle is pinned against outputs of the reference itself, generated in
 the build container by ``oracle/make_golden.py`` (imports the unmodified
 ``/root/reference`` code on CPU) and committed under ``tests/golden/``.
-The PWC path of the reference cannot execute anywhere without CuPy + a GPU
-(``PWCNet_Core/correlation.py:320-321`` raises on CPU), so for it the oracle is
-a literal C restatement of the CUDA-C strings (``oracle/pwc_ref.c``) checked
-against an independent numpy formulation: parity for PWC is "restated, not
-reference-executed".
+The PWC path of the reference has no CPU branch (``PWCNet_Core/correlation.py:320-321``
+raises) and needs CuPy, which is absent -- but its kernels are plain CUDA-C strings, so
+``oracle/build_pwc_ref_cuda.py`` specialises them with the reference's own ``cupy_kernel()``
+and compiles them with nvcc into ``oracle/_ref/libpwc_ref_cuda.so``; ``oracle/make_golden_pwc.py``
+ran them on a B200 and committed ``tests/golden/pwc_ref_cuda.npz``.  The C restatement
+(``oracle/pwc_ref.c``) and the numpy closed form both reproduce those outputs (2e-7 / 2e-6),
+and the GPU suite additionally runs the reference kernels live next to ours.
 """

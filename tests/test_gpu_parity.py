@@ -709,6 +709,52 @@ def test_random_shapes_tiled_rowmajor_alternate_agree():
             assert max_rel(got, ref) <= 1e-5, tag
 
 
+def _pwc_seeded(idx, shape):
+    rng = np.random.default_rng(1000 + idx)       # as oracle/make_golden_pwc.py
+    b, c, h, w = shape
+    return (rng.standard_normal(shape).astype(np.float32), rng.standard_normal(shape).astype(np.float32),
+            rng.standard_normal((b, 81, h, w)).astype(np.float32))
+
+
+def test_pwc_against_reference_cuda_kernel_golden():
+    """Forward and both gradients against tests/golden/pwc_ref_cuda.npz = outputs of the reference's own CUDA kernels."""
+    m = ff()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pwc_ref_cuda.npz"))
+    for idx in sorted(int(k.split("_")[1]) for k in g.files if k.startswith("shape_")):
+        shape = tuple(int(v) for v in g[f"shape_{idx}"])
+        one, two, gout = _pwc_seeded(idx, shape)
+        a, bb = t(one).requires_grad_(True), t(two).requires_grad_(True)
+        out = m.FunctionCorrelation(a, bb)
+        out.backward(t(gout))
+        for name, got, ref in (("out", out.detach(), g[f"out_{idx}"]), ("grad_one", a.grad, g[f"gone_{idx}"]),
+                               ("grad_two", bb.grad, g[f"gtwo_{idx}"])):
+            err = np.abs(got.cpu().numpy() - ref).max()
+            assert err <= 1e-5 * max(1.0, np.abs(ref).max()), (idx, name, err)
+
+
+def test_pwc_against_reference_cuda_kernels_live():
+    """The reference's CUDA kernels (oracle/_ref/libpwc_ref_cuda.so, built from correlation.py by
+    oracle/build_pwc_ref_cuda.py) run next to ours on this GPU, fresh random inputs, all five built shapes."""
+    from oracle import pwc_ref_cuda as ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref/libpwc_ref_cuda.so not built (needs /root/reference at build time)")
+    m = ff()
+    for idx, shape in enumerate(ref.shapes()):
+        torch.manual_seed(500 + idx)
+        b, c, h, w = shape
+        one = torch.randn(shape, device=DEV)
+        two = torch.randn(shape, device=DEV)
+        gout = torch.randn(b, 81, h, w, device=DEV)
+        r_out, r_g1, r_g2 = ref.run(idx, one, two, gout)
+        a, bb = one.clone().requires_grad_(True), two.clone().requires_grad_(True)
+        out = m.FunctionCorrelation(a, bb)
+        out.backward(gout)
+        for name, got, want in (("out", out.detach(), r_out), ("grad_one", a.grad, r_g1), ("grad_two", bb.grad, r_g2)):
+            err = float((got - want).abs().max())
+            assert err <= 1e-5 * max(1.0, float(want.abs().max())), (shape, name, err)
+
+
 def test_random_shapes_pwc_forward_backward():
     """Random PWC shapes (aligned and W % 4 != 0, C around the 8 / 32 channel stage sizes) against the C restatement."""
     m = ff()

@@ -91,6 +91,36 @@ def test_pwc_c_restatement_matches_closed_form():
         assert np.abs(c1 - n1).max() <= 1e-5 and np.abs(c2 - n2).max() <= 1e-5
 
 
+PWC_GOLD = os.path.join(os.path.dirname(__file__), "golden", "pwc_ref_cuda.npz")
+
+
+def _pwc_inputs(idx, shape):
+    """Same seeded inputs as oracle/make_golden_pwc.py."""
+    rng = np.random.default_rng(1000 + idx)
+    b, c, h, w = shape
+    return (rng.standard_normal(shape).astype(np.float32), rng.standard_normal(shape).astype(np.float32),
+            rng.standard_normal((b, 81, h, w)).astype(np.float32))
+
+
+def test_pwc_oracle_matches_the_reference_cuda_kernels():
+    """tests/golden/pwc_ref_cuda.npz holds the outputs of the REFERENCE's own CUDA kernels (correlation.py strings,
+    specialised by its own cupy_kernel() and compiled with nvcc by oracle/build_pwc_ref_cuda.py, run on a B200).
+    Both restatements must reproduce them: the C one keeps the kernel's 32-lane partial-sum order."""
+    g = np.load(PWC_GOLD)
+    idxs = sorted(int(k.split("_")[1]) for k in g.files if k.startswith("shape_"))
+    assert idxs, "empty fixture"
+    for idx in idxs:
+        shape = tuple(int(v) for v in g[f"shape_{idx}"])
+        one, two, gout = _pwc_inputs(idx, shape)
+        ref, r1, r2 = g[f"out_{idx}"], g[f"gone_{idx}"], g[f"gtwo_{idx}"]
+        for name, fwd, bwd, tol in (("c", po.forward_c, po.backward_c, 2e-7), ("numpy", po.forward_np, po.backward_np, 2e-6)):
+            out = fwd(one, two)
+            g1, g2 = bwd(one, two, gout)
+            assert np.abs(out - ref).max() <= tol * max(1.0, np.abs(ref).max()), (idx, name, np.abs(out - ref).max())
+            assert np.abs(g1 - r1).max() <= 10 * tol * max(1.0, np.abs(r1).max()), (idx, name, np.abs(g1 - r1).max())
+            assert np.abs(g2 - r2).max() <= 10 * tol * max(1.0, np.abs(r2).max()), (idx, name, np.abs(g2 - r2).max())
+
+
 def test_pwc_channel_order():
     """correlation.py:71-72: ch%9-4 shifts x, ch//9-4 shifts y."""
     one = np.zeros((1, 1, 9, 9), np.float32)
