@@ -28,6 +28,8 @@ _PROTOS = {
     "ffcorr_version": (_i, []),
     "ffcorr_last_error": (ctypes.c_char_p, []),
     "ffcorr_device_info": (_i, [ctypes.POINTER(_i)] * 3),
+    "ffcorr_set_sampler_semantics": (_i, [_i]),
+    "ffcorr_get_sampler_semantics": (_i, []),
     "ffcorr_set_l2_fetch_granularity": (_i, [_i]),
     "ffcorr_get_l2_fetch_granularity": (_i, [ctypes.POINTER(_i)]),
     "ffcorr_volume_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),

@@ -27,13 +27,27 @@ import torch
 
 from . import _lib
 
-__all__ = ["CorrBlock", "AlternateCorrBlock", "coords_grid", "correlation_volume", "correlation_pyramid", "lookup",
+__all__ = ["CorrBlock", "AlternateCorrBlock", "set_sampler_semantics", "get_sampler_semantics", "coords_grid", "correlation_volume", "correlation_pyramid", "lookup",
            "tiled_pyramid", "lookup_tiled", "tile_levels", "untile_levels"]
 
 DEFAULT_PRECISION = "fp16"
 # storage of the pyramid inside CorrBlock when no gradient is needed: "tiled" (4x4-pixel tiles, the fast
 # path) or "rowmajor" (the reference layout; always used under autograd and for precision="fp32")
 DEFAULT_LAYOUT = os.environ.get("FFCORR_LAYOUT", "tiled")
+
+
+def set_sampler_semantics(which: str) -> None:
+    """``"cpu"`` (default) or ``"cuda"``: reproduce the lookups of the reference run on CPU (ATen divides by ``W-1`` in
+    ``utils.py:61-62``) or on a GPU (ATen's CUDA kernel multiplies by the fp32 reciprocal).  The two differ by <= 1 ulp
+    of the normalised coordinate; the golden vectors in ``tests/golden`` come from the CPU run.  Process-wide."""
+    codes = {"cpu": 0, "cuda": 1}
+    if which not in codes:
+        raise ValueError(f"sampler semantics must be 'cpu' or 'cuda', got {which!r}")
+    _lib.check(_lib.lib().ffcorr_set_sampler_semantics(codes[which]), "ffcorr_set_sampler_semantics")
+
+
+def get_sampler_semantics() -> str:
+    return "cuda" if _lib.lib().ffcorr_get_sampler_semantics() == 1 else "cpu"
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:

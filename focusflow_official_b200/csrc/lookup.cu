@@ -36,6 +36,9 @@ namespace {
 constexpr int kWarpsPerBlock = 2;
 constexpr int kTile = 32;  // queries per warp
 
+// FFCORR_SAMPLER_ATEN_CPU (0, default) or FFCORR_SAMPLER_ATEN_CUDA (1): see source_index()
+int g_sampler_semantics = FFCORR_SAMPLER_ATEN_CPU;
+
 struct LookupParams {
     const float* lvl[FFCORR_MAX_LEVELS];
     int lh[FFCORR_MAX_LEVELS];
@@ -47,16 +50,22 @@ struct LookupParams {
     int blocks_per_batch;
 };
 
-// utils.py:61-62 then GridSampler.cuh:26, every op rounded to fp32 like the reference.
-__device__ __forceinline__ float source_index(float x, float size_m1) {
-    const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, x), size_m1), 1.0f);
+// utils.py:61-62 then GridSampler.cuh:26, every op rounded to fp32 like the reference.  The one place where the
+// reference's CPU and GPU runs differ is the division by (size - 1) in utils.py:61-62: ATen's CPU kernel divides,
+// its CUDA kernel multiplies by the fp32 reciprocal of the scalar (<= 1 ulp of the normalised coordinate, ~1e-5 px at
+// w = 156).  CUDA_SEM selects the latter (ffcorr_set_sampler_semantics); the default is the CPU form the golden
+// vectors were generated with.
+template <bool CUDA_SEM>
+__device__ __forceinline__ float source_index(float x, float size_m1, float rcp_size_m1) {
+    const float t = __fmul_rn(2.0f, x);
+    const float g = __fsub_rn(CUDA_SEM ? __fmul_rn(t, rcp_size_m1) : __fdiv_rn(t, size_m1), 1.0f);
     return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), size_m1);
 }
 
 // |index| beyond this is outside every supported map (h, w <= 16384): all taps are zero.
 constexpr float kWildLimit = 3.0e4f;
 
-template <int R, int QU>
+template <int R, int QU, bool CUDA_SEM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const LookupParams p) {
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;        // window extent incl. the +-1 floor deviation of the round trip
@@ -95,10 +104,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
         cy = __ldg(c + N) * inv_scale;
     }
     const float sx = (float)(lw - 1), sy = (float)(lh - 1);
-    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
-    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
-    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
-    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
+    const float rsx = __frcp_rn(sx), rsy = __frcp_rn(sy);     // ATen: 1.0 / scalar, in fp32
+    const float ixf = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(-R)), sx, rsx);
+    const float ixl = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(R)), sx, rsx);
+    const float iyf = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(-R)), sy, rsy);
+    const float iyl = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(R)), sy, rsy);
     const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
                       !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
     const int map_elems = lh * lw;                // < 2^24 (checked on the host)
@@ -163,9 +173,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
     bool deviated = false;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
+        const float ix = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(a - R)), sx, rsx);
         const float fx = floorf(ix);
-        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
+        const float iy = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(a - R)), sy, rsy);
         const float fy = floorf(iy);
         // corner distances of the ATen CUDA kernel: (ix_se - ix), (ix - ix_nw) with ix_se = ix_nw + 1
         wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
@@ -276,7 +286,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
 }
 
-template <int R>
+template <int R, bool CUDA_SEM>
 __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(const LookupTiledParams p) {
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;
@@ -317,10 +327,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     const float cx = __ldg(cptr) * inv_scale;
     const float cy = __ldg(cptr + p.coords_stride) * inv_scale;
     const float sx = (float)(lw - 1), sy = (float)(lh - 1);
-    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
-    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
-    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
-    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
+    const float rsx = __frcp_rn(sx), rsy = __frcp_rn(sy);     // ATen: 1.0 / scalar, in fp32
+    const float ixf = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(-R)), sx, rsx);
+    const float ixl = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(R)), sx, rsx);
+    const float iyf = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(-R)), sy, rsy);
+    const float iyl = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(R)), sy, rsy);
     const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
                       !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
     int x_lo = 0, y_lo = 0;
@@ -348,9 +359,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     bool deviated = false;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
+        const float ix = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(a - R)), sx, rsx);
         const float fx = floorf(ix);
-        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
+        const float iy = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(a - R)), sy, rsy);
         const float fy = floorf(iy);
         siy[a * kTile + lane] = iy;
         wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
@@ -513,7 +524,10 @@ int launch_lookup_tiled_stream(const LookupTiledParams& p0, cudaStream_t stream)
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kStreamWarps);
     const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
-    lookup_tiled_stream_kernel<R><<<(unsigned)blocks, kStreamWarps * 32, 0, stream>>>(p);
+    if (g_sampler_semantics == FFCORR_SAMPLER_ATEN_CUDA)
+        lookup_tiled_stream_kernel<R, true><<<(unsigned)blocks, kStreamWarps * 32, 0, stream>>>(p);
+    else
+        lookup_tiled_stream_kernel<R, false><<<(unsigned)blocks, kStreamWarps * 32, 0, stream>>>(p);
     return check_launch("lookup_tiled_stream_kernel");
 }
 
@@ -535,7 +549,7 @@ struct LookupBwdParams {
 // wy1[r-1] * hrow[r-1]; finally the warp flushes the 32 windows cooperatively, 32 consecutive window elements
 // per instruction, with red.global.add (the pyramid gradient accumulates over the lookups of all iterations).
 // ~100 reductions per (query, level) in row-contiguous runs instead of 324 scattered ones.
-template <int R>
+template <int R, bool CUDA_SEM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_bwd_kernel(const LookupBwdParams p, const int tiles_per_batch,
                                                                          const int blocks_per_batch) {
     constexpr int K = 2 * R + 1;
@@ -570,10 +584,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_bwd_kernel(const L
         cy = __ldg(c + N) * inv_scale;
     }
     const float sx = (float)(lw - 1), sy = (float)(lh - 1);
-    const float ixf = source_index(__fadd_rn(cx, (float)(-R)), sx);
-    const float ixl = source_index(__fadd_rn(cx, (float)(R)), sx);
-    const float iyf = source_index(__fadd_rn(cy, (float)(-R)), sy);
-    const float iyl = source_index(__fadd_rn(cy, (float)(R)), sy);
+    const float rsx = __frcp_rn(sx), rsy = __frcp_rn(sy);     // ATen: 1.0 / scalar, in fp32
+    const float ixf = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(-R)), sx, rsx);
+    const float ixl = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(R)), sx, rsx);
+    const float iyf = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(-R)), sy, rsy);
+    const float iyl = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(R)), sy, rsy);
     const bool wild = !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
                       !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
     const int map_elems = lh * lw;
@@ -597,9 +612,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_bwd_kernel(const L
     bool deviated = false;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-        const float ix = source_index(__fadd_rn(cx, (float)(a - R)), sx);
+        const float ix = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(a - R)), sx, rsx);
         const float fx = floorf(ix);
-        const float iy = source_index(__fadd_rn(cy, (float)(a - R)), sy);
+        const float iy = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(a - R)), sy, rsy);
         const float fy = floorf(iy);
         const bool dead = wild || !valid;
         wx1[a] = dead ? 0.f : __fsub_rn(ix, fx);
@@ -690,12 +705,16 @@ int launch_lookup_bwd(const LookupBwdParams& p, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
     constexpr int WIN = (K + 2) * (K + 2);
     const size_t smem = (size_t)kWarpsPerBlock * kTile * WIN * sizeof(float);
-    FFCORR_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_per_batch = ceil_div(p.N, kTile);
     const int blocks_per_batch = ceil_div(tiles_per_batch, kWarpsPerBlock);
     const int64_t blocks = (int64_t)p.num_levels * p.B * blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_bwd: grid too large");
-    lookup_bwd_kernel<R><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p, tiles_per_batch, blocks_per_batch);
+    if (g_sampler_semantics == FFCORR_SAMPLER_ATEN_CUDA)
+        lookup_bwd_kernel<R, true><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p, tiles_per_batch, blocks_per_batch);
+    else
+        lookup_bwd_kernel<R, false><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p, tiles_per_batch, blocks_per_batch);
     return check_launch("lookup_bwd_kernel");
 }
 
@@ -708,12 +727,16 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     int dev = 0;
     FFCORR_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FFCORR_CUDA(cudaFuncSetAttribute(lookup_kernel<R, QU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_dev = dev;
     }
     const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup: grid too large (%lld blocks)", (long long)blocks);
-    lookup_kernel<R, QU><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    if (g_sampler_semantics == FFCORR_SAMPLER_ATEN_CUDA)
+        lookup_kernel<R, QU, true><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    else
+        lookup_kernel<R, QU, false><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
     return check_launch("lookup_kernel");
 }
 
@@ -721,6 +744,15 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
 }  // namespace ffcorr
 
 using namespace ffcorr;
+
+extern "C" int ffcorr_set_sampler_semantics(int semantics) {
+    FFCORR_REQUIRE(semantics == FFCORR_SAMPLER_ATEN_CPU || semantics == FFCORR_SAMPLER_ATEN_CUDA, FFCORR_EINVAL,
+                   "set_sampler_semantics: %d is neither FFCORR_SAMPLER_ATEN_CPU nor FFCORR_SAMPLER_ATEN_CUDA", semantics);
+    g_sampler_semantics = semantics;
+    return FFCORR_OK;
+}
+
+extern "C" int ffcorr_get_sampler_semantics(void) { return g_sampler_semantics; }
 
 extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
                                  int B, int h, int w, int radius, void* stream) {

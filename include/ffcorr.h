@@ -102,6 +102,18 @@ int ffcorr_volume_scaled_f32(const float* fmap1, const float* fmap2, float* lvl0
 int ffcorr_pyramid_f32(float* const* lvl, int num_levels, int64_t Q, int h, int w, void* stream);
 
 /*
+ * Which of the reference's two runs the lookups reproduce bit-closely.  bilinear_sampler (utils/utils.py:61-62)
+ * normalises with x / (W-1): ATen's CPU kernel divides, its CUDA kernel multiplies by the fp32 reciprocal of the
+ * scalar -- a <= 1-ulp difference of the normalised coordinate (~1e-5 px at w = 156, ~3e-5 of max|value| in the
+ * output).  Default FFCORR_SAMPLER_ATEN_CPU: the form the golden vectors (reference run on CPU) were made with.
+ * Process-wide; applies to ffcorr_lookup_f32, ffcorr_lookup_tiled*_f32 and ffcorr_lookup_bwd_f32.
+ */
+#define FFCORR_SAMPLER_ATEN_CPU   0
+#define FFCORR_SAMPLER_ATEN_CUDA  1
+int ffcorr_set_sampler_semantics(int semantics);
+int ffcorr_get_sampler_semantics(void);
+
+/*
  * Fused multi-level bilinear window lookup (one launch per refinement iteration).
  *   lvl     : HOST array of num_levels device pointers, lvl[i] = [B*h*w, h>>i, w>>i]
  *   coords  : [B, 2, h, w]  channel 0 = x, channel 1 = y   (utils.py:74-77)

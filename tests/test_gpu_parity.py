@@ -165,6 +165,43 @@ def test_lookup_vs_oracle(shape, radius, nl):
         assert max_rel(got, ref) <= 1e-5, (shape, name, max_rel(got, ref))
 
 
+@pytest.mark.parametrize("shape", [(2, 46, 62), (1, 47, 156), (2, 17, 21)])
+def test_lookup_vs_the_reference_formula_on_torch_cuda(shape):
+    """What the reference runs on a GPU: corr.py:29-50 + utils.py:57-71 through ATen's CUDA kernels, whose division by
+    the scalar (W-1) is a multiplication by its fp32 reciprocal.  With set_sampler_semantics("cuda") the lookups (and
+    the adjoint) follow that form and agree to 1e-5; the default CPU form differs by up to ~3e-5 of max|value| -- the
+    same amount by which the reference's own CPU and GPU runs differ."""
+    m = ff()
+    b, h, w = shape
+    torch.manual_seed(41)
+    n = h * w
+    pyr = [torch.randn(b * n, 1, h >> i, w >> i, device=DEV) for i in range(4)]
+    dd = torch.linspace(-4, 4, 9, device=DEV)
+    delta = torch.stack(torch.meshgrid(dd, dd, indexing="ij"), dim=-1).view(1, 9, 9, 2)
+    assert m.get_sampler_semantics() == "cpu"
+    try:
+        for sigma in (0.7, 3.0, 25.0):
+            coords = m.coords_grid(b, h, w, DEV) + 0.37 + torch.randn(b, 2, h, w, device=DEV) * sigma
+            c = coords.permute(0, 2, 3, 1).reshape(b * n, 1, 1, 2)
+            outs = []
+            for i, lv in enumerate(pyr):
+                cl = c / 2 ** i + delta
+                hh, ww = lv.shape[-2:]
+                xg, yg = cl.split([1, 1], dim=-1)
+                grid = torch.cat([2 * xg / (ww - 1) - 1, 2 * yg / (hh - 1) - 1], dim=-1)
+                outs.append(torch.nn.functional.grid_sample(lv, grid, align_corners=True).view(b, h, w, -1))
+            ref = torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+            scale = float(ref.abs().max())
+            m.set_sampler_semantics("cpu")
+            for got in (m.lookup(pyr, coords, 4), m.lookup_tiled(m.tile_levels(pyr), coords, 4)):
+                assert float((got - ref).abs().max()) <= 1e-4 * scale, ("cpu", sigma)
+            m.set_sampler_semantics("cuda")
+            for got in (m.lookup(pyr, coords, 4), m.lookup_tiled(m.tile_levels(pyr), coords, 4)):
+                assert float((got - ref).abs().max()) <= 1e-5 * scale, ("cuda", sigma, float((got - ref).abs().max()) / scale)
+    finally:
+        m.set_sampler_semantics("cpu")
+
+
 def test_corrblock_surface_and_errors():
     m = ff()
     f = torch.randn(1, 16, 16, 24, device=DEV)
