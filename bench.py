@@ -16,6 +16,8 @@ image pair: every rank runs its own batch, there is no data-path collective (wea
   roofline  the dominant kernel of the hot path (the per-iteration lookup, 12 launches/step):
             algorithmic bytes (2904 B/query) / mean launch duration measured with
             CUDA events around every launch of the timed steps, vs the measured HBM peak
+  stock_gpu_hot_path  (N=1) the reference's own op sequence for the hot path through stock PyTorch CUDA kernels on
+            this GPU, next to this repo's kernels: correlation-path milliseconds per step
   cpu_baseline  the reference's CPU PyTorch path (oracle/corr_torch_cpu.py restates corr.py with
             the same ATen ops; host model = this repo's PyTorch rewrite, validated against the
             reference in tests/test_host_model.py) on a bounded sample: batch 1, same shape
@@ -148,6 +150,65 @@ def make_model(device, channels_last: bool):
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
     return model
+
+
+def stock_gpu_corr_path(b, device):
+    """SURVEY 8(d) 'stock' GPU baseline: the reference's own op sequence for the hot path (corr.py:13-60 +
+    utils.py:57-71: torch.matmul + divide, 3x avg_pool2d, per level meshgrid + grid_sample + glue) on THIS GPU,
+    TF32 matmul as the reference configures it, same fmap shape as the step.  Stock PyTorch CUDA kernels only --
+    none of this repo's code.  Returns (build_ms, lookup_ms), medians of 5 after 2 warm-ups."""
+    import torch.nn.functional as F
+
+    h, w, d = H // 8, W // 8, 256
+    n = h * w
+    g = torch.Generator(device=device)
+    g.manual_seed(1234)
+    f1 = torch.randn(b, d, h, w, device=device, generator=g) * 4.4
+    f2 = torch.randn(b, d, h, w, device=device, generator=g) * 4.4
+    ys, xs = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
+    coords = torch.stack([xs, ys], 0).float()[None].repeat(b, 1, 1, 1) + torch.randn(b, 2, h, w, device=device, generator=g) * 3
+    state = {}
+
+    def build():
+        corr = torch.matmul(f1.view(b, d, n).transpose(1, 2), f2.view(b, d, n)).view(b, h, w, 1, h, w)
+        corr = (corr / torch.sqrt(torch.tensor(d).float())).reshape(b * n, 1, h, w)
+        pyr = [corr]
+        for _ in range(3):
+            corr = F.avg_pool2d(corr, 2, stride=2)
+            pyr.append(corr)
+        state["pyr"] = pyr
+
+    def lookup():
+        r = 4
+        c = coords.permute(0, 2, 3, 1)
+        out = []
+        for i, corr in enumerate(state["pyr"]):
+            dx = torch.linspace(-r, r, 2 * r + 1, device=device)
+            delta = torch.stack(torch.meshgrid(dx, dx, indexing="ij"), axis=-1)
+            cl = c.reshape(b * n, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+            hh, ww = corr.shape[-2:]
+            xg, yg = cl.split([1, 1], dim=-1)
+            grid = torch.cat([2 * xg / (ww - 1) - 1, 2 * yg / (hh - 1) - 1], dim=-1)
+            out.append(F.grid_sample(corr, grid, align_corners=True).view(b, h, w, -1))
+        return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+
+    res = []
+    with torch.no_grad():
+        for fn in (build, lookup):
+            ts = []
+            for i in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                if i >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            res.append(ts[len(ts) // 2])
+    state.clear()
+    torch.cuda.empty_cache()
+    return res[0], res[1]
 
 
 # ------------------------------------------------------------------------------ CPU arm
@@ -407,6 +468,16 @@ def run_gpu_arm(args, rank, world, local):
 
     if rank != 0:
         return
+    stock = None
+    if world == 1 and lookup_ms and build_ms:
+        try:
+            sb, sl = stock_gpu_corr_path(b, device)
+            stock = {"what": "the reference's op sequence for the hot path through stock PyTorch CUDA kernels on this GPU "
+                             "(TF32 matmul), same fmap shape", "build_ms": round(sb, 4), "lookup_ms": round(sl, 4),
+                     "corr_path_ms_per_step": round(sb + ITERS * sl, 3),
+                     "this_repo_corr_path_ms_per_step": round(build_ms + ITERS * lookup_ms, 3)}
+        except Exception as exc:
+            stock = {"failed": str(exc)[:200]}
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -440,6 +511,7 @@ def run_gpu_arm(args, rank, world, local):
                      "volume_plus_pyramid_ms": round(build_ms, 4) if build_ms else None,
                      "build": build_roofline(build_ms, b, meter.tiled, peaks)},
         "cpu_baseline": cpu,
+        "stock_gpu_hot_path": stock,
     }
     print(json.dumps(line), flush=True)
 
