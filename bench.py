@@ -152,6 +152,41 @@ def make_model(device, channels_last: bool):
     return model
 
 
+class StockTorchCorrBlock:
+    """The reference's CorrBlock (corr.py:12-60 + utils.py:57-71) written with the stock PyTorch ops it calls, for
+    the 'what if only the hot path were stock' measurement.  Measurement only; never used by the product."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        import torch.nn.functional as F
+
+        self.num_levels, self.radius = num_levels, radius
+        b, d, h, w = fmap1.shape
+        n = h * w
+        corr = torch.matmul(fmap1.view(b, d, n).transpose(1, 2), fmap2.view(b, d, n)).view(b, h, w, 1, h, w)
+        corr = (corr / torch.sqrt(torch.tensor(d).float())).reshape(b * n, 1, h, w)
+        self.corr_pyramid = [corr]
+        for _ in range(num_levels - 1):
+            corr = F.avg_pool2d(corr, 2, stride=2)
+            self.corr_pyramid.append(corr)
+
+    def __call__(self, coords):
+        import torch.nn.functional as F
+
+        r = self.radius
+        coords = coords.permute(0, 2, 3, 1)
+        b, h, w, _ = coords.shape
+        out = []
+        for i, corr in enumerate(self.corr_pyramid):
+            dx = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
+            delta = torch.stack(torch.meshgrid(dx, dx, indexing="ij"), axis=-1)
+            cl = coords.reshape(b * h * w, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+            hh, ww = corr.shape[-2:]
+            xg, yg = cl.split([1, 1], dim=-1)
+            grid = torch.cat([2 * xg / (ww - 1) - 1, 2 * yg / (hh - 1) - 1], dim=-1)
+            out.append(F.grid_sample(corr, grid, align_corners=True).view(b, h, w, -1))
+        return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+
+
 def stock_gpu_corr_path(b, device):
     """SURVEY 8(d) 'stock' GPU baseline: the reference's own op sequence for the hot path (corr.py:13-60 +
     utils.py:57-71: torch.matmul + divide, 3x avg_pool2d, per level meshgrid + grid_sample + glue) on THIS GPU,
@@ -472,10 +507,20 @@ def run_gpu_arm(args, rank, world, local):
     if world == 1 and lookup_ms and build_ms:
         try:
             sb, sl = stock_gpu_corr_path(b, device)
+            # the whole model with ONLY the correlation block swapped for the stock one (same host code, same inputs)
+            ours_block = model.flow_net.corr_block
+            model.flow_net.corr_block = StockTorchCorrBlock
+            try:
+                ms_stock, _ = timed(step_resident, 2, 1)
+            finally:
+                model.flow_net.corr_block = ours_block
+            stock_pairs = world * b * 2 / (ms_stock * 1e-3)
             stock = {"what": "the reference's op sequence for the hot path through stock PyTorch CUDA kernels on this GPU "
                              "(TF32 matmul), same fmap shape", "build_ms": round(sb, 4), "lookup_ms": round(sl, 4),
                      "corr_path_ms_per_step": round(sb + ITERS * sl, 3),
-                     "this_repo_corr_path_ms_per_step": round(build_ms + ITERS * lookup_ms, 3)}
+                     "this_repo_corr_path_ms_per_step": round(build_ms + ITERS * lookup_ms, 3),
+                     "model_pairs_per_s_with_stock_corr_block": round(stock_pairs, 3),
+                     "model_pairs_per_s_with_this_repo": round(value, 3)}
         except Exception as exc:
             stock = {"failed": str(exc)[:200]}
     cpu = None
