@@ -12,9 +12,9 @@ Differences, all deliberate:
     accumulation by default (the reference uses TF32 cuBLAS, ``common.py:25-27``);
     ``precision="fp32" | "bf16x3" | "tf32"`` select the other operand modes.
   * one kernel per call instead of ~60 (lookup); volume + pyramid are ONE GEMM launch (plus the operand pre-pass)
-    when no gradient is needed -- the pyramid is then stored as 4x4-pixel tiles (``layout="tiled"``) and
-    ``corr_pyramid`` is converted lazily; under autograd the reference's row-major layout is kept and all lookups
-    of a block share one gradient buffer (``_GradSink``).
+    for the tensor-core precisions -- the pyramid is then stored as 4x4-pixel tiles (``layout="tiled"``) and
+    ``corr_pyramid`` is converted lazily; under autograd all lookups of a block share one row-major gradient
+    buffer (``_GradSink``), and the forward pyramid is still tiled because the backward never reads it.
   * range: fp16 operands need |fmap| < 65504 (and lose precision below ~6e-5); feature maps of the trained
     networks are O(1-10).  Use ``precision="tf32"`` / ``"bf16x3"`` for unbounded activations.
 """
@@ -208,8 +208,11 @@ class _GradSink:
 
 class _VolumePyramid(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, fmap1, fmap2, num_levels, precision, sink):
-        levels = _volume_pyramid_raw(fmap1, fmap2, num_levels, precision)
+    def forward(ctx, fmap1, fmap2, num_levels, precision, sink, tiled=False):
+        # tiled=True: the forward pyramid is stored as 4x4 tiles (fused build); the backward never reads it -- it
+        # needs the feature maps and the ROW-MAJOR gradient pyramid the lookups scatter into the sink -- so the
+        # storage order of the forward is free.  The tiled levels are not differentiable outputs themselves.
+        levels = (_volume_pyramid_tiled_raw if tiled else _volume_pyramid_raw)(fmap1, fmap2, num_levels, precision)
         ctx.save_for_backward(fmap1, fmap2)
         ctx.num_levels = num_levels
         ctx.precision = precision
@@ -217,6 +220,8 @@ class _VolumePyramid(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         if sink is None:
             return tuple(levels)
+        if tiled:
+            ctx.mark_non_differentiable(*levels)
         return (*levels, torch.zeros(1, device=fmap1.device, dtype=torch.float32))   # + the anchor
 
     @staticmethod
@@ -249,17 +254,41 @@ class _VolumePyramid(torch.autograd.Function):
                                            g1.data_ptr() if g1 is not None else None,
                                            g2.data_ptr() if g2 is not None else None, b, d, h, w, ctx.precision, stream),
                    "ffcorr_volume_bwd_f32")
-        return g1, g2, None, None, None
+        return g1, g2, None, None, None, None
+
+
+class _UntileWithGrad(torch.autograd.Function):
+    """``corr_pyramid`` of a block that stores its forward pyramid tiled while gradients are tracked: row-major copies
+    whose gradients (a level used directly in a loss) go to the block's sink like those of the lookups."""
+
+    @staticmethod
+    def forward(ctx, anchor, sink, b, h, w, *tiled):
+        ctx.sink = sink
+        ctx.set_materialize_grads(False)
+        return tuple(untile_levels(tiled, b, h, w))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        bufs = ctx.sink.buffers()
+        for buf, g in zip(bufs, grads):
+            if g is not None:
+                buf.add_(g.reshape(buf.shape))
+        return (ctx.sink.anchor_grad(), None, None, None, None, *([None] * len(bufs)))
 
 
 class _Lookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, coords, radius, sink, anchor, *levels):
-        out = _lookup_raw(levels, _lib.ptr_array(levels), coords, radius)
+        tiled = levels[0].dim() == 2                     # [B*N, map_elems] tiles vs [B*N, 1, h, w] rows
+        raw = _lookup_tiled_raw if tiled else _lookup_raw
+        out = raw(levels, _lib.ptr_array(levels), coords, radius)
         ctx.save_for_backward(coords)
         ctx.radius = radius
         ctx.sink = sink
         ctx.shapes = [tuple(l.shape) for l in levels]
+        if tiled and sink is None:
+            raise RuntimeError("a tiled pyramid is differentiable only through its CorrBlock")
         return out
 
     @staticmethod
@@ -326,6 +355,7 @@ class CorrBlock:
         b, _, h, w = fmap1.shape
         self._shape = (b, h, w)
         self._sink = None
+        self._grad_tiled = False
         layout = layout or DEFAULT_LAYOUT
         if layout not in ("tiled", "rowmajor"):
             raise ValueError(f"layout must be 'tiled' or 'rowmajor', got {layout!r}")
@@ -346,9 +376,12 @@ class CorrBlock:
             if f1.shape != f2.shape:
                 raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
             self._sink = _GradSink(_level_shapes(b, h, w, num_levels), f1.device)
-            outs = _VolumePyramid.apply(f1, f2, num_levels, code, self._sink)
+            # forward pyramid tiled (fused build, faster lookups) whenever the tensor-core path is allowed: the
+            # backward only needs the feature maps and the row-major gradient pyramid in the sink
+            self._grad_tiled = (layout == "tiled" and code != _lib.PREC_FP32 and b > 0 and tiled_supported(h, w, num_levels))
+            outs = _VolumePyramid.apply(f1, f2, num_levels, code, self._sink, self._grad_tiled)
             self._levels, self._anchor = list(outs[:-1]), outs[-1]
-            self._rowmajor = self._levels
+            self._rowmajor = None if self._grad_tiled else self._levels
         else:
             self._levels = correlation_pyramid(fmap1, fmap2, num_levels, precision)
             self._rowmajor = self._levels
@@ -360,7 +393,10 @@ class CorrBlock:
         block stores its pyramid in the tiled layout."""
         if self._rowmajor is None:
             b, h, w = self._shape
-            self._rowmajor = untile_levels(self._levels, b, h, w)
+            if self._grad_tiled and torch.is_grad_enabled():
+                self._rowmajor = list(_UntileWithGrad.apply(self._anchor, self._sink, b, h, w, *self._levels))
+            else:
+                self._rowmajor = untile_levels(self._levels, b, h, w)
         return self._rowmajor
 
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
@@ -372,6 +408,8 @@ class CorrBlock:
         if self._sink is not None and torch.is_grad_enabled():
             _require_cuda(coords, "coords")
             return _Lookup.apply(coords.float().contiguous(), self.radius, self._sink, self._anchor, *self._levels)
+        if self._grad_tiled:
+            return lookup_tiled(self._levels, coords, self.radius, self._ptrs)
         return lookup(self._levels, coords, self.radius, self._ptrs)
 
     @staticmethod

@@ -415,6 +415,33 @@ def test_tensor_core_backward_gemms(shape, precision):
         assert float((got - ref).norm() / ref.norm()) <= 2e-3, float((got - ref).norm() / ref.norm())
 
 
+def test_autograd_block_with_tiled_forward_equals_rowmajor_block():
+    """Under autograd the forward pyramid is stored tiled (fused build) when a tensor-core precision is used; outputs
+    and gradients must equal those of the row-major block, including a level used directly in the loss."""
+    m = ff()
+    torch.manual_seed(17)
+    b, d, h, w = 2, 48, 24, 32
+    f1 = (torch.randn(b, d, h, w, device=DEV) * 2).requires_grad_(True)
+    f2 = (torch.randn(b, d, h, w, device=DEV) * 2).requires_grad_(True)
+    coords = [m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 2 for _ in range(4)]
+    wgt = [torch.randn(b, 324, h, w, device=DEV) for _ in range(4)]
+    wl2 = torch.randn(b * h * w, 1, h // 4, w // 4, device=DEV)
+    res = {}
+    for layout in ("tiled", "rowmajor"):
+        f1.grad = f2.grad = None
+        blk = m.CorrBlock(f1, f2, precision="fp16", layout=layout)
+        assert blk._grad_tiled == (layout == "tiled")
+        outs = [blk(c) for c in coords]
+        loss = sum((o * wg).sum() for o, wg in zip(outs, wgt)) + (blk.corr_pyramid[2] * wl2).sum()
+        loss.backward()
+        res[layout] = ([o.detach() for o in outs], f1.grad.clone(), f2.grad.clone())
+    for a, r in zip(res["tiled"][0], res["rowmajor"][0]):
+        assert torch.equal(a, r)
+    for k in (1, 2):
+        a, r = res["tiled"][k], res["rowmajor"][k]
+        assert float((a - r).norm() / r.norm()) <= 1e-5, k     # same terms, different accumulation order in the sink
+
+
 def test_corrblock_gradients_many_lookups_and_direct_level_use():
     """12 lookups share one gradient buffer (_GradSink); a level used directly in the loss adds to it; a second
     backward through the retained graph starts from zero again."""
