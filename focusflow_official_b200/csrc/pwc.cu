@@ -610,10 +610,12 @@ extern "C" int ffcorr_pwc81_f32(const float* one, const float* two, float* out, 
                                        CU_TENSOR_MAP_SWIZZLE_NONE, "pwc two")) return rc;
         if (int rc = encode_tensor_map(&tm_one, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, one, dims, strides, box_one,
                                        CU_TENSOR_MAP_SWIZZLE_NONE, "pwc one")) return rc;
-        // channel split: enough CTAs for ~2 per SM, at most 8 per cluster, at most one stage each
+        // channel split across a cluster only while the grid stays within ONE CTA per SM: the DSMEM reduce-scatter
+        // and its two cluster barriers cost more than a few extra channel stages (28x64, C=96: split 4 = 47 us,
+        // no split = 128 CTAs x 12 stages), so splitting pays only for the levels that would leave most SMs idle.
         const int nstage_all = ceil_div(C, PCC);
         int split = 1;
-        while (split < 8 && (int64_t)num_tiles * split < 2ll * sm_count() && split * 2 <= nstage_all) split *= 2;
+        while (split < 8 && (int64_t)num_tiles * split * 2 <= sm_count() && split * 2 <= nstage_all) split *= 2;
         const bool pow2 = (C & (C - 1)) == 0;
         const float inv_c = 1.0f / (float)C;
         cudaLaunchConfig_t cfg{};
