@@ -29,7 +29,9 @@ SRC = os.path.join(REF, "core/models/ff-pwcnet/PWCNet_Core/correlation.py")
 OUT_DIR = os.path.join(HERE, "_ref")
 
 # (B, C, H, W): small cases incl. C not a multiple of 32, ragged sizes, one config-3 level shape
-SHAPES = [(2, 20, 11, 14), (1, 32, 8, 32), (2, 70, 19, 40), (1, 196, 7, 16), (1, 64, 28, 64)]
+SHAPES = [(2, 20, 11, 14), (1, 32, 8, 32), (2, 70, 19, 40), (1, 196, 7, 16), (1, 64, 28, 64),
+          # the five config-3 level shapes (B = 16), for tests/pwc_reference_timing.py
+          (16, 32, 112, 256), (16, 64, 56, 128), (16, 96, 28, 64), (16, 128, 14, 32), (16, 196, 7, 16)]
 
 
 def load_reference_pieces():

@@ -33,8 +33,9 @@ def shapes():
     return out
 
 
-def run(idx: int, one: torch.Tensor, two: torch.Tensor, gout: torch.Tensor):
-    """-> (out, grad_one, grad_two) as computed by the reference kernels for shape `idx` (inputs must match it)."""
+def run(idx: int, one: torch.Tensor, two: torch.Tensor, gout: torch.Tensor, backward: bool = True):
+    """-> (out, grad_one, grad_two) as computed by the reference kernels for shape `idx` (inputs must match it);
+    backward=False stops after the forward (gradients stay zero)."""
     L = _load()
     b, c, h, w = shapes()[idx]
     assert tuple(one.shape) == tuple(two.shape) == (b, c, h, w) and tuple(gout.shape) == (b, 81, h, w)
@@ -47,6 +48,7 @@ def run(idx: int, one: torch.Tensor, two: torch.Tensor, gout: torch.Tensor):
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     rc = L.pwc_ref_forward(idx, p(one), p(two), p(rbot0), p(rbot1), p(out))
     assert rc == 0, f"pwc_ref_forward -> {rc}"
-    rc = L.pwc_ref_backward(idx, p(rbot0), p(rbot1), p(gout), p(gone), p(gtwo))
-    assert rc == 0, f"pwc_ref_backward -> {rc}"
+    if backward:
+        rc = L.pwc_ref_backward(idx, p(rbot0), p(rbot1), p(gout), p(gone), p(gtwo))
+        assert rc == 0, f"pwc_ref_backward -> {rc}"
     return out, gone, gtwo
