@@ -887,3 +887,28 @@ def test_config4_on_one_gpu_batch64():
         assert torch.equal(one(coords[j:j + 1]), out[j:j + 1]), j
     del blk, out
     torch.cuda.empty_cache()
+
+
+def test_more_than_four_levels_uses_the_rowmajor_path():
+    """num_levels up to 8 is legal (FFCORR_MAX_LEVELS); beyond 4 the block stores row-major levels (generic one-level
+    pooling kernel) and must still match the oracle; gradients flow as well."""
+    m = ff()
+    torch.manual_seed(23)
+    b, d, h, w = 1, 32, 32, 48
+    nl = 5
+    f1 = (torch.randn(b, d, h, w, device=DEV) * 2).requires_grad_(True)
+    f2 = torch.randn(b, d, h, w, device=DEV) * 2
+    coords = m.coords_grid(b, h, w, DEV) + torch.randn(b, 2, h, w, device=DEV) * 2
+    with torch.no_grad():
+        blk = m.CorrBlock(f1, f2, num_levels=nl, radius=3)
+        assert not blk._tiled and len(blk.corr_pyramid) == nl
+        out = blk(coords)
+    pyr = [lv[:, 0].cpu().numpy() for lv in blk.corr_pyramid]
+    own = co.pyramid(pyr[0], nl)
+    assert all(np.array_equal(own[i], pyr[i]) for i in range(nl))
+    ref = co.lookup(pyr, coords.cpu().numpy(), 3)
+    assert out.shape == (b, nl * 49, h, w)
+    assert max_rel(out.cpu().numpy(), ref) <= 1e-5
+    blk_g = m.CorrBlock(f1, f2, num_levels=nl, radius=3)
+    blk_g(coords).square().sum().backward()
+    assert torch.isfinite(f1.grad).all() and float(f1.grad.abs().sum()) > 0
