@@ -559,8 +559,8 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // ------------------------------------------------------------------------------------------
 enum : int { CVT_F16 = 0, CVT_BF16X3_A = 1, CVT_BF16X3_B = 2, CVT_F32 = 3 };
 
-constexpr int PP_D = 32;    // K (channel) extent of a pre-pass tile
-constexpr int PP_N = 128;   // pixel extent of a pre-pass tile
+constexpr int PP_CH = 16;        // channels per thread: one 32-byte K-major piece per pixel in the 16-bit modes
+constexpr int PP_THREADS = 128;
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -573,108 +573,109 @@ __device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Transposing convert.  Reads are 16-byte vectors along the pixel axis, writes are full 32-byte
-// sectors along K (16 consecutive channels of one pixel per thread).
+// Transposing convert, register-only.  A thread owns 4 consecutive output rows (pixels) x 16 channels: it issues 16
+// independent 16-byte loads along the pixel axis (a warp reads 512 contiguous bytes of one channel plane), transposes
+// by register naming, and writes one 32-byte K-major piece per pixel.  (The first version staged 32 x 128 tiles in
+// shared memory and was bound by its scalar shared-memory column reads: 48 us / 19.8 M instructions at config 2.)
 // Tiled ("T4") target order for the B operand: row n' of the staged operand is pixel
-// (y, x) = (4*ty + iy, 4*tx + ix) with n' = (ty*TW + tx)*16 + iy*4 + ix, zero rows for the padding up to
-// multiples of 4, so the GEMM writes every query's map directly as 4x4-pixel tiles of 64 contiguous bytes.
+// (y, x) = (4*ty + iy, 4*tx + ix) with n' = (ty*TW + tx)*16 + iy*4 + ix, zero rows for the padding, so the GEMM
+// writes every query's map directly as 4x4-pixel tiles of 64 contiguous bytes.
 // Super-group order (enabled == 2, fused pyramid build): n' = sg*256 + c*64 + t*16 + iy*4 + ix is pixel
 // (y, x) = (16*sgy + 4*c + iy, 16*sgx + 4*t + ix), sg = sgy*SGW + sgx; padding up to multiples of 16.
 struct TiledB {
     int enabled;   // 0: row-major pixels, 1: 4x4 tiles in row-major tile order, 2: 16x16 super-groups of 4x4 tiles
     int h, w;      // feature-map size
-    int tw;        // enabled == 1: tiles per row, ceil(w / 4); enabled == 2: super-groups per row, ceil(w / 16)
+    int tw;        // enabled == 1: tiles per row (tiled_tw); enabled == 2: super-groups per row, ceil(w / 16)
     int np;        // padded pixel count = rows of the staged operand
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256) operand_prepass_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
-                                                              void* __restrict__ o1, void* __restrict__ o2,
-                                                              int B, int D, int N, int Dp /* padded K per segment */,
-                                                              const TiledB tb) {
-    __shared__ __align__(16) float tile[PP_D][PP_N + 4];
+__global__ void __launch_bounds__(PP_THREADS) operand_prepass_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                                     void* __restrict__ o1, void* __restrict__ o2,
+                                                                     int B, int D, int N, int Dp /* padded K per segment */,
+                                                                     const TiledB tb) {
     const int which = blockIdx.z / B;          // 0: fmap1 (A operand), 1: fmap2 (B operand)
     const int b = blockIdx.z - which * B;
     const float* __restrict__ in = (which == 0 ? f1 : f2) + (size_t)b * D * N;
     void* __restrict__ outp = which == 0 ? o1 : o2;
     const bool tiled = tb.enabled && which == 1;
     const int Nout = tiled ? tb.np : N;        // rows of the staged operand
-    const int n0 = blockIdx.x * PP_N, d0 = blockIdx.y * PP_D;
-    if (n0 >= Nout) return;
-    const int tid = threadIdx.x;
-    const bool vec_ok = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (!tiled || (tb.w & 3) == 0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int dd = (tid >> 5) + 8 * i, nn = (tid & 31) * 4;
-        const int d = d0 + dd, n = n0 + nn;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d < D && n < Nout) {
-            int src_n = n, lim = N - n;            // source pixel of output row n, and how many of the 4 exist
-            if (tiled) {                           // n is a multiple of 4: one row of one 4x4 tile
-                int y, x;
-                if (tb.enabled == 2) {
-                    const int sg = n >> 8, c = (n >> 6) & 3, t = (n >> 4) & 3, iy = (n >> 2) & 3;
-                    const int sgy = sg / tb.tw, sgx = sg - sgy * tb.tw;
-                    y = 16 * sgy + 4 * c + iy;
-                    x = 16 * sgx + 4 * t;
-                } else {
-                    const int t = n >> 4, iy = (n >> 2) & 3;
-                    const int ty = t / tb.tw, tx = t - ty * tb.tw;
-                    y = 4 * ty + iy;
-                    x = 4 * tx;
-                }
-                src_n = y * tb.w + x;
-                lim = (y < tb.h) ? tb.w - x : 0;
-            }
-            const float* src = in + (size_t)d * N + src_n;
-            if (vec_ok) {
-                if (lim >= 4) v = __ldg(reinterpret_cast<const float4*>(src));
-            } else {
-                if (lim > 0) v.x = __ldg(src + 0);
-                if (lim > 1) v.y = __ldg(src + 1);
-                if (lim > 2) v.z = __ldg(src + 2);
-                if (lim > 3) v.w = __ldg(src + 3);
-            }
-        }
-        *reinterpret_cast<float4*>(&tile[dd][nn]) = v;
-    }
-    __syncthreads();
-    const int nl = tid & (PP_N - 1), half = tid >> 7;
-    const int n = n0 + nl;
+    const int n = (blockIdx.x * PP_THREADS + threadIdx.x) * 4;   // first of this thread's 4 output rows
     if (n >= Nout) return;
-    float x[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) x[k] = tile[half * 16 + k][nl];
-    const int dcol = d0 + half * 16;
-    if (MODE == CVT_F16) {
-        __half* o = reinterpret_cast<__half*>(outp) + ((size_t)b * Nout + n) * Dp + dcol;
-        uint4 q0 = make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
-        uint4 q1 = make_uint4(pack_h2(x[8], x[9]), pack_h2(x[10], x[11]), pack_h2(x[12], x[13]), pack_h2(x[14], x[15]));
-        reinterpret_cast<uint4*>(o)[0] = q0;
-        reinterpret_cast<uint4*>(o)[1] = q1;
-    } else if (MODE == CVT_F32) {
-        float* o = reinterpret_cast<float*>(outp) + ((size_t)b * Nout + n) * Dp + dcol;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            reinterpret_cast<float4*>(o)[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
-    } else {
-        // bf16 hi/lo split; A rows hold [hi | hi | lo], B rows [hi | lo | hi] so that one
-        // K = 3*Dp GEMM computes hi*hi + hi*lo + lo*hi with fp32 accumulation.
-        __nv_bfloat16 hi[16], lo[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            hi[k] = __float2bfloat16_rn(x[k]);
-            lo[k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi[k]));
+    const int d0 = blockIdx.y * PP_CH;
+
+    int src_n = n, lim = N - n;                // source pixel of output row n, and how many of the 4 exist
+    if (tiled) {                               // n is a multiple of 4: one row of one 4x4 tile
+        int y, x;
+        if (tb.enabled == 2) {
+            const int sg = n >> 8, c = (n >> 6) & 3, t = (n >> 4) & 3, iy = (n >> 2) & 3;
+            const int sgy = sg / tb.tw, sgx = sg - sgy * tb.tw;
+            y = 16 * sgy + 4 * c + iy;
+            x = 16 * sgx + 4 * t;
+        } else {
+            const int t = n >> 4, iy = (n >> 2) & 3;
+            const int ty = t / tb.tw, tx = t - ty * tb.tw;
+            y = 4 * ty + iy;
+            x = 4 * tx;
         }
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + ((size_t)b * Nout + n) * (3 * (size_t)Dp) + dcol;
+        src_n = y * tb.w + x;
+        lim = (y < tb.h) ? tb.w - x : 0;
+    }
+    const bool vec_ok = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (!tiled || (tb.w & 3) == 0);
+
+    float4 v[PP_CH];                           // v[k] = channel d0 + k at the 4 pixels
 #pragma unroll
-        for (int seg = 0; seg < 3; ++seg) {
-            const bool use_lo = (which == 0) ? (seg == 2) : (seg == 1);
-            const __nv_bfloat16* v = use_lo ? lo : hi;
-            uint4 q0 = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
-            uint4 q1 = make_uint4(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]), pack_bf2(v[12], v[13]), pack_bf2(v[14], v[15]));
-            reinterpret_cast<uint4*>(o + (size_t)seg * Dp)[0] = q0;
-            reinterpret_cast<uint4*>(o + (size_t)seg * Dp)[1] = q1;
+    for (int k = 0; k < PP_CH; ++k) {
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int d = d0 + k;
+        if (d < D && lim > 0) {
+            const float* src = in + (size_t)d * N + src_n;
+            if (vec_ok && lim >= 4) {
+                v[k] = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+                v[k].x = __ldg(src + 0);
+                if (lim > 1) v[k].y = __ldg(src + 1);
+                if (lim > 2) v[k].z = __ldg(src + 2);
+                if (lim > 3) v[k].w = __ldg(src + 3);
+            }
+        }
+    }
+    const int rows = min(4, Nout - n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= rows) break;
+        float x[PP_CH];
+#pragma unroll
+        for (int k = 0; k < PP_CH; ++k) x[k] = j == 0 ? v[k].x : (j == 1 ? v[k].y : (j == 2 ? v[k].z : v[k].w));
+        const size_t row = (size_t)b * Nout + n + j;
+        if (MODE == CVT_F16) {
+            __half* o = reinterpret_cast<__half*>(outp) + row * Dp + d0;
+            reinterpret_cast<uint4*>(o)[0] = make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
+            reinterpret_cast<uint4*>(o)[1] = make_uint4(pack_h2(x[8], x[9]), pack_h2(x[10], x[11]), pack_h2(x[12], x[13]), pack_h2(x[14], x[15]));
+        } else if (MODE == CVT_F32) {
+            float* o = reinterpret_cast<float*>(outp) + row * Dp + d0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                reinterpret_cast<float4*>(o)[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+        } else {
+            // bf16 hi/lo split; A rows hold [hi | hi | lo], B rows [hi | lo | hi] so that one
+            // K = 3*Dp GEMM computes hi*hi + hi*lo + lo*hi with fp32 accumulation.
+            __nv_bfloat16 hi[PP_CH], lo[PP_CH];
+#pragma unroll
+            for (int k = 0; k < PP_CH; ++k) {
+                hi[k] = __float2bfloat16_rn(x[k]);
+                lo[k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi[k]));
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + row * (3 * (size_t)Dp) + d0;
+#pragma unroll
+            for (int seg = 0; seg < 3; ++seg) {
+                const bool use_lo = (which == 0) ? (seg == 2) : (seg == 1);
+                const __nv_bfloat16* q = use_lo ? lo : hi;
+                reinterpret_cast<uint4*>(o + (size_t)seg * Dp)[0] =
+                    make_uint4(pack_bf2(q[0], q[1]), pack_bf2(q[2], q[3]), pack_bf2(q[4], q[5]), pack_bf2(q[6], q[7]));
+                reinterpret_cast<uint4*>(o + (size_t)seg * Dp)[1] =
+                    make_uint4(pack_bf2(q[8], q[9]), pack_bf2(q[10], q[11]), pack_bf2(q[12], q[13]), pack_bf2(q[14], q[15]));
+            }
         }
     }
 }
@@ -882,14 +883,15 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     tlb.np = fused ? ceil_div(h, 16) * tlb.tw * 256 : tiled_th(h) * tlb.tw * 16;
     const int Ncols = tiled ? tlb.np : N;       // columns of the volume == rows of the staged B operand
     if (phase != PHASE_GEMM) {
-        dim3 grid(ceil_div(Ncols, PP_N), Dp / PP_D, 2 * B);
+        // rows of the larger operand in groups of 4 per thread; row-major A (N rows) and B (Ncols >= N rows) share the grid
+        dim3 grid(ceil_div(ceil_div(Ncols > N ? Ncols : N, 4), PP_THREADS), Dp / PP_CH, 2 * B);
         FFCORR_REQUIRE(grid.y < 65536 && grid.z < 65536, FFCORR_EINVAL, "volume: pre-pass grid too large");
         if (precision == FFCORR_PREC_FP16)
-            operand_prepass_kernel<CVT_F16><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
+            operand_prepass_kernel<CVT_F16><<<grid, PP_THREADS, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         else if (precision == FFCORR_PREC_TF32)
-            operand_prepass_kernel<CVT_F32><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
+            operand_prepass_kernel<CVT_F32><<<grid, PP_THREADS, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         else
-            operand_prepass_kernel<CVT_BF16X3_A><<<grid, 256, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
+            operand_prepass_kernel<CVT_BF16X3_A><<<grid, PP_THREADS, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         if (int rc = check_launch("operand_prepass_kernel")) return rc;
     }
     if (phase == PHASE_STAGE) return FFCORR_OK;
