@@ -38,6 +38,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout at
+# communicator init, cuDNN / torch may warn), so the process-level stdout is pointed at stderr for the whole run and the
+# JSON line is written to the saved original descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "FF-RAFT pairs/sec @376x1248, 12 iters"
 UNIT = "pairs/s"
 H, W, ITERS, BATCH = 376, 1248, 12, 8
@@ -287,7 +298,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -558,7 +569,7 @@ def run_gpu_arm(args, rank, world, local):
         "cpu_baseline": cpu,
         "stock_gpu_hot_path": stock,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
