@@ -30,6 +30,43 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().ffcorr_version() == 100
 
 
+def test_ctypes_prototypes_match_the_header_parameter_by_parameter():
+    """Every prototype in _lib.SYMBOLS has the arity and the parameter KINDS (pointer / 32-bit int / 64-bit int /
+    size_t / float) of its declaration in include/ffcorr.h: a mismatch would silently corrupt arguments."""
+    from focusflow_official_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "ffcorr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|int64_t|const char\*)\s+(ffcorr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) == len(_lib.SYMBOLS)
+
+    def kind_of_c(param):
+        p = param.strip()
+        if p in ("void", ""):
+            return None
+        if "*" in p:
+            return "ptr"
+        if p.startswith("size_t"):
+            return "size_t"
+        if p.startswith("int64_t"):
+            return "i64"
+        if p.startswith("float"):
+            return "float"
+        assert p.startswith("int "), p
+        return "int"
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_size_t: "size_t", ctypes.c_int64: "i64", ctypes.c_float: "float", ctypes.c_int: "int"}[t]
+
+    for name, params in protos:
+        want = [k for k in (kind_of_c(p) for p in params.split(",")) if k is not None]
+        restype, argtypes = _lib._PROTOS[name]
+        got = [kind_of_ctypes(t) for t in argtypes]
+        assert got == want, (name, got, want)
+
+
 def test_argument_errors_are_return_codes_not_crashes():
     from focusflow_official_b200 import _lib
 
