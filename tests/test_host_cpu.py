@@ -117,6 +117,25 @@ def test_cpu_tensors_are_refused_not_silently_computed():
     assert g.shape == (2, 2, 3, 5) and float(g[1, 0, 2, 4]) == 4.0 and float(g[1, 1, 2, 4]) == 2.0
 
 
+def test_missing_extension_fails_loudly_in_a_fresh_process():
+    """No fallback: with the shared library absent, the first use of the package raises and names the build command."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from focusflow_official_b200 import _lib\n"
+        "_lib.LIB_PATH = _lib.LIB_PATH + '.absent'\n"
+        "import focusflow_official_b200 as ff\n"
+        "try:\n"
+        "    ff.get_sampler_semantics()\n"
+        "except RuntimeError as e:\n"
+        "    assert 'missing' in str(e) and 'make -C' in str(e), str(e)\n"
+        "    print('LOUD')\n" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "LOUD" in p.stdout, p.stdout + p.stderr[-1500:]
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "focusflow_official_b200")
     for dirpath, _, files in os.walk(pkg):
