@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..corr import AlternateCorrBlock as B200AlternateCorrBlock
 from ..corr import CorrBlock as B200CorrBlock
 from ..corr import coords_grid
 
@@ -253,6 +254,9 @@ class RAFTBody(nn.Module):
         self.update_block = UpdateBlock(self.corr_levels, self.corr_radius, self.hidden_dim)
         self.corr_block: Callable = B200CorrBlock
         self.corr_precision: Optional[str] = None
+        # raft.py:63,195-196 `alternate_corr` (config key ALT_CORR): the memory-bounded block that recomputes the
+        # pyramid per lookup; inference only, like the reference's alt_cuda_corr
+        self.alternate_corr = False
         # host plumbing knob: run the GRU update block in channels_last (NHWC) so cuDNN's tensor-core
         # kernels need no per-conv NCHW<->NHWC transposes; numerically the same convolutions
         self.update_channels_last = False
@@ -263,6 +267,9 @@ class RAFTBody(nn.Module):
                 m.eval()
 
     def _make_corr(self, fmap1, fmap2):
+        if self.alternate_corr and self.corr_block is B200CorrBlock and not torch.is_grad_enabled():
+            return B200AlternateCorrBlock(fmap1, fmap2, num_levels=self.corr_levels, radius=self.corr_radius,
+                                          precision=self.corr_precision)
         if self.corr_block is B200CorrBlock:
             return B200CorrBlock(fmap1, fmap2, num_levels=self.corr_levels, radius=self.corr_radius,
                                  precision=self.corr_precision)

@@ -912,3 +912,17 @@ def test_more_than_four_levels_uses_the_rowmajor_path():
     blk_g = m.CorrBlock(f1, f2, num_levels=nl, radius=3)
     blk_g(coords).square().sum().backward()
     assert torch.isfinite(f1.grad).all() and float(f1.grad.abs().sum()) > 0
+
+
+def test_host_model_with_alternate_corr_gives_the_same_flow():
+    """raft.py:195-196 `alternate_corr`: the memory-bounded block behind the same host model -> identical flow."""
+    from test_host_model import make_model
+    from weights import synthetic_pair
+
+    model = make_model().to(DEV).eval()
+    im1, im2, m1, _ = (x.to(DEV) for x in synthetic_pair(1, 128, 192, seed=3))
+    with torch.no_grad():
+        ref = model(im1, im2, m1, None, raft_iters=4, test_mode=True)[1]
+        model.flow_net.alternate_corr = True
+        alt = model(im1, im2, m1, None, raft_iters=4, test_mode=True)[1]
+    assert torch.equal(ref, alt)
