@@ -258,19 +258,42 @@ def stock_gpu_corr_path(b, device):
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(steps: int, warmup: int, batch: int = 1):
-    """Reference CPU path (ATen ops of corr.py) under the PyTorch host model, all host threads."""
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def load_reference_model(device):
+    """The UNMODIFIED reference FF_RAFT_FUSION (ff_raft.py:75-160) from /root/reference or its verbatim copy under
+    baseline/_ref (oracle/install_reference.py), with the same deterministic weights the B200 arm uses.
+    Returns (model, kind): kind "reference", or ("port", this repo's host model + oracle/corr_torch_cpu.py) when the
+    reference sources are not installed."""
+    from oracle import reference_loader as RL
+    from weights import fill_state_dict
+
+    if RL.reference_root() is not None:
+        model, _, _ = RL.load_ff_raft()
+        sd = model.state_dict()
+        fill_state_dict(sd, seed=1234)
+        model.load_state_dict(sd, strict=True)
+        return model.to(device).eval(), "reference"
     from oracle.corr_torch_cpu import TorchCorrBlock
+
+    model = make_model(device, False)
+    model.flow_net.corr_block = TorchCorrBlock
+    return model, "port"
+
+
+def cpu_reference_run(steps: int, warmup: int, batch: int = 1):
+    """The reference's own CPU path (FF_RAFT_FUSION.forward, ff_raft.py:134, test mode, 12 iterations) on all host
+    threads, on a bounded sample of the workload: `batch` pair(s) per step."""
     from weights import synthetic_pair
 
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can get
-    try:
-        ncpu = len(os.sched_getaffinity(0))
-    except AttributeError:
-        ncpu = os.cpu_count() or 1
-    torch.set_num_threads(max(1, ncpu))
-    model = make_model("cpu", False)
-    model.flow_net.corr_block = TorchCorrBlock
+    torch.set_num_threads(host_threads())
+    model, kind = load_reference_model("cpu")
     im1, im2, m1, m2 = synthetic_pair(batch, H, W, seed=1234)
     with torch.no_grad():
         for _ in range(warmup):
@@ -279,26 +302,57 @@ def cpu_reference_run(steps: int, warmup: int, batch: int = 1):
         for _ in range(steps):
             model(im1, im2, m1, m2, raft_iters=ITERS, test_mode=True)
         dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads()
+    return batch * steps / dt, dt / steps, torch.get_num_threads(), kind
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    val, sec, cores = cpu_reference_run(steps, min(args.warmup, 1))
+    steps = max(5, min(args.steps, 8))            # >= 5 timed steps: a 3-step sample swung 1.1-2.0 pairs/s in round 1
+    warmup = max(1, min(args.warmup, 2))
+    val, sec, cores, kind = cpu_reference_run(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "FocusRAFT inference, KITTI shape 376x1248, 12 iters, CPU", "batch": 1,
-                   "note": "bounded sample: 1 pair per step on the host cores"},
-        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} step(s) of 1 pair, 376x1248, 12 iters"},
+                   "note": "bounded sample: 1 pair per step on the host cores",
+                   "code": "unmodified reference FF_RAFT_FUSION (baseline/_ref or /root/reference)" if kind == "reference"
+                   else "this repo's PyTorch host model + oracle/corr_torch_cpu.py (reference sources not installed)"},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{steps} step(s) of 1 pair, 376x1248, 12 iters, after {warmup} warm-up"},
         "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def reference_on_this_gpu(b, device, steps=3, warmup=2):
+    """SURVEY 8(d) 'stock' baseline: the UNMODIFIED reference model (its own CorrBlock: cuBLAS TF32 matmul, avg_pool2d,
+    grid_sample + glue; its own encoder / update block code) on THIS GPU, same batch, same inputs, same weights,
+    TF32 and cudnn.benchmark as the reference configures them (common.py:20-27).  None if the sources are absent."""
+    from oracle import reference_loader as RL
+    from weights import synthetic_pair
+
+    if RL.reference_root() is None:
+        return None
+    model, _ = load_reference_model(device)
+    im1, im2, m1, m2 = (t.to(device) for t in synthetic_pair(b, H, W, seed=1234))
+    with torch.no_grad():
+        for _ in range(warmup):
+            model(im1, im2, m1, m2, raft_iters=ITERS, test_mode=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            model(im1, im2, m1, m2, raft_iters=ITERS, test_mode=True)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model
+    torch.cuda.empty_cache()
+    return {"what": "unmodified reference FF_RAFT_FUSION on this GPU (TF32, cudnn.benchmark), same batch / weights / inputs",
+            "ms_per_step": round(ms, 3), "pairs_per_s": round(b / (ms * 1e-3), 3), "steps": steps}
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -327,6 +381,7 @@ class LaunchMeter:
         self.build_events = []
         self.enabled = False
         self.tiled = False
+        self.nhwc = False
 
     def install(self):
         from focusflow_official_b200 import corr as C
@@ -335,12 +390,12 @@ class LaunchMeter:
         raw_lookup, raw_build = C._lookup_raw, C._volume_pyramid_raw
         raw_lookup_t, raw_build_t = C._lookup_tiled_raw, C._volume_pyramid_tiled_raw
 
-        def lookup(levels, ptrs, coords, radius):
+        def lookup(*a, **k):
             if not meter.enabled:
-                return raw_lookup(levels, ptrs, coords, radius)
+                return raw_lookup(*a, **k)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = raw_lookup(levels, ptrs, coords, radius)
+            out = raw_lookup(*a, **k)
             e1.record()
             meter.lookup_events.append((e0, e1))
             meter.launches += 1
@@ -357,16 +412,17 @@ class LaunchMeter:
             meter.launches += 3 if prec != 1 else 2  # operand pre-pass + GEMM + pyramid
             return out
 
-        def lookup_t(levels, ptrs, coords, radius):
+        def lookup_t(*a, **k):
             if not meter.enabled:
-                return raw_lookup_t(levels, ptrs, coords, radius)
+                return raw_lookup_t(*a, **k)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = raw_lookup_t(levels, ptrs, coords, radius)
+            out = raw_lookup_t(*a, **k)
             e1.record()
             meter.lookup_events.append((e0, e1))
             meter.launches += 1
             meter.tiled = True
+            meter.nhwc = bool(out.dim() == 4 and out.stride(1) == 1 and out.shape[1] > 1)
             return out
 
         def build_t(f1, f2, nl, prec):
@@ -532,16 +588,20 @@ def run_gpu_arm(args, rank, world, local):
                      "this_repo_corr_path_ms_per_step": round(build_ms + ITERS * lookup_ms, 3),
                      "model_pairs_per_s_with_stock_corr_block": round(stock_pairs, 3),
                      "model_pairs_per_s_with_this_repo": round(value, 3)}
+            try:
+                stock["reference_model"] = reference_on_this_gpu(b, device)
+            except Exception as exc:
+                stock["reference_model"] = {"failed": str(exc)[:200]}
         except Exception as exc:
             stock = {"failed": str(exc)[:200]}
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            v, sec, cores = cpu_reference_run(steps=1, warmup=1)
-            cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "1 warm-up + 1 timed forward of 1 pair, 376x1248, 12 iters (reference ATen ops on CPU)"}
+            v, sec, cores, kind = cpu_reference_run(steps=3, warmup=1)
+            cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "1 warm-up + 3 timed forwards of 1 pair, 376x1248, 12 iters (FF_RAFT_FUSION on the host cores)"}
         except Exception as exc:  # keep the GPU numbers even if the CPU arm fails
-            cpu = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {exc}"}
+            cpu = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "none", "sample": f"failed: {exc}"}
 
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -557,7 +617,8 @@ def run_gpu_arm(args, rank, world, local):
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "lookup_tiled_stream_kernel<4> (ffcorr_lookup_tiled_f32)" if meter.tiled else "lookup_kernel<4> (ffcorr_lookup_f32)",
+        "roofline": {"kernel": ("lookup_tiled_nhwc_kernel<4> (ffcorr_lookup_tiled_f32, out_channels_last)" if meter.nhwc else
+                                "lookup_tiled_stream_kernel<4> (ffcorr_lookup_tiled_f32)") if meter.tiled else "lookup_kernel<4> (ffcorr_lookup_f32)",
                      "bound": "hbm",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(achieved / peaks["hbm_gbs"], 4) if achieved else None, "traffic": traffic,

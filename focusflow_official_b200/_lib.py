@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 PREC_FP16, PREC_FP32, PREC_BF16X3, PREC_TF32 = 0, 1, 2, 3
 PRECISIONS = {"fp16": PREC_FP16, "fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "tf32": PREC_TF32}
+SAMPLERS = {"cpu": 0, "cuda": 1}   # FFCORR_SAMPLER_ATEN_CPU / FFCORR_SAMPLER_ATEN_CUDA
 MAX_LEVELS = 8
 
 _lock = threading.Lock()
@@ -28,15 +29,13 @@ _PROTOS = {
     "ffcorr_version": (_i, []),
     "ffcorr_last_error": (ctypes.c_char_p, []),
     "ffcorr_device_info": (_i, [ctypes.POINTER(_i)] * 3),
-    "ffcorr_set_sampler_semantics": (_i, [_i]),
-    "ffcorr_get_sampler_semantics": (_i, []),
     "ffcorr_set_l2_fetch_granularity": (_i, [_i]),
     "ffcorr_get_l2_fetch_granularity": (_i, [ctypes.POINTER(_i)]),
     "ffcorr_volume_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i, _i]),
     "ffcorr_volume_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_volume_scaled_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_float, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_pyramid_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
-    "ffcorr_lookup_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_lookup_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_tiled_map_elems": (ctypes.c_int64, [_i, _i, _i]),
     "ffcorr_tiled_supported": (_i, [_i, _i, _i]),
     "ffcorr_volume_tiled_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
@@ -44,11 +43,11 @@ _PROTOS = {
     "ffcorr_build_tiled_f32": (_i, [_vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_stage_operands_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_build_tiled_chunk_f32": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
-    "ffcorr_lookup_tiled_chunk_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "ffcorr_lookup_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_lookup_tiled_chunk_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ffcorr_lookup_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_untile_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_tile_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
-    "ffcorr_lookup_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_lookup_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_pyramid_bwd_f32": (_i, [ctypes.POINTER(_vp), _i, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_volume_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_pwc81_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]),
@@ -97,7 +96,35 @@ def ptr_array(tensors) -> ctypes.Array:
     return arr
 
 
-def current_stream() -> int:
+def current_stream(device=None) -> int:
+    """Raw cudaStream_t of torch's current stream ON `device` (default: the current device)."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """``with on_device(t0, t1, ...) as stream:`` -- every launch of this package runs inside one of these.
+
+    Checks that all tensors live on ONE CUDA device, makes that device current for the duration of the launch (the
+    kernels, the TMA descriptors and cudaFuncSetAttribute all act on the current device) and yields the raw handle of
+    torch's current stream on THAT device.  ATen ops guard the device the same way; without this a model on cuda:1
+    driven while cuda:0 is current would launch on device 0 with device-1 pointers."""
+
+    def __init__(self, *tensors):
+        import torch
+
+        devs = {t.device for t in tensors if t is not None}
+        if len(devs) != 1:
+            raise ValueError(f"all tensors of one call must live on the same device, got {sorted(map(str, devs))}")
+        (self.device,) = devs
+        if self.device.type != "cuda":
+            raise NotImplementedError(f"tensor on {self.device}: the B200 correlation path has no CPU implementation")
+        self._guard = torch.cuda.device(self.device)
+
+    def __enter__(self) -> int:
+        self._guard.__enter__()
+        return current_stream(self.device)
+
+    def __exit__(self, *exc):
+        return self._guard.__exit__(*exc)

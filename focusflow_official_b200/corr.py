@@ -17,6 +17,11 @@ Differences, all deliberate:
     buffer (``_GradSink``), and the forward pyramid is still tiled because the backward never reads it.
   * range: fp16 operands need |fmap| < 65504 (and lose precision below ~6e-5); feature maps of the trained
     networks are O(1-10).  Use ``precision="tf32"`` / ``"bf16x3"`` for unbounded activations.
+  * ``sampler="cuda"`` (default) reproduces the lookups of the reference run on a GPU, ``"cpu"`` those of its CPU run
+    (they differ by <= 1 ulp of the normalised coordinate, see :func:`set_sampler_semantics`); per block / per call.
+  * ``channels_last=True`` returns the same ``[B, C, h, w]`` values in NHWC memory (``torch.channels_last``), the
+    layout the consumer ``convc1`` (``update.py:82-83,90``) runs in, written directly by the lookup kernel.
+  * every launch runs under a device guard on the device of its tensors, on torch's current stream of that device.
 """
 from __future__ import annotations
 
@@ -36,18 +41,30 @@ DEFAULT_PRECISION = "fp16"
 DEFAULT_LAYOUT = os.environ.get("FFCORR_LAYOUT", "tiled")
 
 
+_default_sampler = "cuda"
+
+
 def set_sampler_semantics(which: str) -> None:
-    """``"cpu"`` (default) or ``"cuda"``: reproduce the lookups of the reference run on CPU (ATen divides by ``W-1`` in
-    ``utils.py:61-62``) or on a GPU (ATen's CUDA kernel multiplies by the fp32 reciprocal).  The two differ by <= 1 ulp
-    of the normalised coordinate; the golden vectors in ``tests/golden`` come from the CPU run.  Process-wide."""
-    codes = {"cpu": 0, "cuda": 1}
-    if which not in codes:
+    """Default ``sampler`` of blocks / calls that do not name one: ``"cuda"`` (initial value) reproduces the lookups of
+    the reference run on a GPU (ATen's CUDA kernel multiplies by the fp32 reciprocal of ``W-1`` in ``utils.py:61-62``),
+    ``"cpu"`` those of its CPU run (ATen divides) -- the form the golden vectors in ``tests/golden`` were made with.
+    The two differ by <= 1 ulp of the normalised coordinate.  This is a Python-side default only: the library has no
+    global state, the choice travels with every call (``include/ffcorr.h``: ``sampler``)."""
+    global _default_sampler
+    if which not in _lib.SAMPLERS:
         raise ValueError(f"sampler semantics must be 'cpu' or 'cuda', got {which!r}")
-    _lib.check(_lib.lib().ffcorr_set_sampler_semantics(codes[which]), "ffcorr_set_sampler_semantics")
+    _default_sampler = which
 
 
 def get_sampler_semantics() -> str:
-    return "cuda" if _lib.lib().ffcorr_get_sampler_semantics() == 1 else "cpu"
+    return _default_sampler
+
+
+def _sampler_code(sampler) -> int:
+    try:
+        return _lib.SAMPLERS[sampler or _default_sampler]
+    except KeyError:
+        raise ValueError(f"sampler must be 'cpu' or 'cuda', got {sampler!r}") from None
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -78,10 +95,10 @@ def _volume_pyramid_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: in
     levels = [torch.empty(s, device=fmap1.device, dtype=torch.float32) for s in _level_shapes(b, h, w, num_levels)]
     ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
     ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
-    stream = _lib.current_stream()
-    _lib.check(L.ffcorr_volume_f32(fmap1.data_ptr(), fmap2.data_ptr(), levels[0].data_ptr(), b, d, h, w, precision,
-                                   ws.data_ptr() if ws_bytes else None, ws_bytes, stream), "ffcorr_volume_f32")
-    _lib.check(L.ffcorr_pyramid_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream), "ffcorr_pyramid_f32")
+    with _lib.on_device(fmap1, fmap2) as stream:
+        _lib.check(L.ffcorr_volume_f32(fmap1.data_ptr(), fmap2.data_ptr(), levels[0].data_ptr(), b, d, h, w, precision,
+                                       ws.data_ptr() if ws_bytes else None, ws_bytes, stream), "ffcorr_volume_f32")
+        _lib.check(L.ffcorr_pyramid_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream), "ffcorr_pyramid_f32")
     # `ws` may be freed here: the caching allocator is stream-ordered on the current stream.
     return levels
 
@@ -106,24 +123,37 @@ def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_leve
               for i in range(num_levels)]
     ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
     ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
-    stream = _lib.current_stream()
-    if fused:
-        _lib.check(L.ffcorr_build_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), _lib.ptr_array(levels), num_levels, b, d, h, w,
-                                            precision, ws.data_ptr(), ws_bytes, stream), "ffcorr_build_tiled_f32")
-        return levels
-    _lib.check(L.ffcorr_volume_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), levels[0].data_ptr(), b, d, h, w, precision,
-                                         ws.data_ptr(), ws_bytes, stream), "ffcorr_volume_tiled_f32")
-    _lib.check(L.ffcorr_pyramid_tiled_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream),
-               "ffcorr_pyramid_tiled_f32")
+    with _lib.on_device(fmap1, fmap2) as stream:
+        if fused:
+            _lib.check(L.ffcorr_build_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), _lib.ptr_array(levels), num_levels, b, d, h, w,
+                                                precision, ws.data_ptr(), ws_bytes, stream), "ffcorr_build_tiled_f32")
+            return levels
+        _lib.check(L.ffcorr_volume_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), levels[0].data_ptr(), b, d, h, w, precision,
+                                             ws.data_ptr(), ws_bytes, stream), "ffcorr_volume_tiled_f32")
+        _lib.check(L.ffcorr_pyramid_tiled_f32(_lib.ptr_array(levels), num_levels, b * h * w, h, w, stream),
+                   "ffcorr_pyramid_tiled_f32")
     return levels
 
 
-def _lookup_tiled_raw(levels, level_ptrs, coords: torch.Tensor, radius: int) -> torch.Tensor:
+def _alloc_lookup_out(coords: torch.Tensor, num_levels: int, radius: int, channels_last: bool):
+    """-> (storage handed to the kernel, the [B, C, h, w] tensor the caller sees).  channels_last: NHWC storage, viewed
+    as NCHW with torch.channels_last strides -- what cuDNN's tensor-core kernels for the consumer conv want."""
     b, _, h, w = coords.shape
     k = 2 * radius + 1
-    out = torch.empty((b, len(levels) * k * k, h, w), device=coords.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ffcorr_lookup_tiled_f32(level_ptrs, len(levels), coords.data_ptr(), out.data_ptr(), b, h, w, radius,
-                                                  _lib.current_stream()), "ffcorr_lookup_tiled_f32")
+    if channels_last:
+        store = torch.empty((b, h, w, num_levels * k * k), device=coords.device, dtype=torch.float32)
+        return store, store.permute(0, 3, 1, 2)
+    store = torch.empty((b, num_levels * k * k, h, w), device=coords.device, dtype=torch.float32)
+    return store, store
+
+
+def _lookup_tiled_raw(levels, level_ptrs, coords: torch.Tensor, radius: int, sampler: int = 1,
+                      channels_last: bool = False) -> torch.Tensor:
+    b, _, h, w = coords.shape
+    store, out = _alloc_lookup_out(coords, len(levels), radius, channels_last)
+    with _lib.on_device(coords, levels[0]) as stream:
+        _lib.check(_lib.lib().ffcorr_lookup_tiled_f32(level_ptrs, len(levels), coords.data_ptr(), store.data_ptr(), b, h, w, radius,
+                                                      sampler, int(channels_last), stream), "ffcorr_lookup_tiled_f32")
     return out
 
 
@@ -133,8 +163,8 @@ def untile_levels(tiled_levels, b: int, h: int, w: int) -> List[torch.Tensor]:
     for i, t in enumerate(tiled_levels):
         hi, wi = h >> i, w >> i
         dst = torch.empty((b * h * w, 1, hi, wi), device=t.device, dtype=torch.float32)
-        _lib.check(_lib.lib().ffcorr_untile_f32(t.data_ptr(), dst.data_ptr(), b * h * w, hi, wi, _lib.current_stream()),
-                   "ffcorr_untile_f32")
+        with _lib.on_device(t) as stream:
+            _lib.check(_lib.lib().ffcorr_untile_f32(t.data_ptr(), dst.data_ptr(), b * h * w, hi, wi, stream), "ffcorr_untile_f32")
         out.append(dst)
     return out
 
@@ -147,7 +177,8 @@ def tile_levels(levels) -> List[torch.Tensor]:
         lv = lv.float().contiguous()
         q, _, hi, wi = lv.shape
         dst = torch.empty((q, _tiled_elems(hi, wi, 0)), device=lv.device, dtype=torch.float32)
-        _lib.check(_lib.lib().ffcorr_tile_f32(lv.data_ptr(), dst.data_ptr(), q, hi, wi, _lib.current_stream()), "ffcorr_tile_f32")
+        with _lib.on_device(lv) as stream:
+            _lib.check(_lib.lib().ffcorr_tile_f32(lv.data_ptr(), dst.data_ptr(), q, hi, wi, stream), "ffcorr_tile_f32")
         out.append(dst)
     return out
 
@@ -158,18 +189,20 @@ def tiled_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None, fused: bool
     return _volume_pyramid_tiled_raw(fmap1, fmap2, num_levels, _precision_code(precision), fused)
 
 
-def lookup_tiled(tiled_levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None) -> torch.Tensor:
+def lookup_tiled(tiled_levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None, sampler=None,
+                 channels_last: bool = False) -> torch.Tensor:
     _require_cuda(coords, "coords")
     coords = coords.float().contiguous()
-    return _lookup_tiled_raw(tiled_levels, level_ptrs if level_ptrs is not None else _lib.ptr_array(tiled_levels), coords, radius)
+    return _lookup_tiled_raw(tiled_levels, level_ptrs if level_ptrs is not None else _lib.ptr_array(tiled_levels), coords, radius,
+                             _sampler_code(sampler), channels_last)
 
 
-def _lookup_raw(levels, level_ptrs, coords: torch.Tensor, radius: int) -> torch.Tensor:
+def _lookup_raw(levels, level_ptrs, coords: torch.Tensor, radius: int, sampler: int = 1, channels_last: bool = False) -> torch.Tensor:
     b, _, h, w = coords.shape
-    k = 2 * radius + 1
-    out = torch.empty((b, len(levels) * k * k, h, w), device=coords.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ffcorr_lookup_f32(level_ptrs, len(levels), coords.data_ptr(), out.data_ptr(), b, h, w, radius,
-                                            _lib.current_stream()), "ffcorr_lookup_f32")
+    store, out = _alloc_lookup_out(coords, len(levels), radius, channels_last)
+    with _lib.on_device(coords, levels[0]) as stream:
+        _lib.check(_lib.lib().ffcorr_lookup_f32(level_ptrs, len(levels), coords.data_ptr(), store.data_ptr(), b, h, w, radius,
+                                                sampler, int(channels_last), stream), "ffcorr_lookup_f32")
     return out
 
 
@@ -245,15 +278,15 @@ class _VolumePyramid(torch.autograd.Function):
             for gl, gi in zip(g, direct):
                 if gi is not None:
                     gl.add_(gi.reshape(gl.shape))
-        stream = _lib.current_stream()
-        _lib.check(L.ffcorr_pyramid_bwd_f32(_lib.ptr_array(g), ctx.num_levels, b * h * w, h, w, stream),
-                   "ffcorr_pyramid_bwd_f32")
         g1 = torch.empty_like(fmap1) if ctx.needs_input_grad[0] else None
         g2 = torch.empty_like(fmap2) if ctx.needs_input_grad[1] else None
-        _lib.check(L.ffcorr_volume_bwd_f32(g[0].data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(),
-                                           g1.data_ptr() if g1 is not None else None,
-                                           g2.data_ptr() if g2 is not None else None, b, d, h, w, ctx.precision, stream),
-                   "ffcorr_volume_bwd_f32")
+        with _lib.on_device(fmap1, fmap2, g[0]) as stream:
+            _lib.check(L.ffcorr_pyramid_bwd_f32(_lib.ptr_array(g), ctx.num_levels, b * h * w, h, w, stream),
+                       "ffcorr_pyramid_bwd_f32")
+            _lib.check(L.ffcorr_volume_bwd_f32(g[0].data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(),
+                                               g1.data_ptr() if g1 is not None else None,
+                                               g2.data_ptr() if g2 is not None else None, b, d, h, w, ctx.precision, stream),
+                       "ffcorr_volume_bwd_f32")
         return g1, g2, None, None, None, None
 
 
@@ -279,12 +312,13 @@ class _UntileWithGrad(torch.autograd.Function):
 
 class _Lookup(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, coords, radius, sink, anchor, *levels):
+    def forward(ctx, coords, radius, sink, anchor, sampler, channels_last, *levels):
         tiled = levels[0].dim() == 2                     # [B*N, map_elems] tiles vs [B*N, 1, h, w] rows
         raw = _lookup_tiled_raw if tiled else _lookup_raw
-        out = raw(levels, _lib.ptr_array(levels), coords, radius)
+        out = raw(levels, _lib.ptr_array(levels), coords, radius, sampler, channels_last)
         ctx.save_for_backward(coords)
         ctx.radius = radius
+        ctx.sampler = sampler
         ctx.sink = sink
         ctx.shapes = [tuple(l.shape) for l in levels]
         if tiled and sink is None:
@@ -296,14 +330,15 @@ class _Lookup(torch.autograd.Function):
     def backward(ctx, gout):
         (coords,) = ctx.saved_tensors
         b, _, h, w = coords.shape
-        gout = gout.contiguous().float()
+        gout = gout.contiguous().float()                 # NCHW, whatever layout the forward's output had
         shared = ctx.sink is not None
         glv = ctx.sink.buffers() if shared else [torch.zeros(s, device=coords.device, dtype=torch.float32) for s in ctx.shapes]
-        _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), len(glv), coords.data_ptr(), gout.data_ptr(),
-                                                    b, h, w, ctx.radius, _lib.current_stream()), "ffcorr_lookup_bwd_f32")
+        with _lib.on_device(coords, gout, glv[0]) as stream:
+            _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), len(glv), coords.data_ptr(), gout.data_ptr(),
+                                                        b, h, w, ctx.radius, ctx.sampler, stream), "ffcorr_lookup_bwd_f32")
         if shared:   # the gradient reaches _VolumePyramid through the sink; the anchor only orders the two
-            return (None, None, None, ctx.sink.anchor_grad(), *([None] * len(glv)))
-        return (None, None, None, None, *glv)
+            return (None, None, None, ctx.sink.anchor_grad(), None, None, *([None] * len(glv)))
+        return (None, None, None, None, None, None, *glv)
 
 
 def _prep(fmap: torch.Tensor, name: str) -> torch.Tensor:
@@ -339,19 +374,25 @@ def correlation_volume(fmap1, fmap2, precision=None) -> torch.Tensor:
     return correlation_pyramid(fmap1, fmap2, 1, precision)[0].view(b, h, w, 1, h, w)
 
 
-def lookup(levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None) -> torch.Tensor:
+def lookup(levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None, sampler=None, channels_last: bool = False) -> torch.Tensor:
     _require_cuda(coords, "coords")
     coords = coords.float().contiguous()
+    code = _sampler_code(sampler)
     if torch.is_grad_enabled() and any(l.requires_grad for l in levels):
-        return _Lookup.apply(coords, radius, None, None, *levels)
-    return _lookup_raw(levels, level_ptrs if level_ptrs is not None else _lib.ptr_array(levels), coords, radius)
+        return _Lookup.apply(coords, radius, None, None, code, channels_last, *levels)
+    return _lookup_raw(levels, level_ptrs if level_ptrs is not None else _lib.ptr_array(levels), coords, radius, code, channels_last)
 
 
 class CorrBlock:
     def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4, precision: Optional[str] = None,
-                 layout: Optional[str] = None):
+                 layout: Optional[str] = None, sampler: Optional[str] = None, channels_last: bool = False):
         self.num_levels = num_levels
         self.radius = radius
+        self.sampler = sampler or _default_sampler
+        self._sampler = _sampler_code(sampler)
+        self.channels_last = bool(channels_last)
+        if fmap1.device != fmap2.device:
+            raise ValueError(f"fmap1 is on {fmap1.device}, fmap2 on {fmap2.device}")
         b, _, h, w = fmap1.shape
         self._shape = (b, h, w)
         self._sink = None
@@ -404,13 +445,14 @@ class CorrBlock:
         if (b, h, w) != self._shape or two != 2:
             raise ValueError(f"coords {tuple(coords.shape)} does not match the volume built for B,h,w={self._shape}")
         if self._tiled:
-            return lookup_tiled(self._levels, coords, self.radius, self._ptrs)
+            return lookup_tiled(self._levels, coords, self.radius, self._ptrs, self.sampler, self.channels_last)
         if self._sink is not None and torch.is_grad_enabled():
             _require_cuda(coords, "coords")
-            return _Lookup.apply(coords.float().contiguous(), self.radius, self._sink, self._anchor, *self._levels)
+            return _Lookup.apply(coords.float().contiguous(), self.radius, self._sink, self._anchor, self._sampler,
+                                 self.channels_last, *self._levels)
         if self._grad_tiled:
-            return lookup_tiled(self._levels, coords, self.radius, self._ptrs)
-        return lookup(self._levels, coords, self.radius, self._ptrs)
+            return lookup_tiled(self._levels, coords, self.radius, self._ptrs, self.sampler, self.channels_last)
+        return lookup(self._levels, coords, self.radius, self._ptrs, self.sampler, self.channels_last)
 
     @staticmethod
     def corr(fmap1, fmap2, precision: Optional[str] = None):
@@ -425,9 +467,13 @@ class AlternateCorrBlock:
     either: ``alt_cuda_corr`` is forward-only in every shipped config)."""
 
     def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4, precision: Optional[str] = None,
-                 chunk: Optional[int] = None, max_pyramid_bytes: int = 512 << 20):
+                 chunk: Optional[int] = None, max_pyramid_bytes: int = 512 << 20, sampler: Optional[str] = None,
+                 channels_last: bool = False):
         self.num_levels = num_levels
         self.radius = radius
+        self.sampler = sampler or _default_sampler
+        self._sampler = _sampler_code(sampler)
+        self.channels_last = bool(channels_last)
         f1, f2 = _prep(fmap1, "fmap1").detach(), _prep(fmap2, "fmap2").detach()
         if f1.shape != f2.shape:
             raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
@@ -447,9 +493,9 @@ class AlternateCorrBlock:
         L = _lib.lib()
         self._ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, self._code)
         self._ws = torch.empty(max(self._ws_bytes, 1), device=f1.device, dtype=torch.uint8)
-        _lib.check(L.ffcorr_stage_operands_f32(f1.data_ptr(), f2.data_ptr(), num_levels, b, d, h, w, self._code,
-                                               self._ws.data_ptr(), self._ws_bytes, _lib.current_stream()),
-                   "ffcorr_stage_operands_f32")
+        with _lib.on_device(f1, f2) as stream:
+            _lib.check(L.ffcorr_stage_operands_f32(f1.data_ptr(), f2.data_ptr(), num_levels, b, d, h, w, self._code,
+                                                   self._ws.data_ptr(), self._ws_bytes, stream), "ffcorr_stage_operands_f32")
         self._levels = [torch.empty((b * self.chunk, _tiled_elems(h, w, i)), device=f1.device, dtype=torch.float32)
                         for i in range(num_levels)]
         self._ptrs = _lib.ptr_array(self._levels)
@@ -460,16 +506,16 @@ class AlternateCorrBlock:
         if tuple(coords.shape) != (b, 2, h, w):
             raise ValueError(f"coords {tuple(coords.shape)} does not match B,h,w={(b, h, w)}")
         coords = coords.detach().float().contiguous()
-        k = 2 * self.radius + 1
-        out = torch.empty((b, self.num_levels * k * k, h, w), device=coords.device, dtype=torch.float32)
+        store, out = _alloc_lookup_out(coords, self.num_levels, self.radius, self.channels_last)
         L = _lib.lib()
-        stream = _lib.current_stream()
         n = h * w
-        for q0 in range(0, n, self.chunk):
-            nq = min(self.chunk, n - q0)            # q0 stays a multiple of 32
-            _lib.check(L.ffcorr_build_tiled_chunk_f32(self._ptrs, self.num_levels, b, d, h, w, q0, nq, self._code,
-                                                      self._ws.data_ptr(), self._ws_bytes, stream),
-                       "ffcorr_build_tiled_chunk_f32")
-            _lib.check(L.ffcorr_lookup_tiled_chunk_f32(self._ptrs, self.num_levels, coords.data_ptr(), out.data_ptr(),
-                                                       b, h, w, q0, nq, self.radius, stream), "ffcorr_lookup_tiled_chunk_f32")
+        with _lib.on_device(coords, self._ws) as stream:
+            for q0 in range(0, n, self.chunk):
+                nq = min(self.chunk, n - q0)            # q0 stays a multiple of 32
+                _lib.check(L.ffcorr_build_tiled_chunk_f32(self._ptrs, self.num_levels, b, d, h, w, q0, nq, self._code,
+                                                          self._ws.data_ptr(), self._ws_bytes, stream),
+                           "ffcorr_build_tiled_chunk_f32")
+                _lib.check(L.ffcorr_lookup_tiled_chunk_f32(self._ptrs, self.num_levels, coords.data_ptr(), store.data_ptr(),
+                                                           b, h, w, q0, nq, self.radius, self._sampler, int(self.channels_last),
+                                                           stream), "ffcorr_lookup_tiled_chunk_f32")
         return out

@@ -4,7 +4,7 @@
 ``[B, 81, H, W]`` (mean over channels, zero outside the image; channel = (dy+4)*9 + (dx+4)),
 differentiable w.r.t. both inputs like the reference's ``_FunctionCorrelation``
 (``correlation.py:276-380``).  CUDA tensors only: the reference raises ``NotImplementedError``
-on CPU (``correlation.py:320-321``) and so does this.  Kernels run on torch's CURRENT stream
+on CPU (``correlation.py:320-321``) and so does this.  Kernels run on the tensors' device, on torch's CURRENT stream of it
 (the reference launches on CuPy's stream, a latent hazard -- SURVEY.md Appendix B.8).
 """
 from __future__ import annotations
@@ -19,8 +19,9 @@ __all__ = ["FunctionCorrelation", "ModuleCorrelation", "correlation_leaky"]
 def _launch_fwd(one: torch.Tensor, two: torch.Tensor, leaky: float) -> torch.Tensor:
     b, c, h, w = one.shape
     out = torch.empty((b, 81, h, w), device=one.device, dtype=torch.float32)
-    _lib.check(_lib.lib().ffcorr_pwc81_f32(one.data_ptr(), two.data_ptr(), out.data_ptr(), b, c, h, w, leaky,
-                                           _lib.current_stream()), "ffcorr_pwc81_f32")
+    with _lib.on_device(one, two) as stream:
+        _lib.check(_lib.lib().ffcorr_pwc81_f32(one.data_ptr(), two.data_ptr(), out.data_ptr(), b, c, h, w, leaky, stream),
+                   "ffcorr_pwc81_f32")
     return out
 
 
@@ -46,10 +47,11 @@ class _FunctionCorrelation(torch.autograd.Function):
         g = grad_output.contiguous().float()
         g1 = torch.empty_like(one) if ctx.needs_input_grad[0] else None
         g2 = torch.empty_like(two) if ctx.needs_input_grad[1] else None
-        _lib.check(_lib.lib().ffcorr_pwc81_bwd_f32(one.data_ptr(), two.data_ptr(), g.data_ptr(),
-                                                   g1.data_ptr() if g1 is not None else None,
-                                                   g2.data_ptr() if g2 is not None else None, b, c, h, w,
-                                                   _lib.current_stream()), "ffcorr_pwc81_bwd_f32")
+        with _lib.on_device(one, two, g) as stream:
+            _lib.check(_lib.lib().ffcorr_pwc81_bwd_f32(one.data_ptr(), two.data_ptr(), g.data_ptr(),
+                                                       g1.data_ptr() if g1 is not None else None,
+                                                       g2.data_ptr() if g2 is not None else None, b, c, h, w, stream),
+                       "ffcorr_pwc81_bwd_f32")
         return g1, g2
 
 

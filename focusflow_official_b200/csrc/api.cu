@@ -31,17 +31,19 @@ int sm_count() {
     return cached_sms;
 }
 
+static PFN_cuTensorMapEncodeTiled resolve_encode_fn() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    return nullptr;
+}
+
 static PFN_cuTensorMapEncodeTiled get_encode_fn() {
-    static PFN_cuTensorMapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-    }
+    // C++11 magic static: initialised exactly once, concurrent first callers (PyTorch's autograd worker threads reach
+    // this from the backward) block until it is
+    static const PFN_cuTensorMapEncodeTiled fn = resolve_encode_fn();
     return fn;
 }
 

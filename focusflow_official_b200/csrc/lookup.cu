@@ -36,9 +36,6 @@ namespace {
 constexpr int kWarpsPerBlock = 2;
 constexpr int kTile = 32;  // queries per warp
 
-// FFCORR_SAMPLER_ATEN_CPU (0, default) or FFCORR_SAMPLER_ATEN_CUDA (1): see source_index()
-int g_sampler_semantics = FFCORR_SAMPLER_ATEN_CPU;
-
 struct LookupParams {
     const float* lvl[FFCORR_MAX_LEVELS];
     int lh[FFCORR_MAX_LEVELS];
@@ -48,13 +45,14 @@ struct LookupParams {
     int B, N, num_levels;
     int tiles_per_batch;
     int blocks_per_batch;
+    int64_t cstride;      // floats between consecutive output channels of one query: N (NCHW) or 1 (NHWC)
+    int64_t qstride;      // floats between consecutive queries of one channel:       1 (NCHW) or L*K*K (NHWC)
 };
 
 // utils.py:61-62 then GridSampler.cuh:26, every op rounded to fp32 like the reference.  The one place where the
 // reference's CPU and GPU runs differ is the division by (size - 1) in utils.py:61-62: ATen's CPU kernel divides,
 // its CUDA kernel multiplies by the fp32 reciprocal of the scalar (<= 1 ulp of the normalised coordinate, ~1e-5 px at
-// w = 156).  CUDA_SEM selects the latter (ffcorr_set_sampler_semantics); the default is the CPU form the golden
-// vectors were generated with.
+// w = 156).  CUDA_SEM selects the latter (the `sampler` argument of every lookup entry point).
 template <bool CUDA_SEM>
 __device__ __forceinline__ float source_index(float x, float size_m1, float rcp_size_m1) {
     const float t = __fmul_rn(2.0f, x);
@@ -190,7 +188,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
 
     const float* sq = swin + lane * WIN;
     const int CT = p.num_levels * K * K;
-    float* __restrict__ op = p.out + ((int64_t)b * CT + (int64_t)level * K * K) * N + n;
+    // NCHW: channel c of query n at ((b*CT + c)*N + n); NHWC: at ((b*N + n)*CT + c)
+    float* __restrict__ op = p.out + (int64_t)b * CT * N + (int64_t)level * K * K * p.cstride + (int64_t)n * p.qstride;
+    const int64_t cs = p.cstride;
 
     if (!__any_sync(0xffffffffu, deviated)) {
         // Fast path (no tap of any query in the warp changed its floor through the round trip):
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
 #pragma unroll
                 for (int a = 0; a < K; ++a) {
                     const float o = __fmaf_rn(wy1[bb], tcur[a], __fmul_rn(wy0[bb], tprev[a]));
-                    if (valid) op[(int64_t)(a * K + bb) * N] = o;
+                    if (valid) op[(int64_t)(a * K + bb) * cs] = o;
                 }
             }
 #pragma unroll
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_kernel(const Looku
                 o = __fmaf_rn(v01, ne, o);
                 o = __fmaf_rn(v10, sw, o);
                 o = __fmaf_rn(v11, se, o);
-                if (valid) op[(int64_t)(a * K + bb) * N] = o;
+                if (valid) op[(int64_t)(a * K + bb) * cs] = o;
             }
         }
     }
@@ -518,13 +518,286 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// NHWC ("channels last") row-streaming tiled lookup: out[b, n, lvl*K*K + a*K + bb] -- the layout the consumer of
+// the lookup, the 1x1 convolution convc1 (update.py:82-83,90), runs in on tensor cores; the NCHW kernel above forces
+// a transposing copy of the whole result (76 MB at config 2) per refinement iteration on the host side.
+//
+// Unit of work = 8 consecutive queries x ALL (<= 4) levels per warp: window wi = lane = level * 8 + query.  The
+// warp's 8 x L*K*K results are one CONTIGUOUS piece of the output (10 368 bytes for r = 4, L = 4): every lane drops
+// its samples into a shared-memory staging block (conflict-free: (4 q + 17 lvl) mod 32 are 32 distinct banks) and one
+// elected lane hands the block to the TMA engine (cp.async.bulk shared -> global), so the SM spends no issue slots on
+// the 76 MB of stores.  Mixing the levels in a warp also makes every warp cost the same (the level-major kernel has
+// cheap level-3 blocks in its tail).  Gather role: slot j of lane (query = lane >> 2, tile column = lane & 3) serves
+// level j, so all level constants of a slot are warp-uniform.  Evaluate role: the row buffer is read with four
+// 16-byte loads per lane (8 consecutive lanes hit 8 distinct 16-byte bank groups with the 80-byte pitch, whatever
+// the flow field) and shifted by x_lo & 3 in registers.
+// ---------------------------------------------------------------------------------
+#ifndef FFCORR_NHWC_WARPS
+#define FFCORR_NHWC_WARPS 2
+#endif
+constexpr int kNhwcWarps = FFCORR_NHWC_WARPS;
+constexpr int kNhwcQ = 8;          // queries per warp
+
+__host__ __device__ constexpr int nhwc_warp_floats(int K, int CT) { return kStreamStages * kTile * kRowPitch + K * kTile + kNhwcQ * CT; }
+
+template <int R, bool CUDA_SEM>
+__global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(const LookupTiledParams p) {
+    constexpr int K = 2 * R + 1;
+    constexpr int W2 = K + 2;
+    constexpr int KK = K * K;
+    constexpr int S = kStreamStages;
+    constexpr int ROWBUF = kTile * kRowPitch;
+    static_assert(W2 + 3 <= 16, "window + sub-tile shift must fit in the 16 columns of the tile block");
+
+    extern __shared__ __align__(16) float smem_nhwc[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int CT = p.num_levels * KK;
+    float* ring = smem_nhwc + (size_t)warp * nhwc_warp_floats(K, CT);
+    float* siy = ring + S * ROWBUF;
+    float* stage = siy + K * kTile;                      // [8 queries][CT]
+
+    const int b = blockIdx.x / p.blocks_per_batch;
+    const int unit = (blockIdx.x - b * p.blocks_per_batch) * kNhwcWarps + warp;
+    if (unit >= p.tiles_per_batch) return;               // warp-uniform; no block-level sync below
+
+    const int N = p.N;
+    const int n0 = unit * kNhwcQ;
+    const int lvl_of_lane = lane >> 3;
+    const bool lvl_on = lvl_of_lane < p.num_levels;
+    const int level = lvl_on ? lvl_of_lane : 0;
+    const int q = lane & 7;
+    const int n = min(n0 + q, N - 1);                    // tail lanes recompute the last query (never stored)
+    const int lh = p.lh[level], lw = p.lw[level];
+    const int th = p.th[level], tw = p.tw[level];
+    const int twr = (lw + 3) >> 2;
+    const float inv_scale = __int_as_float((127 - level) << 23);
+
+    // ---------------- phase A (lane = window) ----------------
+    const float* cptr = p.coords + (size_t)b * 2 * p.coords_stride + n;
+    const float cx = __ldg(cptr) * inv_scale;
+    const float cy = __ldg(cptr + p.coords_stride) * inv_scale;
+    const float sx = (float)(lw - 1), sy = (float)(lh - 1);
+    const float rsx = __frcp_rn(sx), rsy = __frcp_rn(sy);
+    const float ixf = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(-R)), sx, rsx);
+    const float ixl = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(R)), sx, rsx);
+    const float iyf = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(-R)), sy, rsy);
+    const float iyl = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(R)), sy, rsy);
+    const bool wild = !lvl_on || !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
+                      !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
+    int x_lo = 0, y_lo = 0;
+    int my_base = 0, my_pack = 0;
+    if (!wild) {
+        x_lo = (int)floorf(ixf);
+        y_lo = (int)floorf(iyf);
+        const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
+        my_base = (ty0 * tw + tx0) * 16;
+        int tmask = 0;
+#pragma unroll
+        for (int tyi = 0; tyi < 4; ++tyi)
+#pragma unroll
+            for (int txi = 0; txi < 4; ++txi)
+                if ((unsigned)(ty0 + tyi) < (unsigned)th && (unsigned)(tx0 + txi) < (unsigned)twr) tmask |= 1 << (tyi * 4 + txi);
+        my_pack = (x_lo & 3) | ((y_lo & 3) << 2) | (tmask << 4);
+    }
+
+    float wx0[K], wx1[K];
+    unsigned px = 0, py = 0;
+    bool deviated = false;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const float ix = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(a - R)), sx, rsx);
+        const float fx = floorf(ix);
+        const float iy = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(a - R)), sy, rsy);
+        const float fy = floorf(iy);
+        siy[a * kTile + lane] = iy;
+        wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
+        wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+        const int dxa = wild ? 0 : min(max((int)fx - x_lo, 0), W2 - 2) - a;
+        const int dya = wild ? 0 : min(max((int)fy - y_lo, 0), W2 - 2) - a;
+        px |= (unsigned)((dxa + 1) & 3) << (2 * a);
+        py |= (unsigned)((dya + 1) & 3) << (2 * a);
+        deviated |= (dxa != 0) | (dya != 0);
+    }
+    const bool slow = __any_sync(0xffffffffu, deviated);
+    auto ytap = [&](int bb, float& w0, float& w1) {
+        const float iy = siy[bb * kTile + lane];
+        const float fy = floorf(iy);
+        w1 = wild ? 0.f : __fsub_rn(iy, fy);
+        w0 = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+    };
+
+    // ---------------- gather slots: slot j = level j, lane = (query lane >> 2, tile column lane & 3) ----------------
+    const int txi = lane & 3;
+    const int qj = lane >> 2;
+    const int last_q = N - 1 - n0;
+    const float* tbase[4];
+    int goff[4], gnext[4];
+    unsigned gmask[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int lj = j < p.num_levels ? j : 0;
+        const int map_elems = p.th[lj] * p.tw[lj] * 16;
+        tbase[j] = p.lvl[lj] + ((int64_t)b * N + n0) * (int64_t)map_elems;
+        const int base = __shfl_sync(0xffffffffu, my_base, j * 8 + qj);
+        const int pk = __shfl_sync(0xffffffffu, my_pack, j * 8 + qj);       // 0 for a wild / absent window
+        const int gy = (pk >> 2) & 3;
+        goff[j] = min(qj, last_q) * map_elems + base + txi * 16 + gy * 4;
+        const unsigned e = (unsigned)pk >> (4 + txi);
+        const unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
+                             (((e >> 12) & 1u) * 0xF000u);
+        gmask[j] = ((okT >> gy) & 0xFFFFu) | ((0x8888u >> gy) << 16);
+        gnext[j] = p.tw[lj] * 16 - 12;
+    }
+    const unsigned gdst = (unsigned)(qj * kRowPitch + 4 * txi) * 4u;          // + j * 8 * kRowPitch * 4 per slot
+    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
+    int rows_issued = 0;
+    uint32_t issue_saddr = ring_saddr;
+    auto issue_row = [&](bool active) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned m = gmask[j] >> rows_issued;
+                const bool ok = m & 1u;
+                const float* src = tbase[j] + (ok ? goff[j] : 0);
+                cp_async16_zfill(issue_saddr + gdst + (unsigned)(j * 8 * kRowPitch * 4), src, ok ? 16u : 0u);
+                goff[j] += (m & 0x10000u) ? gnext[j] : 4;
+            }
+            ++rows_issued;
+            issue_saddr += ROWBUF * 4;
+            if (issue_saddr == ring_saddr + S * ROWBUF * 4) issue_saddr = ring_saddr;
+        }
+        cp_async_commit();
+    };
+
+    float* sout = stage + q * CT + level * KK;            // this window's K*K samples
+    const int shift = x_lo & 3;
+    const float* my_row = ring + lane * kRowPitch;
+
+#pragma unroll
+    for (int r = 0; r < S - 1; ++r) issue_row(true);
+
+    if (!slow) {
+        float tprev[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) tprev[a] = 0.f;
+        const float* sq = my_row;
+#pragma unroll 1
+        for (int r = 0; r <= K; ++r) {
+            cp_async_wait<S - 2>();
+            __syncwarp();
+            issue_row(r + S - 1 <= K);
+            float f[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float4 t4 = reinterpret_cast<const float4*>(sq)[v];
+                f[4 * v] = t4.x; f[4 * v + 1] = t4.y; f[4 * v + 2] = t4.z; f[4 * v + 3] = t4.w;
+            }
+            // barrel shift by x_lo & 3 so that f[c] is window column c
+#pragma unroll
+            for (int c = 0; c < 15; ++c) f[c] = (shift & 1) ? f[c + 1] : f[c];
+#pragma unroll
+            for (int c = 0; c < 13; ++c) f[c] = (shift & 2) ? f[c + 2] : f[c];
+            float tcur[K];
+#pragma unroll
+            for (int a = 0; a < K; ++a) tcur[a] = __fmaf_rn(wx1[a], f[a + 1], __fmul_rn(wx0[a], f[a]));
+            if (r > 0) {
+                float w0, w1;
+                ytap(r - 1, w0, w1);
+                if (lvl_on) {
+#pragma unroll
+                    for (int a = 0; a < K; ++a) sout[a * K + (r - 1)] = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
+            sq += ROWBUF;
+            if (sq == my_row + S * ROWBUF) sq = my_row;
+        }
+    } else {
+        const float* cur = my_row + shift;
+        const float* prev = cur;
+#pragma unroll 1
+        for (int r = 0; r < W2; ++r) {
+            cp_async_wait<S - 2>();
+            __syncwarp();
+#pragma unroll 1
+            for (int bb = 0; bb < K; ++bb) {
+                const int ryb = bb + (int)((py >> (2 * bb)) & 3u) - 1;
+                if (ryb + 1 == r) {
+                    float wy0b, wy1b;
+                    ytap(bb, wy0b, wy1b);
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        const int rxa = a + (int)((px >> (2 * a)) & 3u) - 1;
+                        const float v00 = prev[rxa], v01 = prev[rxa + 1], v10 = cur[rxa], v11 = cur[rxa + 1];
+                        const float nw = __fmul_rn(wx0[a], wy0b);
+                        const float ne = __fmul_rn(wx1[a], wy0b);
+                        const float sw = __fmul_rn(wx0[a], wy1b);
+                        const float se = __fmul_rn(wx1[a], wy1b);
+                        float o = __fmul_rn(v00, nw);
+                        o = __fmaf_rn(v01, ne, o);
+                        o = __fmaf_rn(v10, sw, o);
+                        o = __fmaf_rn(v11, se, o);
+                        if (lvl_on) sout[a * K + bb] = o;
+                    }
+                }
+            }
+            __syncwarp();
+            issue_row(r + S - 1 < W2);
+            prev = cur;
+            cur += ROWBUF;
+            if (cur == my_row + shift + S * ROWBUF) cur = my_row + shift;
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---------------- flush: the warp's 8 x CT block is contiguous in the NHWC output ----------------
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+        const int nq = min(kNhwcQ, N - n0);
+        float* gdst_ptr = p.out + ((int64_t)b * p.out_stride + n0) * CT;
+        const uint32_t bytes = (uint32_t)(nq * CT) * 4u;               // CT*4 is a multiple of 16 only for even CT/4 ...
+        if ((bytes & 15u) == 0 && (((uintptr_t)gdst_ptr) & 15u) == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst_ptr),
+                         "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the read
+        } else {
+            for (int i = 0; i < nq * CT; ++i) gdst_ptr[i] = stage[i];        // odd tails only (never at r = 4, L = 4)
+        }
+    }
+}
+
 template <int R>
-int launch_lookup_tiled_stream(const LookupTiledParams& p0, cudaStream_t stream) {
+int launch_lookup_tiled_nhwc(const LookupTiledParams& p0, int sampler, cudaStream_t stream) {
+    constexpr int K = 2 * R + 1;
+    LookupTiledParams p = p0;
+    FFCORR_REQUIRE(p.num_levels <= 4, FFCORR_EINVAL, "lookup_tiled (channels last): at most 4 levels, got %d", p.num_levels);
+    p.tiles_per_batch = ceil_div(p.N, kNhwcQ);
+    p.blocks_per_batch = ceil_div(p.tiles_per_batch, kNhwcWarps);
+    const int64_t blocks = (int64_t)p.B * p.blocks_per_batch;
+    FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
+    const size_t smem = (size_t)kNhwcWarps * nhwc_warp_floats(K, p.num_levels * K * K) * sizeof(float);
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (sampler == FFCORR_SAMPLER_ATEN_CUDA)
+        lookup_tiled_nhwc_kernel<R, true><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
+    else
+        lookup_tiled_nhwc_kernel<R, false><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
+    return check_launch("lookup_tiled_nhwc_kernel");
+}
+
+template <int R>
+int launch_lookup_tiled_stream(const LookupTiledParams& p0, int sampler, cudaStream_t stream) {
     LookupTiledParams p = p0;
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kStreamWarps);
     const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
-    if (g_sampler_semantics == FFCORR_SAMPLER_ATEN_CUDA)
+    if (sampler == FFCORR_SAMPLER_ATEN_CUDA)
         lookup_tiled_stream_kernel<R, true><<<(unsigned)blocks, kStreamWarps * 32, 0, stream>>>(p);
     else
         lookup_tiled_stream_kernel<R, false><<<(unsigned)blocks, kStreamWarps * 32, 0, stream>>>(p);
@@ -701,7 +974,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) lookup_bwd_kernel(const L
 }
 
 template <int R>
-int launch_lookup_bwd(const LookupBwdParams& p, cudaStream_t stream) {
+int launch_lookup_bwd(const LookupBwdParams& p, int sampler, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
     constexpr int WIN = (K + 2) * (K + 2);
     const size_t smem = (size_t)kWarpsPerBlock * kTile * WIN * sizeof(float);
@@ -711,7 +984,7 @@ int launch_lookup_bwd(const LookupBwdParams& p, cudaStream_t stream) {
     const int blocks_per_batch = ceil_div(tiles_per_batch, kWarpsPerBlock);
     const int64_t blocks = (int64_t)p.num_levels * p.B * blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_bwd: grid too large");
-    if (g_sampler_semantics == FFCORR_SAMPLER_ATEN_CUDA)
+    if (sampler == FFCORR_SAMPLER_ATEN_CUDA)
         lookup_bwd_kernel<R, true><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p, tiles_per_batch, blocks_per_batch);
     else
         lookup_bwd_kernel<R, false><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p, tiles_per_batch, blocks_per_batch);
@@ -719,7 +992,7 @@ int launch_lookup_bwd(const LookupBwdParams& p, cudaStream_t stream) {
 }
 
 template <int R, int QU>
-int launch_lookup(const LookupParams& p, cudaStream_t stream) {
+int launch_lookup(const LookupParams& p, int sampler, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
     constexpr int WIN = (K + 2) * (K + 2);
     const size_t smem = (size_t)kWarpsPerBlock * kTile * WIN * sizeof(float);
@@ -733,7 +1006,7 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
     }
     const int64_t blocks = (int64_t)p.num_levels * p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup: grid too large (%lld blocks)", (long long)blocks);
-    if (g_sampler_semantics == FFCORR_SAMPLER_ATEN_CUDA)
+    if (sampler == FFCORR_SAMPLER_ATEN_CUDA)
         lookup_kernel<R, QU, true><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
     else
         lookup_kernel<R, QU, false><<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
@@ -745,23 +1018,22 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
 
 using namespace ffcorr;
 
-extern "C" int ffcorr_set_sampler_semantics(int semantics) {
-    FFCORR_REQUIRE(semantics == FFCORR_SAMPLER_ATEN_CPU || semantics == FFCORR_SAMPLER_ATEN_CUDA, FFCORR_EINVAL,
-                   "set_sampler_semantics: %d is neither FFCORR_SAMPLER_ATEN_CPU nor FFCORR_SAMPLER_ATEN_CUDA", semantics);
-    g_sampler_semantics = semantics;
+static int check_sampler(int sampler, const char* who) {
+    FFCORR_REQUIRE(sampler == FFCORR_SAMPLER_ATEN_CPU || sampler == FFCORR_SAMPLER_ATEN_CUDA, FFCORR_EINVAL,
+                   "%s: sampler=%d is neither FFCORR_SAMPLER_ATEN_CPU nor FFCORR_SAMPLER_ATEN_CUDA", who, sampler);
     return FFCORR_OK;
 }
 
-extern "C" int ffcorr_get_sampler_semantics(void) { return g_sampler_semantics; }
-
 extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
-                                 int B, int h, int w, int radius, void* stream) {
+                                 int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream) {
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup: B=%d", B);
     if (B == 0) return FFCORR_OK;  // empty batch: pointers may legitimately be null
     FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "lookup: null pointer");
     FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup: radius=%d outside [1,4]", radius);
+    if (int rc = check_sampler(sampler, "lookup")) return rc;
     if (int rc = check_levels(num_levels, h, w, "lookup")) return rc;
-    if (B == 0) return FFCORR_OK;
+    // the kernel keeps a 32-query tile's element offsets in 32 bits: 31 * h*w + window offset < 2^31
+    FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "lookup: h*w = %lld must be below 2^24", (long long)h * w);
     LookupParams p{};
     for (int i = 0; i < num_levels; ++i) {
         FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "lookup: lvl[%d] is null", i);
@@ -776,23 +1048,26 @@ extern "C" int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const 
     p.num_levels = num_levels;
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
+    const int CT = num_levels * (2 * radius + 1) * (2 * radius + 1);
+    p.cstride = out_channels_last ? 1 : p.N;
+    p.qstride = out_channels_last ? CT : 1;
     cudaStream_t s = (cudaStream_t)stream;
     switch (radius) {
-        case 1: return launch_lookup<1, 4>(p, s);
-        case 2: return launch_lookup<2, 4>(p, s);
-        case 3: return launch_lookup<3, 4>(p, s);
-        default: return launch_lookup<4, 8>(p, s);
+        case 1: return launch_lookup<1, 4>(p, sampler, s);
+        case 2: return launch_lookup<2, 4>(p, sampler, s);
+        case 3: return launch_lookup<3, 4>(p, sampler, s);
+        default: return launch_lookup<4, 8>(p, sampler, s);
     }
 }
 
 extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, const float* coords,
-                                     const float* grad_out, int B, int h, int w, int radius, void* stream) {
+                                     const float* grad_out, int B, int h, int w, int radius, int sampler, void* stream) {
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "lookup_bwd: B=%d", B);
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(grad_lvl && coords && grad_out, FFCORR_EINVAL, "lookup_bwd: null pointer");
     FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup_bwd: radius=%d outside [1,4]", radius);
+    if (int rc = check_sampler(sampler, "lookup_bwd")) return rc;
     if (int rc = check_levels(num_levels, h, w, "lookup_bwd")) return rc;
-    if (B == 0) return FFCORR_OK;
     LookupBwdParams p{};
     for (int i = 0; i < num_levels; ++i) {
         FFCORR_REQUIRE(grad_lvl[i] != nullptr, FFCORR_EINVAL, "lookup_bwd: grad_lvl[%d] is null", i);
@@ -809,22 +1084,25 @@ extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, con
     FFCORR_REQUIRE((int64_t)(h) * w < (1ll << 24), FFCORR_EINVAL, "lookup_bwd: h*w too large");
     cudaStream_t s = (cudaStream_t)stream;
     switch (radius) {
-        case 1: return launch_lookup_bwd<1>(p, s);
-        case 2: return launch_lookup_bwd<2>(p, s);
-        case 3: return launch_lookup_bwd<3>(p, s);
-        default: return launch_lookup_bwd<4>(p, s);
+        case 1: return launch_lookup_bwd<1>(p, sampler, s);
+        case 2: return launch_lookup_bwd<2>(p, sampler, s);
+        case 3: return launch_lookup_bwd<3>(p, sampler, s);
+        default: return launch_lookup_bwd<4>(p, sampler, s);
     }
 }
 
 
 static int lookup_tiled_impl(const float* const* lvl, int num_levels, const float* coords, float* out, int B, int h, int w,
-                             int nq, int64_t coords_stride, int64_t out_stride, int radius, void* stream, const char* who) {
+                             int nq, int64_t coords_stride, int64_t out_stride, int radius, int sampler, int out_channels_last,
+                             void* stream, const char* who) {
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "%s: B=%d", who, B);
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "%s: null pointer", who);
     FFCORR_REQUIRE(radius >= 1 && radius <= 4, FFCORR_EINVAL, "%s: radius=%d outside [1,4]", who, radius);
+    if (int rc = check_sampler(sampler, who)) return rc;
     if (int rc = check_levels(num_levels, h, w, who)) return rc;
     FFCORR_REQUIRE(nq >= 1 && nq <= h * w, FFCORR_EINVAL, "%s: %d queries for a %dx%d map", who, nq, h, w);
+    FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "%s: h*w = %lld must be below 2^24", who, (long long)h * w);
     LookupTiledParams p{};
     for (int i = 0; i < num_levels; ++i) {
         FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "%s: lvl[%d] is null", who, i);
@@ -845,27 +1123,40 @@ static int lookup_tiled_impl(const float* const* lvl, int num_levels, const floa
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
+    if (out_channels_last) {
+        switch (radius) {
+            case 1: return launch_lookup_tiled_nhwc<1>(p, sampler, s);
+            case 2: return launch_lookup_tiled_nhwc<2>(p, sampler, s);
+            case 3: return launch_lookup_tiled_nhwc<3>(p, sampler, s);
+            default: return launch_lookup_tiled_nhwc<4>(p, sampler, s);
+        }
+    }
     switch (radius) {
-        case 1: return launch_lookup_tiled_stream<1>(p, s);
-        case 2: return launch_lookup_tiled_stream<2>(p, s);
-        case 3: return launch_lookup_tiled_stream<3>(p, s);
-        default: return launch_lookup_tiled_stream<4>(p, s);
+        case 1: return launch_lookup_tiled_stream<1>(p, sampler, s);
+        case 2: return launch_lookup_tiled_stream<2>(p, sampler, s);
+        case 3: return launch_lookup_tiled_stream<3>(p, sampler, s);
+        default: return launch_lookup_tiled_stream<4>(p, sampler, s);
     }
 }
 
 extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
-                                       int B, int h, int w, int radius, void* stream) {
-    return lookup_tiled_impl(lvl, num_levels, coords, out, B, h, w, h * w, (int64_t)h * w, (int64_t)h * w, radius, stream,
-                             "lookup_tiled");
+                                       int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream) {
+    return lookup_tiled_impl(lvl, num_levels, coords, out, B, h, w, h * w, (int64_t)h * w, (int64_t)h * w, radius, sampler,
+                             out_channels_last, stream, "lookup_tiled");
 }
 
 extern "C" int ffcorr_lookup_tiled_chunk_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
-                                             int B, int h, int w, int q0, int nq, int radius, void* stream) {
+                                             int B, int h, int w, int q0, int nq, int radius, int sampler, int out_channels_last,
+                                             void* stream) {
     FFCORR_REQUIRE(q0 >= 0 && nq >= 1 && (int64_t)q0 + nq <= (int64_t)h * w, FFCORR_EINVAL,
                    "lookup_tiled_chunk: query range [%d, %d) outside the %dx%d map", q0, q0 + nq, h, w);
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(coords && out, FFCORR_EINVAL, "lookup_tiled_chunk: null pointer");
-    // coords / out are the FULL [B, 2, h*w] / [B, L*K*K, h*w] tensors; the chunk reads and writes its slice in place
-    return lookup_tiled_impl(lvl, num_levels, coords + q0, out + q0, B, h, w, nq, (int64_t)h * w, (int64_t)h * w, radius, stream,
-                             "lookup_tiled_chunk");
+    FFCORR_REQUIRE(num_levels >= 1 && radius >= 1 && radius <= 4, FFCORR_EINVAL, "lookup_tiled_chunk: bad levels / radius");
+    // coords / out are the FULL [B, 2, h*w] / [B, L*K*K, h*w] (or [B, h*w, L*K*K]) tensors; the chunk reads and writes
+    // its slice in place
+    const int64_t CT = (int64_t)num_levels * (2 * radius + 1) * (2 * radius + 1);
+    float* out_chunk = out_channels_last ? out + (int64_t)q0 * CT : out + q0;
+    return lookup_tiled_impl(lvl, num_levels, coords + q0, out_chunk, B, h, w, nq, (int64_t)h * w, (int64_t)h * w, radius,
+                             sampler, out_channels_last, stream, "lookup_tiled_chunk");
 }

@@ -36,9 +36,9 @@ def cost_volume(fmap1: torch.Tensor, fmap2: torch.Tensor, heads: int = 1, precis
     out = torch.empty((b * heads, n, n), device=fmap1.device, dtype=torch.float32)
     ws_bytes = L.ffcorr_volume_workspace_bytes(b * heads, d, h, w, code)
     ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
-    _lib.check(L.ffcorr_volume_scaled_f32(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), b * heads, d, h, w, code, 1.0,
-                                          ws.data_ptr() if ws_bytes else None, ws_bytes, _lib.current_stream()),
-               "ffcorr_volume_scaled_f32")
+    with _lib.on_device(fmap1, fmap2) as stream:
+        _lib.check(L.ffcorr_volume_scaled_f32(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), b * heads, d, h, w, code, 1.0,
+                                              ws.data_ptr() if ws_bytes else None, ws_bytes, stream), "ffcorr_volume_scaled_f32")
     return out.view(b, heads, h, w, h, w)
 
 

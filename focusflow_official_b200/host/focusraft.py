@@ -254,6 +254,7 @@ class RAFTBody(nn.Module):
         self.update_block = UpdateBlock(self.corr_levels, self.corr_radius, self.hidden_dim)
         self.corr_block: Callable = B200CorrBlock
         self.corr_precision: Optional[str] = None
+        self.corr_sampler: Optional[str] = None      # None = the package default ("cuda": the reference's GPU run)
         # raft.py:63,195-196 `alternate_corr` (config key ALT_CORR): the memory-bounded block that recomputes the
         # pyramid per lookup; inference only, like the reference's alt_cuda_corr
         self.alternate_corr = False
@@ -267,12 +268,13 @@ class RAFTBody(nn.Module):
                 m.eval()
 
     def _make_corr(self, fmap1, fmap2):
+        # the lookup writes NHWC directly when the update block runs channels_last (its consumer convc1, update.py:90)
+        kw = dict(num_levels=self.corr_levels, radius=self.corr_radius, precision=self.corr_precision,
+                  sampler=self.corr_sampler, channels_last=self.update_channels_last)
         if self.alternate_corr and self.corr_block is B200CorrBlock and not torch.is_grad_enabled():
-            return B200AlternateCorrBlock(fmap1, fmap2, num_levels=self.corr_levels, radius=self.corr_radius,
-                                          precision=self.corr_precision)
+            return B200AlternateCorrBlock(fmap1, fmap2, **kw)
         if self.corr_block is B200CorrBlock:
-            return B200CorrBlock(fmap1, fmap2, num_levels=self.corr_levels, radius=self.corr_radius,
-                                 precision=self.corr_precision)
+            return B200CorrBlock(fmap1, fmap2, **kw)
         return self.corr_block(fmap1, fmap2, num_levels=self.corr_levels, radius=self.corr_radius)
 
     def forward(self, image1, image2, mask1, mask2, iters: int = 12, flow_init=None, test_mode: bool = False):
@@ -302,7 +304,7 @@ class RAFTBody(nn.Module):
             corr = corr_fn(coords1)
             flow = coords1 - coords0
             if cl:
-                corr = corr.contiguous(memory_format=torch.channels_last)
+                corr = corr.contiguous(memory_format=torch.channels_last)   # a no-op for the B200 block (already NHWC)
                 flow = flow.contiguous(memory_format=torch.channels_last)
             need_up = (not test_mode) or it == iters - 1
             net, up_mask, delta = self.update_block(net, inp, corr, flow, with_mask=need_up)

@@ -30,7 +30,8 @@
  *   - return value: 0 on success, a negative FFCORR_E* code for argument errors,
  *     a positive cudaError_t when the CUDA runtime reports one.  Nothing throws.
  *     ffcorr_last_error() returns a thread-local message for the last failure.
- *   - re-entrant: no global mutable state besides cached function attributes.
+ *   - re-entrant: no global mutable state besides cached function attributes (every behavioural switch --
+ *     operand precision, sampler semantics, output layout -- is an argument of the call it affects).
  */
 #ifndef FFCORR_H_
 #define FFCORR_H_
@@ -42,7 +43,7 @@
 extern "C" {
 #endif
 
-#define FFCORR_VERSION 100
+#define FFCORR_VERSION 200
 
 #define FFCORR_OK            0
 #define FFCORR_EINVAL      (-1)   /* bad shape / null pointer / unsupported argument   */
@@ -102,16 +103,14 @@ int ffcorr_volume_scaled_f32(const float* fmap1, const float* fmap2, float* lvl0
 int ffcorr_pyramid_f32(float* const* lvl, int num_levels, int64_t Q, int h, int w, void* stream);
 
 /*
- * Which of the reference's two runs the lookups reproduce bit-closely.  bilinear_sampler (utils/utils.py:61-62)
+ * `sampler`: which of the reference's two runs the lookups reproduce bit-closely.  bilinear_sampler (utils/utils.py:61-62)
  * normalises with x / (W-1): ATen's CPU kernel divides, its CUDA kernel multiplies by the fp32 reciprocal of the
  * scalar -- a <= 1-ulp difference of the normalised coordinate (~1e-5 px at w = 156, ~3e-5 of max|value| in the
- * output).  Default FFCORR_SAMPLER_ATEN_CPU: the form the golden vectors (reference run on CPU) were made with.
- * Process-wide; applies to ffcorr_lookup_f32, ffcorr_lookup_tiled*_f32 and ffcorr_lookup_bwd_f32.
+ * output).  FFCORR_SAMPLER_ATEN_CUDA is what a GPU user of the reference gets (and the Python default);
+ * FFCORR_SAMPLER_ATEN_CPU is the form the golden vectors (reference run on CPU) were made with.  Per call.
  */
 #define FFCORR_SAMPLER_ATEN_CPU   0
 #define FFCORR_SAMPLER_ATEN_CUDA  1
-int ffcorr_set_sampler_semantics(int semantics);
-int ffcorr_get_sampler_semantics(void);
 
 /*
  * Fused multi-level bilinear window lookup (one launch per refinement iteration).
@@ -119,11 +118,14 @@ int ffcorr_get_sampler_semantics(void);
  *   coords  : [B, 2, h, w]  channel 0 = x, channel 1 = y   (utils.py:74-77)
  *   out     : [B, num_levels*(2r+1)^2, h, w]; channel = lvl*(2r+1)^2 + a*(2r+1) + b samples
  *             (x/2^lvl + a - r, y/2^lvl + b - r)            (corr.py:37-43)
+ *             out_channels_last != 0: the same values stored [B, h, w, num_levels*(2r+1)^2] (NHWC) -- the layout the
+ *             consumer, the 1x1 convolution `convc1` (update.py:82-83,90), wants on tensor cores; every query's
+ *             channels are then one contiguous run.
  * Zero padding, align_corners=True and the normalise/un-normalise fp32 round trip of
- * bilinear_sampler + grid_sample are reproduced tap by tap.  radius in [1, 4].
+ * bilinear_sampler + grid_sample are reproduced tap by tap.  radius in [1, 4]; h*w < 2^24.
  */
 int ffcorr_lookup_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
-                      int B, int h, int w, int radius, void* stream);
+                      int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream);
 
 /*
  * Tiled ("T4") pyramid layout -- the inference fast path.  Every level is stored per query map as
@@ -153,7 +155,7 @@ int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, float* const*
                            int B, int D, int h, int w, int precision,
                            void* workspace, size_t workspace_bytes, void* stream);
 int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
-                            int B, int h, int w, int radius, void* stream);
+                            int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream);
 
 /*
  * Query-chunked build + lookup: AlternateCorrBlock semantics (corr.py:63-91) -- the same lookup values with
@@ -169,7 +171,8 @@ int ffcorr_stage_operands_f32(const float* fmap1, const float* fmap2, int num_le
 int ffcorr_build_tiled_chunk_f32(float* const* lvl, int num_levels, int B, int D, int h, int w, int q0, int nq,
                                  int precision, void* workspace, size_t workspace_bytes, void* stream);
 int ffcorr_lookup_tiled_chunk_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
-                                  int B, int h, int w, int q0, int nq, int radius, void* stream);
+                                  int B, int h, int w, int q0, int nq, int radius, int sampler, int out_channels_last,
+                                  void* stream);
 int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int h_level, int w_level, void* stream);
 int ffcorr_tile_f32(const float* src, float* tiled, int64_t Q, int h_level, int w_level, void* stream);
 
@@ -178,7 +181,7 @@ int ffcorr_tile_f32(const float* src, float* tiled, int64_t Q, int h_level, int 
  * contributions are accumulated with atomics (red.global.add.f32).
  */
 int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, const float* coords,
-                          const float* grad_out, int B, int h, int w, int radius, void* stream);
+                          const float* grad_out, int B, int h, int w, int radius, int sampler, void* stream);
 
 /*
  * Adjoint of the pyramid: grad_lvl[i-1] += upsample(grad_lvl[i]) / 4 for i = L-1 .. 1

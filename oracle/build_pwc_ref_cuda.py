@@ -5,8 +5,10 @@ The reference (core/models/ff-pwcnet/PWCNet_Core/correlation.py) keeps its kerne
 JIT-compiles after a textual SIZE_n(tensor) substitution (cupy_kernel, :234-269).  CuPy is not installed here, but nvcc
 is: this recipe
   1. reads correlation.py WHERE IT LIES under /root/reference (nothing is copied into the repository),
-  2. executes only its kernel-string assignments and its cupy_kernel() function (the module itself cannot be imported:
-     `import cupy`) to specialise the four kernels for a fixed list of shapes, exactly as the reference would,
+  2. reads the four kernel strings out of its syntax tree AS DATA (string constants of the `kernel_Correlation_* = ...`
+     assignments; no reference code is executed -- the module could not be imported anyway: `import cupy`) and
+     specialises them for a fixed list of shapes with a local restatement of the only macro they use, SIZE_n(tensor)
+     -> the n-th extent of that tensor (what the reference's cupy_kernel(), :234-269, substitutes textually),
   3. appends a small host launcher restating the launch geometry of _FunctionCorrelation.forward/backward
      (:278-380: grid / block / shared-memory sizes, per-sample backward launches),
   4. compiles everything for sm_100a into oracle/_ref/ (git-ignored; travels to the GPU box with the snapshot).
@@ -21,10 +23,8 @@ import re
 import subprocess
 import sys
 
-import torch
-
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF = os.environ.get("FFCORR_REFERENCE", "/root/reference")
+REF = "/root/reference"
 SRC = os.path.join(REF, "core/models/ff-pwcnet/PWCNet_Core/correlation.py")
 OUT_DIR = os.path.join(HERE, "_ref")
 
@@ -35,28 +35,44 @@ SHAPES = [(2, 20, 11, 14), (1, 32, 8, 32), (2, 70, 19, 40), (1, 196, 7, 16), (1,
 
 
 def load_reference_pieces():
-    tree = ast.parse(open(SRC).read(), SRC)
-    keep = []
+    """{name: CUDA-C text} of the reference's kernel strings, taken from the syntax tree as constants (nothing runs)."""
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)      # the reference's regex literals are not raw strings
+        tree = ast.parse(open(SRC).read(), SRC)
+    kernels = {}
     for node in tree.body:
-        if isinstance(node, ast.Assign) and any(isinstance(t, ast.Name) and t.id.startswith("kernel_Correlation_") for t in node.targets):
-            keep.append(node)
-        if isinstance(node, ast.FunctionDef) and node.name == "cupy_kernel":
-            keep.append(node)
-    ns = {"re": re, "torch": torch}
-    exec(compile(ast.Module(body=keep, type_ignores=[]), SRC, "exec"), ns)
-    return ns
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) \
+                and node.targets[0].id.startswith("kernel_Correlation_") and isinstance(node.value, ast.Constant) \
+                and isinstance(node.value.value, str):
+            kernels[node.targets[0].id] = node.value.value
+    want = {"kernel_Correlation_rearrange", "kernel_Correlation_updateOutput", "kernel_Correlation_updateGradOne",
+            "kernel_Correlation_updateGradTwo"}
+    if set(kernels) != want:
+        raise RuntimeError(f"expected the kernel strings {sorted(want)} in {SRC}, found {sorted(kernels)}")
+    return kernels
+
+
+def substitute_sizes(text: str, sizes: dict) -> str:
+    """SIZE_n(name) -> str(sizes[name][n]): the shape specialisation the reference applies before NVRTC."""
+    def rep(m):
+        return str(sizes[m.group(2)][int(m.group(1))])
+    out = re.sub(r"SIZE_([0-4])\(([^\)]*)\)", rep, text)
+    if "VALUE_" in out:
+        raise RuntimeError("the kernel strings use VALUE_n(), which this recipe does not restate")
+    return out
 
 
 def specialise(ns, idx, shape):
     b, c, h, w = shape
-    meta = lambda *s: torch.empty(*s, device="meta")
-    one, rbot = meta(b, c, h, w), meta(b, h + 8, w + 8, c)
-    out = meta(b, 81, h, w)
-    grad = meta(b, c, h, w)
+    one, rbot = (b, c, h, w), (b, h + 8, w + 8, c)
+    out = (b, 81, h, w)
+    grad = (b, c, h, w)
     srcs = []
 
     def emit(name, variables, suffix):
-        s = ns["cupy_kernel"](name, variables)
+        s = substitute_sizes(ns[name], {k: v for k, v in variables.items() if v is not None})
         s = s.replace("#define ROUND_OFF 50000", "")          # defined once at the top of the generated file
         return s.replace(name + "(", f"{name}_{suffix}_s{idx}(")
 

@@ -112,9 +112,86 @@ def make_e2e():
     print("wrote", path)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE shapes.  Inputs are pure functions of a seed (tests/weights.py: seeded_fmaps / seeded_coords /
+# synthetic_pair / fill_state_dict), so the files hold only reference OUTPUTS, and those on a fixed subset:
+#   fullsize_corr_*.npz   pyramid maps of `CorrBlock` for 24 queries, lookups for NQ evenly spaced queries
+#   ffraft_e2e_full.npz  `FF_RAFT_FUSION` test-mode flow: the 1/8-resolution flow in full, flow_up on every 4th pixel
+# ---------------------------------------------------------------------------------------------------------------
+FULL_CORR = {  # name: (b, d, h, w, seed)
+    "c1_46x62": (1, 256, 46, 62, 2101),       # BASELINE config 1 / 5 (368x496)
+    "c2_47x156": (1, 256, 47, 156, 2102),     # BASELINE config 2 (376x1248)
+}
+FULL_COORDS = {"grid": (0.0, 0.0), "half": (0.0, 0.5), "s3": (3.0, 0.37), "s20": (20.0, 0.0)}   # name: (sigma, offset)
+NQ = 192
+
+
+def make_corr_full():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from weights import seeded_coords, seeded_fmaps
+
+    CorrBlock, _ = _ref_corr()
+    for name, (b, d, h, w, seed) in FULL_CORR.items():
+        f1, f2 = seeded_fmaps(seed, b, d, h, w)
+        n = h * w
+        sel = np.unique(np.concatenate([np.linspace(0, b * n - 1, NQ).astype(np.int64), [0, w - 1, n - w, n - 1]]))
+        sel_lv = np.unique(np.concatenate([sel[::10], [0, w - 1, n - w, n - 1]]))      # a subset of `queries`
+        out = {"shape": np.array([b, d, h, w, seed]), "queries": sel, "queries_levels": sel_lv}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            blk = CorrBlock(torch.from_numpy(f1), torch.from_numpy(f2), num_levels=4, radius=4)
+            for i, lvl in enumerate(blk.corr_pyramid):
+                out[f"level{i}"] = lvl.numpy()[sel_lv, 0]
+            out["level0_absmax"] = np.float32(blk.corr_pyramid[0].abs().max())
+            for k, (sigma, offset) in FULL_COORDS.items():
+                c = seeded_coords(seed + 7, b, h, w, sigma, offset)
+                res = blk(torch.from_numpy(c)).numpy().reshape(b, 324, n)            # [B, 324, N]
+                out[f"lookup_{k}"] = np.ascontiguousarray(res.transpose(0, 2, 1).reshape(b * n, 324)[sel])
+                out[f"lookup_{k}_absmax"] = np.float32(np.abs(res).max())
+        path = os.path.join(GOLD, f"fullsize_corr_{name}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path) >> 10, "KiB")
+
+
+FULL_E2E = {  # tag: (b, H, W, iters, flow_gain name)
+    "c1": (1, 368, 496, 12, "damped"),        # BASELINE config 1
+    "c1_lively": (1, 368, 496, 12, "lively"),  # same, multi-pixel updates (ADVICE: the damped head hides correlation errors)
+    "c2": (1, 376, 1248, 12, "damped"),       # BASELINE config 2, one pair of the batch
+    "c4": (1, 440, 1024, 32, "damped"),       # BASELINE config 4: Sintel 436x1024 padded (utils.py:9-16), 32 iterations
+    "c4_lively": (1, 440, 1024, 32, "lively"),
+}
+
+
+def make_e2e_full():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle.reference_loader import load_ff_raft
+    from weights import DAMPED_GAIN, LIVELY_GAIN, fill_state_dict, synthetic_pair
+
+    model, _, _ = load_ff_raft()
+    out = {}
+    for tag, (b, hh, ww, iters, gain) in FULL_E2E.items():
+        sd = model.state_dict()
+        fill_state_dict(sd, seed=1234, flow_gain=LIVELY_GAIN if gain == "lively" else DAMPED_GAIN)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        im1, im2, m1, m2 = synthetic_pair(b, hh, ww, seed=4321)
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            lo, up = model(im1, im2, m1, m2, raft_iters=iters, test_mode=True)
+        out[f"{tag}_shape"] = np.array([b, hh, ww, iters])
+        out[f"{tag}_gain"] = np.array(gain)
+        out[f"{tag}_flow_lo"] = lo.numpy()
+        out[f"{tag}_flow_up_s4"] = np.ascontiguousarray(up.numpy()[:, :, ::4, ::4])
+        print(tag, "flow_up mean |f| =", float(up.abs().mean()), "max", float(up.abs().max()))
+    path = os.path.join(GOLD, "ffraft_e2e_full.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) >> 10, "KiB")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", choices=["corr", "e2e"], default=None)
+    ap.add_argument("--only", choices=["corr", "e2e", "corr_full", "e2e_full"], default=None)
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -124,3 +201,7 @@ if __name__ == "__main__":
         make_corr("b1_d256_16x16", b=1, d=256, h=16, w=16, seed=13, keep=("grid", "s1"))    # the real D
     if a.only in (None, "e2e"):
         make_e2e()
+    if a.only in (None, "corr_full"):
+        make_corr_full()
+    if a.only in (None, "e2e_full"):
+        make_e2e_full()

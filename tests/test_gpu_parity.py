@@ -28,6 +28,18 @@ def ff():
     return m
 
 
+@pytest.fixture(autouse=True)
+def _cpu_sampler_default():
+    """The oracle and the golden vectors follow the reference's CPU run (ATen divides by W-1), so inside this module
+    blocks and calls that do not name a sampler use "cpu"; the package default is "cuda" (tested in test_host_cpu.py,
+    and against ATen's CUDA grid_sample in test_lookup_vs_the_reference_formula_on_torch_cuda)."""
+    m = ff()
+    before = m.get_sampler_semantics()
+    m.set_sampler_semantics("cpu")
+    yield
+    m.set_sampler_semantics(before)
+
+
 def t(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 
@@ -168,9 +180,9 @@ def test_lookup_vs_oracle(shape, radius, nl):
 @pytest.mark.parametrize("shape", [(2, 46, 62), (1, 47, 156), (2, 17, 21)])
 def test_lookup_vs_the_reference_formula_on_torch_cuda(shape):
     """What the reference runs on a GPU: corr.py:29-50 + utils.py:57-71 through ATen's CUDA kernels, whose division by
-    the scalar (W-1) is a multiplication by its fp32 reciprocal.  With set_sampler_semantics("cuda") the lookups (and
-    the adjoint) follow that form and agree to 1e-5; the default CPU form differs by up to ~3e-5 of max|value| -- the
-    same amount by which the reference's own CPU and GPU runs differ."""
+    the scalar (W-1) is a multiplication by its fp32 reciprocal.  With sampler="cuda" (the default) the lookups (and
+    the adjoint) follow that form and agree to 1e-5; sampler="cpu" differs by up to ~3e-5 of max|value| -- the
+    same amount by which the reference's own CPU and GPU runs differ.  Both output layouts."""
     m = ff()
     b, h, w = shape
     torch.manual_seed(41)
@@ -178,28 +190,26 @@ def test_lookup_vs_the_reference_formula_on_torch_cuda(shape):
     pyr = [torch.randn(b * n, 1, h >> i, w >> i, device=DEV) for i in range(4)]
     dd = torch.linspace(-4, 4, 9, device=DEV)
     delta = torch.stack(torch.meshgrid(dd, dd, indexing="ij"), dim=-1).view(1, 9, 9, 2)
-    assert m.get_sampler_semantics() == "cpu"
-    try:
-        for sigma in (0.7, 3.0, 25.0):
-            coords = m.coords_grid(b, h, w, DEV) + 0.37 + torch.randn(b, 2, h, w, device=DEV) * sigma
-            c = coords.permute(0, 2, 3, 1).reshape(b * n, 1, 1, 2)
-            outs = []
-            for i, lv in enumerate(pyr):
-                cl = c / 2 ** i + delta
-                hh, ww = lv.shape[-2:]
-                xg, yg = cl.split([1, 1], dim=-1)
-                grid = torch.cat([2 * xg / (ww - 1) - 1, 2 * yg / (hh - 1) - 1], dim=-1)
-                outs.append(torch.nn.functional.grid_sample(lv, grid, align_corners=True).view(b, h, w, -1))
-            ref = torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().float()
-            scale = float(ref.abs().max())
-            m.set_sampler_semantics("cpu")
-            for got in (m.lookup(pyr, coords, 4), m.lookup_tiled(m.tile_levels(pyr), coords, 4)):
+    for sigma in (0.7, 3.0, 25.0):
+        coords = m.coords_grid(b, h, w, DEV) + 0.37 + torch.randn(b, 2, h, w, device=DEV) * sigma
+        c = coords.permute(0, 2, 3, 1).reshape(b * n, 1, 1, 2)
+        outs = []
+        for i, lv in enumerate(pyr):
+            cl = c / 2 ** i + delta
+            hh, ww = lv.shape[-2:]
+            xg, yg = cl.split([1, 1], dim=-1)
+            grid = torch.cat([2 * xg / (ww - 1) - 1, 2 * yg / (hh - 1) - 1], dim=-1)
+            outs.append(torch.nn.functional.grid_sample(lv, grid, align_corners=True).view(b, h, w, -1))
+        ref = torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+        scale = float(ref.abs().max())
+        tl = m.tile_levels(pyr)
+        for cl_out in (False, True):
+            for got in (m.lookup(pyr, coords, 4, sampler="cpu", channels_last=cl_out),
+                        m.lookup_tiled(tl, coords, 4, sampler="cpu", channels_last=cl_out)):
                 assert float((got - ref).abs().max()) <= 1e-4 * scale, ("cpu", sigma)
-            m.set_sampler_semantics("cuda")
-            for got in (m.lookup(pyr, coords, 4), m.lookup_tiled(m.tile_levels(pyr), coords, 4)):
+            for got in (m.lookup(pyr, coords, 4, sampler="cuda", channels_last=cl_out),
+                        m.lookup_tiled(tl, coords, 4, sampler="cuda", channels_last=cl_out)):
                 assert float((got - ref).abs().max()) <= 1e-5 * scale, ("cuda", sigma, float((got - ref).abs().max()) / scale)
-    finally:
-        m.set_sampler_semantics("cpu")
 
 
 def test_corrblock_surface_and_errors():
@@ -502,7 +512,7 @@ def test_lookup_backward_vs_oracle_adjoint():
     glv = [torch.zeros(q, 1, h >> i, w >> i, device=DEV) for i in range(2)]
     c_dev, g_dev = t(coords), t(gout)  # keep alive: data_ptr() of a temporary dangles
     _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), 2, c_dev.data_ptr(), g_dev.data_ptr(), b, h, w, 4,
-                                                _lib.current_stream()), "bwd")
+                                                0, _lib.current_stream()), "bwd")
     torch.cuda.synchronize()
     c = coords.transpose(0, 2, 3, 1).reshape(q, 2)
     g = gout.transpose(0, 2, 3, 1).reshape(q, 2, 81)
@@ -533,7 +543,7 @@ def test_lookup_backward_is_the_adjoint_of_the_forward(shape, radius, nl):
         glv = [torch.zeros_like(p) for p in pyr]
         for _ in range(2):
             _lib.check(_lib.lib().ffcorr_lookup_bwd_f32(_lib.ptr_array(glv), nl, c_dev.data_ptr(), gout.data_ptr(), b, h, w,
-                                                        radius, _lib.current_stream()), "bwd")
+                                                        radius, 1, _lib.current_stream()), "bwd")
         torch.cuda.synchronize()
         rhs = sum(float((p.double() * g.double()).sum()) for p, g in zip(pyr, glv)) / 2
         scale = float(out.double().abs().mul(gout.double().abs()).sum()) + 1e-30
@@ -926,3 +936,157 @@ def test_host_model_with_alternate_corr_gives_the_same_flow():
         model.flow_net.alternate_corr = True
         alt = model(im1, im2, m1, None, raft_iters=4, test_mode=True)[1]
     assert torch.equal(ref, alt)
+
+
+# ---------------------------------------------------------------- reference vectors at the BASELINE shapes
+FULL_CORR = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "fullsize_corr_*.npz")))
+FULL_COORDS = {"grid": (0.0, 0.0), "half": (0.0, 0.5), "s3": (3.0, 0.37), "s20": (20.0, 0.0)}
+
+
+@pytest.mark.parametrize("path", FULL_CORR, ids=[os.path.basename(p) for p in FULL_CORR])
+def test_reference_vectors_at_baseline_shapes(path):
+    """fullsize_corr_*.npz: the UNMODIFIED reference CorrBlock (CPU) at D=256 on 46x62 (configs 1/5) and 47x156
+    (config 2) feature maps -- pyramid maps of 24 queries, lookups of 196 queries, four coordinate regimes.
+    Inputs are regenerated from the seed.  Bars: volume <= 1e-3 relative (tensor-core operands) / 2e-6 (fp32 path),
+    lookups <= 1e-5 of max|ref| on a pyramid that agrees with the reference's to fp32 rounding."""
+    from weights import seeded_coords, seeded_fmaps
+
+    m = ff()
+    g = np.load(path)
+    b, d, h, w, seed = [int(v) for v in g["shape"]]
+    n = h * w
+    f1, f2 = seeded_fmaps(seed, b, d, h, w)
+    ql, q = torch.from_numpy(g["queries_levels"]).to(DEV), torch.from_numpy(g["queries"]).to(DEV)
+    for prec, vtol, ltol in (("fp32", 2e-6, 1e-5), ("fp16", 1e-3, 1e-3), ("tf32", 1e-3, 1e-3), ("bf16x3", 3e-5, 3e-5)):
+        blk = m.CorrBlock(t(f1), t(f2), num_levels=4, radius=4, precision=prec, sampler="cpu")
+        for i in range(4):
+            got = blk.corr_pyramid[i][ql, 0].cpu().numpy()
+            assert got.shape == g[f"level{i}"].shape
+            assert rel_fro(got, g[f"level{i}"]) <= vtol, (prec, i, rel_fro(got, g[f"level{i}"]))
+        for k, (sigma, offset) in FULL_COORDS.items():
+            c = seeded_coords(seed + 7, b, h, w, sigma, offset)
+            out = blk(t(c)).view(b, 324, n).permute(0, 2, 1).reshape(b * n, 324)[q].cpu().numpy()
+            err = np.abs(out - g[f"lookup_{k}"]).max() / float(g[f"lookup_{k}_absmax"])
+            assert err <= ltol, (prec, k, err)
+        del blk
+
+
+E2E_FULL = os.path.join(os.path.dirname(__file__), "golden", "ffraft_e2e_full.npz")
+
+
+@pytest.mark.parametrize("tag", ["c1", "c1_lively", "c2", "c4", "c4_lively"])
+def test_e2e_epe_at_baseline_shapes(tag):
+    """north_star: "end-point error after 12 refinement iterations within 0.01 px" -- against FF_RAFT_FUSION (the
+    unmodified reference, CPU fp32) at 368x496 x12 (config 1), 376x1248 x12 (config 2) and 440x1024 x32 (config 4,
+    evaluate.py:62/105 iterations).  `lively` = flow head gain 0.05: 2.5 px of motion per iteration (27 / 70 px mean
+    flow at the end), so the lookups sample far from the integer grid; `damped` = 0.004 (sub-pixel updates).
+    Host convolutions run in fp32 (TF32 off) so that the difference isolates the correlation path."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from weights import DAMPED_GAIN, LIVELY_GAIN, fill_state_dict, synthetic_pair
+    from focusflow_official_b200.host import FocusRAFT
+
+    g = np.load(E2E_FULL)
+    b, hh, ww, iters = [int(v) for v in g[f"{tag}_shape"]]
+    gain = LIVELY_GAIN if str(g[f"{tag}_gain"]) == "lively" else DAMPED_GAIN
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = FocusRAFT()
+    sd = model.state_dict()
+    fill_state_dict(sd, seed=1234, flow_gain=gain)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    im1, im2, m1, m2 = (x.to(DEV) for x in synthetic_pair(b, hh, ww, seed=4321))
+    ref_lo = torch.from_numpy(g[f"{tag}_flow_lo"])
+    ref_up = torch.from_numpy(g[f"{tag}_flow_up_s4"])
+    for prec in ("fp16", "fp32"):
+        model.flow_net.corr_precision = prec
+        with torch.no_grad():
+            lo, up = model(im1, im2, m1, m2, raft_iters=iters, test_mode=True)
+        epe = torch.linalg.norm(up.cpu()[:, :, ::4, ::4] - ref_up, dim=1)
+        epe_lo = torch.linalg.norm(lo.cpu() - ref_lo, dim=1) * 8.0          # in full-resolution pixels
+        print(f"e2e_full {tag} {prec}: EPE mean {float(epe.mean()):.2e} max {float(epe.max()):.2e} "
+              f"(1/8-res flow x8: max {float(epe_lo.max()):.2e}); |flow| mean {float(ref_up.abs().mean()):.1f}")
+        assert float(epe.max()) <= 1e-2, (tag, prec, float(epe.max()))
+        assert float(epe_lo.max()) <= 1e-2, (tag, prec, float(epe_lo.max()))
+
+
+# ---------------------------------------------------------------- channels-last (NHWC) lookups: SURVEY 8b / 8f N3
+@pytest.mark.parametrize("shape,radius,nl", [((1, 46, 62), 4, 4), ((2, 17, 21), 4, 4), ((1, 24, 40), 3, 4), ((2, 12, 9), 2, 3),
+                                             ((1, 9, 33), 1, 2), ((3, 8, 8), 4, 1), ((1, 47, 156), 4, 4), ((2, 13, 11), 1, 1)])
+def test_channels_last_lookup_is_the_same_values_in_nhwc_memory(shape, radius, nl):
+    """out_channels_last = 1 (include/ffcorr.h): [B, h, w, L*K*K] storage, bit-identical values, for the row-major
+    kernel, the tiled kernel (8 queries x all levels per warp, TMA bulk store) and the chunked (AlternateCorrBlock)
+    entry point; query counts that are not multiples of 8 / 32, 1-4 levels, radii 1-4, every coordinate regime."""
+    m = ff()
+    b, h, w = shape
+    rng = np.random.default_rng(5)
+    q = b * h * w
+    k2 = (2 * radius + 1) ** 2
+    pyr = [rng.standard_normal((q, h >> i, w >> i)).astype(np.float32) for i in range(nl)]
+    levels = [t(p[:, None]) for p in pyr]
+    tl = m.tile_levels(levels)
+    for name, c in _coords_cases(rng, b, h, w).items():
+        cd = t(c)
+        ref = co.lookup(pyr, c, radius)
+        for fn, lv in ((m.lookup, levels), (m.lookup_tiled, tl)):
+            nchw = fn(lv, cd, radius)
+            nhwc = fn(lv, cd, radius, channels_last=True)
+            assert nhwc.shape == (b, nl * k2, h, w) and nhwc.is_contiguous(memory_format=torch.channels_last) or nl * k2 == 1
+            assert nhwc.permute(0, 2, 3, 1).is_contiguous()
+            assert torch.equal(nhwc.contiguous(), nchw), (fn.__name__, name)
+            assert max_rel(nhwc.cpu().numpy(), ref) <= 1e-5, (fn.__name__, name)
+
+
+def test_channels_last_blocks_and_the_host_model_use_no_layout_copy():
+    m = ff()
+    torch.manual_seed(3)
+    f1, f2 = torch.randn(2, 64, 24, 40, device=DEV), torch.randn(2, 64, 24, 40, device=DEV)
+    coords = m.coords_grid(2, 24, 40, DEV) + torch.randn(2, 2, 24, 40, device=DEV) * 2
+    a = m.CorrBlock(f1, f2)(coords)
+    for blk in (m.CorrBlock(f1, f2, channels_last=True), m.AlternateCorrBlock(f1, f2, channels_last=True, chunk=200),
+                m.CorrBlock(f1, f2, channels_last=True, precision="fp32")):
+        out = blk(coords)
+        assert out.is_contiguous(memory_format=torch.channels_last)
+        assert out.contiguous(memory_format=torch.channels_last).data_ptr() == out.data_ptr()     # no copy for convc1
+        if blk.__class__.__name__ != "CorrBlock" or blk._tiled:
+            assert torch.equal(out.contiguous(), a)
+    # autograd through a channels-last block == through the NCHW one
+    g = torch.randn_like(a)
+    grads = []
+    for cl in (False, True):
+        x1, x2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+        out = m.CorrBlock(x1, x2, channels_last=cl)(coords)
+        (out * g).sum().backward()
+        grads.append((x1.grad, x2.grad))
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_launches_follow_the_tensors_device_not_the_current_one():
+    """with cuda:0 current and the model on cuda:1, kernels, TMA descriptors and the stream must be those of
+    cuda:1 (ATen guards the device the same way); mixing devices in one call is a ValueError."""
+    m = ff()
+    assert torch.cuda.current_device() == 0
+    dev1 = torch.device("cuda", 1)
+    torch.manual_seed(9)
+    f1, f2 = torch.randn(1, 64, 24, 32), torch.randn(1, 64, 24, 32)
+    coords = m.coords_grid(1, 24, 32, "cpu") + torch.randn(1, 2, 24, 32)
+    ref = m.CorrBlock(f1.to(DEV), f2.to(DEV))(coords.to(DEV))
+    side = torch.cuda.Stream(device=dev1)
+    with torch.cuda.stream(side):                       # current stream of cuda:1 only; current device stays 0
+        pass
+    blk = m.CorrBlock(f1.to(dev1), f2.to(dev1))
+    out = blk(coords.to(dev1))
+    assert out.device == dev1 and torch.cuda.current_device() == 0
+    assert torch.equal(out.cpu(), ref.cpu())
+    cv = m.FunctionCorrelation(f1.to(dev1), f2.to(dev1))
+    assert torch.equal(cv.cpu(), m.FunctionCorrelation(f1.to(DEV), f2.to(DEV)).cpu())
+    x1 = f1.to(dev1).requires_grad_(True)
+    m.CorrBlock(x1, f2.to(dev1))(coords.to(dev1)).sum().backward()
+    assert x1.grad is not None and x1.grad.device == dev1 and torch.isfinite(x1.grad).all()
+    with pytest.raises(ValueError):
+        m.CorrBlock(f1.to(DEV), f2.to(dev1))
+    with pytest.raises(ValueError):
+        blk(coords.to(DEV))

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in include/ffcorr.h but not exported"
     assert set(syms) == set(_lib.SYMBOLS), "ctypes prototypes and header disagree"
-    assert _lib.lib().ffcorr_version() == 100
+    assert _lib.lib().ffcorr_version() == 200
 
 
 def test_ctypes_prototypes_match_the_header_parameter_by_parameter():
@@ -72,11 +72,15 @@ def test_argument_errors_are_return_codes_not_crashes():
 
     L = _lib.lib()
     # bad shapes are rejected before any CUDA call, so this is safe without a GPU
-    assert L.ffcorr_lookup_f32(None, 4, None, None, -1, 8, 8, 4, None) == -1
+    assert L.ffcorr_lookup_f32(None, 4, None, None, -1, 8, 8, 4, 1, 0, None) == -1
     assert b"B=-1" in L.ffcorr_last_error()
     ptrs = (ctypes.c_void_p * 4)()
-    assert L.ffcorr_lookup_f32(ptrs, 4, 1, 1, 1, 8, 8, 9, None) == -1          # radius out of range
-    assert L.ffcorr_lookup_f32(ptrs, 4, 1, 1, 1, 4, 4, 4, None) == -1          # map too small for 4 levels
+    assert L.ffcorr_lookup_f32(ptrs, 4, 1, 1, 1, 8, 8, 9, 1, 0, None) == -1    # radius out of range
+    assert L.ffcorr_lookup_f32(ptrs, 4, 1, 1, 1, 16, 16, 4, 7, 0, None) == -1  # sampler is neither ATEN_CPU nor ATEN_CUDA
+    assert b"sampler" in L.ffcorr_last_error()
+    assert L.ffcorr_lookup_f32(ptrs, 1, 1, 1, 1, 8192, 4096, 4, 1, 0, None) == -1   # h*w >= 2^24: 32-bit tile offsets
+    assert b"2^24" in L.ffcorr_last_error()
+    assert L.ffcorr_lookup_f32(ptrs, 4, 1, 1, 1, 4, 4, 4, 1, 0, None) == -1    # map too small for 4 levels
     assert L.ffcorr_pyramid_f32(ptrs, 99, 1, 8, 8, None) == -1
     assert L.ffcorr_volume_f32(1, 1, 1, 1, 0, 8, 8, 0, None, 0, None) == -1    # D = 0
     assert L.ffcorr_volume_workspace_bytes(8, 256, 47, 156, 0) == 2 * 8 * (48 * 160) * 256 * 2  # padded to 16x16 super-groups
@@ -92,17 +96,31 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert L.ffcorr_build_tiled_f32(1, 1, None, 4, 1, 256, 16, 16, 0, None, 0, None) == -1          # null level table
     assert L.ffcorr_build_tiled_f32(1, 1, ptrs, 5, 1, 256, 64, 64, 0, None, 0, None) == -1          # > 4 levels
     assert L.ffcorr_build_tiled_chunk_f32(ptrs, 4, 1, 256, 16, 16, 0, 32, 0, None, 0, None) == -1   # null level pointers
-    assert L.ffcorr_lookup_tiled_chunk_f32(ptrs, 4, 1, 1, 1, 16, 16, 250, 32, 4, None) == -1        # chunk beyond the map
+    assert L.ffcorr_lookup_tiled_chunk_f32(ptrs, 4, 1, 1, 1, 16, 16, 250, 32, 4, 1, 0, None) == -1  # chunk beyond the map
     assert b"query range" in L.ffcorr_last_error()
     assert L.ffcorr_volume_scaled_f32(1, 1, 1, 1, 8, 8, 8, 0, ctypes.c_float(0.0), None, 0, None) == -1
     assert b"divisor" in L.ffcorr_last_error()
     assert L.ffcorr_stage_operands_f32(1, 1, 9, 1, 8, 8, 8, 0, None, 0, None) == -1                 # 9 levels
     # empty batches are a no-op, even with null pointers
-    assert L.ffcorr_lookup_f32(None, 4, None, None, 0, 16, 16, 4, None) == 0
+    assert L.ffcorr_lookup_f32(None, 4, None, None, 0, 16, 16, 4, 1, 1, None) == 0
     assert L.ffcorr_build_tiled_f32(None, None, ptrs, 4, 0, 256, 16, 16, 0, None, 0, None) == 0
-    assert L.ffcorr_lookup_tiled_chunk_f32(ptrs, 4, None, None, 0, 16, 16, 0, 32, 4, None) == 0
+    assert L.ffcorr_lookup_tiled_chunk_f32(ptrs, 4, None, None, 0, 16, 16, 0, 32, 4, 0, 1, None) == 0
     with pytest.raises(RuntimeError):
         _lib.check(-1, "x")
+
+
+def test_sampler_default_and_validation():
+    """The library has no global switch any more: the sampler travels with every call; Python keeps only a default."""
+    import focusflow_official_b200 as ff
+    from focusflow_official_b200 import _lib
+
+    assert ff.get_sampler_semantics() == "cuda"          # what a GPU user of the reference gets
+    ff.set_sampler_semantics("cpu")
+    assert ff.get_sampler_semantics() == "cpu"
+    ff.set_sampler_semantics("cuda")
+    with pytest.raises(ValueError):
+        ff.set_sampler_semantics("gpu")
+    assert not hasattr(_lib.lib(), "ffcorr_set_sampler_semantics")
 
 
 def test_cpu_tensors_are_refused_not_silently_computed():
@@ -128,7 +146,8 @@ def test_missing_extension_fails_loudly_in_a_fresh_process():
         "_lib.LIB_PATH = _lib.LIB_PATH + '.absent'\n"
         "import focusflow_official_b200 as ff\n"
         "try:\n"
-        "    ff.get_sampler_semantics()\n"
+        "    ff.CorrBlock  # importing is fine; the first USE must fail\n"
+        "    _lib.lib()\n"
         "except RuntimeError as e:\n"
         "    assert 'missing' in str(e) and 'make -C' in str(e), str(e)\n"
         "    print('LOUD')\n" % ROOT)

@@ -12,8 +12,17 @@ import numpy as np
 import torch
 
 
-def fill_state_dict(sd: dict, seed: int = 1234) -> dict:
-    """In-place, key-wise deterministic fill (kaiming-like scale so activations stay O(1))."""
+DAMPED_GAIN = 0.004    # sub-pixel updates per iteration, like a converged trained network
+LIVELY_GAIN = 0.05     # ~0.3 low-res px (2.5 full-res px) per iteration: multi-pixel motion, windows far from the grid
+
+
+def fill_state_dict(sd: dict, seed: int = 1234, flow_gain: float = DAMPED_GAIN) -> dict:
+    """In-place, key-wise deterministic fill (kaiming-like scale so activations stay O(1)).
+
+    `flow_gain` scales the last conv of the flow head: DAMPED_GAIN keeps the random-init refinement contractive
+    (every iteration moves the flow by ~0.2 px at full resolution); LIVELY_GAIN lets it move ~2.5 px per iteration
+    (27 px mean / 90 px max after 12 iterations at 368x496), so the lookups leave the integer grid by several cells
+    and the end-to-end comparison becomes sensitive to the correlation values themselves."""
     for key in sorted(sd.keys()):
         t = sd[key]
         rng = np.random.RandomState((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31 - 1))
@@ -29,7 +38,7 @@ def fill_state_dict(sd: dict, seed: int = 1234) -> dict:
             fan_out = shape[0] * shape[2] * shape[3]
             v = rng.randn(*shape) * np.sqrt(2.0 / fan_out)
             if key.endswith("flow_head.conv2.weight"):
-                v = v * 0.004  # keep the random-init refinement contractive (sub-px updates, like a trained net)
+                v = v * flow_gain
         elif key.endswith("weight"):  # norm scale
             v = 1.0 + 0.05 * rng.randn(*shape)
         else:  # biases
@@ -53,3 +62,21 @@ def synthetic_pair(batch: int, height: int, width: int, seed: int = 1234, keypoi
     for b in range(batch):
         mask[b, 0, ys[b], xs[b]] = 255.0
     return im1, im2, mask, mask.clone()
+
+
+def seeded_fmaps(seed: int, b: int, d: int, h: int, w: int, scale: float = 4.4):
+    """Feature maps as a pure function of the seed (legacy RandomState: bit-stable across numpy versions), so that
+    full-size golden files need not store their 7.5 MB inputs."""
+    rng = np.random.RandomState(seed)
+    f1 = (rng.standard_normal((b, d, h, w)) * scale).astype(np.float32)
+    f2 = (rng.standard_normal((b, d, h, w)) * scale).astype(np.float32)
+    return f1, f2
+
+
+def seeded_coords(seed: int, b: int, h: int, w: int, sigma: float, offset: float = 0.0):
+    """coords_grid (x, y order) + offset + sigma * N(0,1), a pure function of the seed."""
+    rng = np.random.RandomState(seed)
+    ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    grid = np.repeat(np.stack([xs, ys], 0).astype(np.float32)[None], b, axis=0)
+    noise = rng.standard_normal(grid.shape).astype(np.float32) * np.float32(sigma) if sigma else np.float32(0)
+    return np.ascontiguousarray(grid + np.float32(offset) + noise, dtype=np.float32)

@@ -108,7 +108,7 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         _lib.check(L.ffcorr_pyramid_f32(ptrs, nl, b * n, h, w, stream), "pyramid")
 
     def k_lookup():
-        _lib.check(L.ffcorr_lookup_f32(ptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, stream), "lookup")
+        _lib.check(L.ffcorr_lookup_f32(ptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, 1, 0, stream), "lookup")
 
     def k_volume_t():
         _lib.check(L.ffcorr_volume_tiled_f32(f1.data_ptr(), f2.data_ptr(), tl[0].data_ptr(), b, d, h, w, code,
@@ -122,7 +122,12 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
                                             stream), "build_tiled")
 
     def k_lookup_t():
-        _lib.check(L.ffcorr_lookup_tiled_f32(tptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, stream), "lookup_tiled")
+        _lib.check(L.ffcorr_lookup_tiled_f32(tptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, 1, 0, stream), "lookup_tiled")
+
+    out_nhwc = torch.empty(b, h, w, nl * 81, device=dev)
+
+    def k_lookup_t_nhwc():
+        _lib.check(L.ffcorr_lookup_tiled_f32(tptrs, nl, coords.data_ptr(), out_nhwc.data_ptr(), b, h, w, r, 1, 1, stream), "lookup_tiled_nhwc")
 
     res = []
     lv_elems = [(h >> i) * (w >> i) for i in range(nl)]
@@ -134,7 +139,7 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     if tiled_ok:  # same algorithmic bytes: the padding of the tiled layout is overhead, not work
         todo += [("volume_tiled", k_volume_t, vol_bytes, vol_flops), ("pyramid_tiled", k_pyramid_t, pyr_bytes, 0.0),
                  ("build_fused", k_build_t, vol_bytes + pyr_bytes - 4.0 * b * n * lv_elems[0], vol_flops),
-                 ("lookup_tiled", k_lookup_t, look_bytes, 0.0)]
+                 ("lookup_tiled", k_lookup_t, look_bytes, 0.0), ("lookup_tiled_nhwc", k_lookup_t_nhwc, look_bytes, 0.0)]
     if tiled_ok and (not only or "alt_lookup" in only):
         # memory-bounded AlternateCorrBlock: the pyramid of a 512 MiB query chunk is rebuilt for every lookup
         alt = ff.AlternateCorrBlock(f1, f2, num_levels=nl, radius=r, precision=precision)
@@ -149,7 +154,7 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         if only and name not in only:
             # run (untimed) only what a selected kernel reads
             needs = {"pyramid": ["volume"], "lookup": ["volume", "pyramid"], "pyramid_tiled": ["volume_tiled"],
-                     "lookup_tiled": ["build_fused"]}
+                     "lookup_tiled": ["build_fused"], "lookup_tiled_nhwc": ["build_fused"]}
             if any(name in needs.get(o, []) for o in only):
                 fn()
             continue

@@ -7,6 +7,9 @@
 //   mode 4: LDGSTS 16 B, 4 lanes per granule
 //   mode 5: cp.async.bulk 64 B per lane (TMA engine), mbarrier completion
 //   mode 6: LDG.128 x4 per lane: a lane reads its whole random 64-byte granule
+//   mode 7: LDG.128, 16 lanes cover one random aligned 256-byte block
+//   mode 8: LDG.128, 32 lanes cover one random aligned 512-byte block
+//   mode 9: LDG.128, 8 lanes cover 128 bytes starting at a random 64-byte granule (half the runs straddle two lines)
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -29,14 +32,17 @@ __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ 
     }
     uint32_t phase = 0;
     for (int it = 0; it < iters; it += 8) {
-        if (MODE <= 2 || MODE == 6) {
+        if (MODE <= 2 || MODE >= 6) {
             float4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                uint32_t key = (MODE == 0 || MODE == 6) ? gtid : (MODE == 1 ? (gtid >> 2) : (gtid >> 3));
+                uint32_t key = (MODE == 0 || MODE == 6) ? gtid : (MODE == 1 ? (gtid >> 2) : (MODE == 7 ? (gtid >> 4) : (MODE == 8 ? (gtid >> 5) : (gtid >> 3))));
                 uint32_t g = hash32(key * 977u + (uint32_t)(it + u) * 0x9e3779b9u) % granules;
                 size_t idx = (size_t)g * 4 + (MODE == 1 ? (lane & 3) : 0);
                 if (MODE == 2) idx = ((size_t)(g & ~1u)) * 4 + (lane & 7);
+                if (MODE == 7) idx = ((size_t)(g & ~3u)) * 4 + (lane & 15);
+                if (MODE == 8) idx = ((size_t)(g & ~7u)) * 4 + (lane & 31);
+                if (MODE == 9) idx = (size_t)(g < granules - 2 ? g : 0) * 4 + (lane & 7);
                 v[u] = __ldg(buf + idx);
                 if (MODE == 6) {
                     float4 b = __ldg(buf + idx + 1), c = __ldg(buf + idx + 2), d = __ldg(buf + idx + 3);
@@ -106,6 +112,9 @@ int main(int argc, char** argv) {
     run<1>(buf, granules, sink, blocks, iters, "LDG.128  4 lanes / 64B granule", 4, 64);
     run<2>(buf, granules, sink, blocks, iters, "LDG.128  8 lanes / 128B line", 8, 128);
     run<6>(buf, granules, sink, blocks, iters, "LDG.128x4 1 lane reads whole 64B granule", 1, 64);
+    run<7>(buf, granules, sink, blocks, iters, "LDG.128 16 lanes / aligned 256B block", 16, 256);
+    run<8>(buf, granules, sink, blocks, iters, "LDG.128 32 lanes / aligned 512B block", 32, 512);
+    run<9>(buf, granules, sink, blocks, iters, "LDG.128  8 lanes / 128B at a random 64B offset", 8, 128);
     run<3>(buf, granules, sink, blocks, iters, "LDGSTS.16 1 lane / 64B granule", 1, 64);
     run<4>(buf, granules, sink, blocks, iters, "LDGSTS.16 4 lanes / 64B granule", 4, 64);
     run<5>(buf, granules, sink, blocks, iters, "cp.async.bulk 64 B / lane", 1, 64);
