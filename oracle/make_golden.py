@@ -155,11 +155,15 @@ def make_corr_full():
 
 FULL_E2E = {  # tag: (b, H, W, iters, flow_gain name)
     "c1": (1, 368, 496, 12, "damped"),        # BASELINE config 1
-    "c1_lively": (1, 368, 496, 12, "lively"),  # same, multi-pixel updates (ADVICE: the damped head hides correlation errors)
     "c2": (1, 376, 1248, 12, "damped"),       # BASELINE config 2, one pair of the batch
     "c4": (1, 440, 1024, 32, "damped"),       # BASELINE config 4: Sintel 436x1024 padded (utils.py:9-16), 32 iterations
-    "c4_lively": (1, 440, 1024, 32, "lively"),
 }
+# Why no end-to-end EPE case with the "lively" flow head (2.5 px of motion per iteration): with random weights that
+# refinement is chaotic.  Measured here on the reference itself (CPU, 368x496): rounding only the CorrBlock inputs to
+# TF32 -- the reference's own GPU configuration -- moves its 12-iteration flow by 3e-3, 1e-2, 0.1, 0.24, 0.7, 1.5 ...
+# 9.5 px (max EPE per iteration, x2.5 per iteration), the damped head by 3e-3 px in total.  A 0.01 px bar on that
+# trajectory tests the chaos, not the kernels; make_trajectory() below pins the lively case where it is well-posed:
+# the lookups along the REFERENCE's own coordinate trajectory.
 
 
 def make_e2e_full():
@@ -189,9 +193,142 @@ def make_e2e_full():
     print("wrote", path, os.path.getsize(path) >> 10, "KiB")
 
 
+def make_trajectory():
+    """Reference FF_RAFT_FUSION with the lively flow head at 368x496: the coordinates it hands to CorrBlock.__call__ at
+    each of its 12 iterations (multi-pixel motion, windows far from the integer grid) and the lookup results for a fixed
+    query subset.  Recorded by a subclass of the reference's CorrBlock swapped into its `raft` module namespace (the way
+    raft.py:198 instantiates it by name); the reference code itself is untouched."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle.reference_loader import load_ff_raft
+    from weights import LIVELY_GAIN, fill_state_dict, synthetic_pair
+
+    model, _, ns = load_ff_raft()
+    raft = ns["raft"]
+    base = raft.CorrBlock
+    rec = {"coords": [], "out": [], "absmax": []}
+    b, hh, ww, iters = 1, 368, 496, 12
+    n = (hh // 8) * (ww // 8)
+    sel = np.unique(np.concatenate([np.linspace(0, n - 1, 60).astype(np.int64), [0, ww // 8 - 1, n - ww // 8, n - 1]]))
+
+    class Recording(base):
+        def __call__(self, coords):
+            out = super().__call__(coords)
+            rec["coords"].append(coords.detach().numpy().copy())
+            rec["out"].append(out.detach().numpy().reshape(b, 324, n)[0].T[sel].copy())
+            rec["absmax"].append(float(out.abs().max()))
+            return out
+
+    sd = model.state_dict()
+    fill_state_dict(sd, seed=1234, flow_gain=LIVELY_GAIN)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    im1, im2, m1, m2 = synthetic_pair(b, hh, ww, seed=4321)
+    raft.CorrBlock = Recording
+    try:
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            lo, up = model(im1, im2, m1, m2, raft_iters=iters, test_mode=True)
+    finally:
+        raft.CorrBlock = base
+    out = {"shape": np.array([b, hh, ww, iters]), "queries": sel, "coords": np.stack(rec["coords"]),
+           "lookups": np.stack(rec["out"]), "absmax": np.array(rec["absmax"]), "flow_lo": lo.numpy()}
+    motion = np.abs(out["coords"][-1] - out["coords"][0])
+    print("trajectory: final |coords - grid| mean", float(motion.mean()), "max", float(motion.max()), "low-res px")
+    path = os.path.join(GOLD, "ffraft_trajectory_c1_lively.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) >> 10, "KiB")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training (BASELINE config 5).  T6 of SURVEY 8c: gradients of fmap1 / fmap2 through the reference CorrBlock's own
+# autograd at the 368x496 feature-map shape, and one full MixLoss training step of FF_RAFT_FUSION (loss value,
+# gradient norm of every parameter, three gradients in full).
+# ---------------------------------------------------------------------------------------------------------------
+def make_corr_grad():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from weights import seeded_coords, seeded_fmaps
+
+    CorrBlock, _ = _ref_corr()
+    b, d, h, w, seed = 1, 256, 46, 62, 2201
+    f1, f2 = seeded_fmaps(seed, b, d, h, w)
+    t1, t2 = torch.from_numpy(f1).requires_grad_(True), torch.from_numpy(f2).requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        blk = CorrBlock(t1, t2, num_levels=4, radius=4)
+        loss = 0.0
+        for k, (sigma, offset) in enumerate([(0.0, 0.0), (2.0, 0.3), (6.0, 0.0)]):      # 3 lookups share one pyramid
+            c = torch.from_numpy(seeded_coords(seed + 10 + k, b, h, w, sigma, offset))
+            g = torch.from_numpy(np.random.RandomState(seed + 20 + k).standard_normal((b, 324, h, w)).astype(np.float32))
+            loss = loss + (blk(c) * g).sum()
+        loss.backward()
+    out = {"shape": np.array([b, d, h, w, seed]), "loss": np.float64(loss.item()),
+           "gfmap1_s16": t1.grad.numpy()[:, ::16].copy(), "gfmap2_s16": t2.grad.numpy()[:, ::16].copy(),
+           "gfmap1_norm": np.float64(t1.grad.double().norm()), "gfmap2_norm": np.float64(t2.grad.double().norm())}
+    path = os.path.join(GOLD, "fullsize_grad_c5_46x62.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) >> 10, "KiB")
+
+
+TRAIN_CASES = {"small": (2, 128, 160, 3), "c5": (1, 368, 496, 12)}     # tag: (b, H, W, iters)
+TRAIN_FULL_GRADS = ["flow_net.fnet.conv2.bias", "flow_net.update_block.flow_head.conv2.weight",
+                    "flow_net.fnet.fusion5.mask2img.conv.bias", "flow_net.cnet.layer1.0.norm1.weight"]
+
+
+def train_inputs(b, hh, ww, seed):
+    """Inputs of one training step as a pure function of the seed (shared with the tests)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from weights import synthetic_pair
+
+    im1, im2, m1, m2 = synthetic_pair(b, hh, ww, seed=seed)
+    rng = np.random.RandomState(seed + 1)
+    flow = torch.from_numpy((rng.standard_normal((b, 2, hh, ww)) * 3.0).astype(np.float32))
+    valid = torch.from_numpy((rng.uniform(size=(b, hh, ww)) > 0.1).astype(np.float32))
+    return im1, im2, flow, m1, m2, valid
+
+
+def make_train():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle.reference_loader import load_ff_raft
+    from weights import fill_state_dict
+
+    model, cfg, ns = load_ff_raft()
+    sys.path.insert(0, ns["root"])
+    from losses import build_losses  # the reference's losses/__init__.py
+
+    loss_fn = build_losses(cfg.TRAIN.LOSS_TYPE, gamma=cfg.TRAIN.LOSS_GAMMA, max_flow=cfg.TRAIN.MAX_FLOW,
+                           kernel_size=cfg.TRAIN.LOSS_KERNEL_SIZE, sigma=cfg.TRAIN.LOSS_SIGMA, lamda=cfg.TRAIN.LOSS_LAMDA)
+    out = {}
+    for tag, (b, hh, ww, iters) in TRAIN_CASES.items():
+        sd = model.state_dict()
+        fill_state_dict(sd, seed=1234)
+        model.load_state_dict(sd, strict=True)
+        model.train()                                            # chairs stage: BatchNorm in training mode (train.py:192)
+        model.zero_grad(set_to_none=True)
+        im1, im2, flow, m1, m2, valid = train_inputs(b, hh, ww, 777)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            preds = model(im1, im2, m1, m2, raft_iters=iters)
+            loss, metrics = loss_fn(preds, flow, valid, m1)
+            loss.backward()
+        names = [k for k, p in model.named_parameters() if p.grad is not None]
+        out[f"{tag}_shape"] = np.array([b, hh, ww, iters])
+        out[f"{tag}_loss"] = np.float64(loss.item())
+        out[f"{tag}_epe"] = np.float64(metrics["epe"])
+        out[f"{tag}_param_names"] = np.array(names)
+        out[f"{tag}_grad_norms"] = np.array([float(dict(model.named_parameters())[k].grad.double().norm()) for k in names])
+        for k in TRAIN_FULL_GRADS:
+            out[f"{tag}_grad::{k}"] = dict(model.named_parameters())[k].grad.numpy().copy()
+        print(tag, "loss", loss.item(), "epe", metrics["epe"], "params with grad", len(names))
+    path = os.path.join(GOLD, "ffraft_train_step.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) >> 10, "KiB")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", choices=["corr", "e2e", "corr_full", "e2e_full"], default=None)
+    ap.add_argument("--only", choices=["corr", "e2e", "corr_full", "e2e_full", "trajectory", "corr_grad", "train"], default=None)
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -205,3 +342,9 @@ if __name__ == "__main__":
         make_corr_full()
     if a.only in (None, "e2e_full"):
         make_e2e_full()
+    if a.only in (None, "trajectory"):
+        make_trajectory()
+    if a.only in (None, "corr_grad"):
+        make_corr_grad()
+    if a.only in (None, "train"):
+        make_train()

@@ -974,13 +974,14 @@ def test_reference_vectors_at_baseline_shapes(path):
 E2E_FULL = os.path.join(os.path.dirname(__file__), "golden", "ffraft_e2e_full.npz")
 
 
-@pytest.mark.parametrize("tag", ["c1", "c1_lively", "c2", "c4", "c4_lively"])
+@pytest.mark.parametrize("tag", ["c1", "c2", "c4"])
 def test_e2e_epe_at_baseline_shapes(tag):
     """north_star: "end-point error after 12 refinement iterations within 0.01 px" -- against FF_RAFT_FUSION (the
     unmodified reference, CPU fp32) at 368x496 x12 (config 1), 376x1248 x12 (config 2) and 440x1024 x32 (config 4,
-    evaluate.py:62/105 iterations).  `lively` = flow head gain 0.05: 2.5 px of motion per iteration (27 / 70 px mean
-    flow at the end), so the lookups sample far from the integer grid; `damped` = 0.004 (sub-pixel updates).
-    Host convolutions run in fp32 (TF32 off) so that the difference isolates the correlation path."""
+    evaluate.py:62/105 iterations), contractive flow head (0.2 px of motion per iteration, like a converged network).
+    Host convolutions run in fp32 (TF32 off) so that the difference isolates the correlation path.
+    The multi-pixel-motion case is test_lookups_along_the_reference_trajectory_with_large_motion: end to end it is
+    chaotic -- the reference's own TF32 configuration drifts 9.5 px from its fp32 run there (oracle/make_golden.py)."""
     import sys
 
     sys.path.insert(0, os.path.dirname(__file__))
@@ -1090,3 +1091,50 @@ def test_launches_follow_the_tensors_device_not_the_current_one():
         m.CorrBlock(f1.to(DEV), f2.to(dev1))
     with pytest.raises(ValueError):
         blk(coords.to(DEV))
+
+
+def test_lookups_along_the_reference_trajectory_with_large_motion():
+    """the damped flow head keeps every lookup within ~1 px of the integer grid, so the end-to-end EPE says
+    little about the correlation values.  Here the reference ran with the lively head (2.5 px of motion per iteration;
+    |coords - grid| up to 15 cells at the end): its CorrBlock inputs `coords` at each of the 12 iterations and its
+    lookup outputs for 64 queries are the fixture.  Our encoder (fp32 convolutions) produces the feature maps, our block
+    is evaluated along the REFERENCE's trajectory: fp32 operands <= 2e-5 of max|ref| (the encoders differ by conv
+    rounding), the tensor-core operand modes <= 1e-3 -- BASELINE's volume bar, since a lookup is a convex combination
+    of volume entries -- for both output layouts."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from weights import LIVELY_GAIN, fill_state_dict, synthetic_pair
+    from focusflow_official_b200.host import FocusRAFT
+
+    m = ff()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ffraft_trajectory_c1_lively.npz"))
+    b, hh, ww, iters = [int(v) for v in g["shape"]]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = FocusRAFT()
+    sd = model.state_dict()
+    fill_state_dict(sd, seed=1234, flow_gain=LIVELY_GAIN)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    im1, im2, m1, _ = (x.to(DEV) for x in synthetic_pair(b, hh, ww, seed=4321))
+    from focusflow_official_b200.host.focusraft import init_point_mask
+
+    mk1, mk2 = init_point_mask(m1, 3)
+    sc = lambda x: 2 * (x / 255.0) - 1.0
+    with torch.no_grad():
+        fnet = model.flow_net.fnet
+        fmap1, fmap2 = fnet(sc(im1), sc(mk1)).float(), fnet(sc(im2), sc(mk2)).float()
+    q = torch.from_numpy(g["queries"]).to(DEV)
+    n = (hh // 8) * (ww // 8)
+    assert float(np.abs(g["coords"][-1] - g["coords"][0]).max()) > 10          # the trajectory really moves
+    for prec, tol in (("fp32", 2e-5), ("fp16", 1e-3), ("tf32", 1e-3), ("bf16x3", 5e-5)):
+        for cl in (False, True):
+            blk = m.CorrBlock(fmap1, fmap2, precision=prec, sampler="cpu", channels_last=cl)
+            worst = 0.0
+            for it in range(iters):
+                out = blk(t(g["coords"][it]))
+                got = out.reshape(b, 324, n)[0].t()[q].cpu().numpy()
+                worst = max(worst, float(np.abs(got - g["lookups"][it]).max() / g["absmax"][it]))
+            print(f"trajectory {prec} channels_last={cl}: worst lookup error {worst:.2e} of max|ref|")
+            assert worst <= tol, (prec, cl, worst)
