@@ -52,6 +52,7 @@ _PROTOS = {
     "ffcorr_volume_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_pwc81_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]),
     "ffcorr_pwc81_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_backwarp_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]),
 }
 SYMBOLS = tuple(_PROTOS)
 

@@ -277,8 +277,20 @@ constexpr int kStreamWarps = 4;
 constexpr int kStreamStages = FFCORR_STREAM_STAGES;
 constexpr int kRowPitch = 20;     // floats per query row: the 16 columns of the 4x4 tile block + 4 (16-byte aligned)
 
+// FFCORR_CP_L2 (development switch): L2 prefetch size hint of the gather's cp.async (0 = none, 64, 128, 256)
+#ifndef FFCORR_CP_L2
+#define FFCORR_CP_L2 0
+#endif
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+#if FFCORR_CP_L2 == 64
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#elif FFCORR_CP_L2 == 128
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#elif FFCORR_CP_L2 == 256
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING>
@@ -407,8 +419,13 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         const int gy = (pk >> 2) & 3;
         goff[j] = min(qj, last_q) * map_elems + base + txi * 16 + gy * 4;    // < 2^31 (host check: 32 maps)
         const unsigned e = (unsigned)pk >> (4 + txi);
-        const unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
-                             (((e >> 12) & 1u) * 0xF000u);
+        unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
+                       (((e >> 12) & 1u) * 0xF000u);
+#ifndef FFCORR_NO_COLUMN_MASK
+        // only the tile columns the window's columns [x_lo & 3, (x_lo & 3) + ncols) reach: the fourth one is needed by a
+        // quarter of the windows only (fetching all four cost 23 % more DRAM sectors)
+        if (txi * 4 >= (pk & 3) + (slow ? W2 : K + 1)) okT = 0;
+#endif
         gmask[j] = ((okT >> gy) & 0xFFFFu) | ((0x8888u >> gy) << 16);
         gdst[j] = (unsigned)(slot_of(qj) * kRowPitch + 4 * txi) * 4u;
     }
@@ -646,8 +663,11 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
         const int gy = (pk >> 2) & 3;
         goff[j] = min(qj, last_q) * map_elems + base + txi * 16 + gy * 4;
         const unsigned e = (unsigned)pk >> (4 + txi);
-        const unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
-                             (((e >> 12) & 1u) * 0xF000u);
+        unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
+                       (((e >> 12) & 1u) * 0xF000u);
+#ifndef FFCORR_NO_COLUMN_MASK
+        if (txi * 4 >= (pk & 3) + (slow ? W2 : K + 1)) okT = 0;       // only the tile columns the window reaches
+#endif
         gmask[j] = ((okT >> gy) & 0xFFFFu) | ((0x8888u >> gy) << 16);
         gnext[j] = p.tw[lj] * 16 - 12;
     }

@@ -5,5 +5,6 @@ repo.  `FocusRAFT` keeps the reference's state_dict key names so `ffraft_*.pth` 
 load unchanged.
 """
 from .focusraft import FocusRAFT, RAFTBody, build_focusraft  # noqa: F401
+from .focuspwc import FocusPWC, backwarp  # noqa: F401
 from .losses import CPCL, EPELoss, MixLoss, build_losses  # noqa: F401
 from .train import TrainStep, parallel_model  # noqa: F401

@@ -20,6 +20,7 @@
  *   ffcorr_pwc81_f32       core/models/ff-pwcnet/PWCNet_Core/correlation.py:278-328
  *                          _FunctionCorrelation.forward (rearrange x2 + updateOutput)
  *   ffcorr_pwc81_bwd_f32   correlation.py:331-380 _FunctionCorrelation.backward
+ *   ffcorr_backwarp_f32    core/models/ff-pwcnet/PWCNet_Core/ff_pwcnet.py:27-46 backwarp (caller side of the PWC op)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching
@@ -213,6 +214,19 @@ int ffcorr_pwc81_f32(const float* one, const float* two, float* out,
 /* gradients of the raw cost volume; either output may be NULL. */
 int ffcorr_pwc81_bwd_f32(const float* one, const float* two, const float* grad_out,
                          float* grad_one, float* grad_two, int B, int C, int H, int W, void* stream);
+
+/*
+ * backwarp of FF-PWC (core/models/ff-pwcnet/PWCNet_Core/ff_pwcnet.py:27-46): the second feature map warped towards
+ * the first by the up-sampled flow, before the correlation of decoder levels 5..2 (ff_pwcnet.py:322-325).
+ *   input : [B, C, H, W];  flow : [B, 2, H, W] (channel 0 = x);  out : [B, C, H, W]
+ *   grid_x[W], grid_y[H] : the pixel-centre grids linspace(-1 + 1/size, 1 - 1/size, size) the reference caches
+ *                          (ff_pwcnet.py:29-31), passed in so that they are bit-identical to torch.linspace
+ *   out = grid_sample(input, grid + flow * flow_scale / ((size-1)/2), bilinear, zeros, align_corners=False)
+ *         * (sum of in-bounds tap weights > 0.999)
+ * One kernel instead of the reference's ~9 (mul, div x2, cat x2, add, permute, grid_sample over C+1 planes, mask, mul).
+ */
+int ffcorr_backwarp_f32(const float* input, const float* flow, const float* grid_x, const float* grid_y, float* out,
+                        int B, int C, int H, int W, float flow_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -275,23 +275,11 @@ TRAIN_FULL_GRADS = ["flow_net.fnet.conv2.bias", "flow_net.update_block.flow_head
                     "flow_net.fnet.fusion5.mask2img.conv.bias", "flow_net.cnet.layer1.0.norm1.weight"]
 
 
-def train_inputs(b, hh, ww, seed):
-    """Inputs of one training step as a pure function of the seed (shared with the tests)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from weights import synthetic_pair
-
-    im1, im2, m1, m2 = synthetic_pair(b, hh, ww, seed=seed)
-    rng = np.random.RandomState(seed + 1)
-    flow = torch.from_numpy((rng.standard_normal((b, 2, hh, ww)) * 3.0).astype(np.float32))
-    valid = torch.from_numpy((rng.uniform(size=(b, hh, ww)) > 0.1).astype(np.float32))
-    return im1, im2, flow, m1, m2, valid
-
-
 def make_train():
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle.reference_loader import load_ff_raft
-    from weights import fill_state_dict
+    from weights import fill_state_dict, train_inputs
 
     model, cfg, ns = load_ff_raft()
     sys.path.insert(0, ns["root"])

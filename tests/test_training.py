@@ -14,18 +14,9 @@ import pytest
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-from weights import fill_state_dict, seeded_coords, seeded_fmaps, synthetic_pair  # noqa: E402
+from weights import fill_state_dict, seeded_coords, seeded_fmaps, train_inputs  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-
-
-def train_inputs(b, hh, ww, seed):
-    """Same as oracle/make_golden.py:train_inputs."""
-    im1, im2, m1, m2 = synthetic_pair(b, hh, ww, seed=seed)
-    rng = np.random.RandomState(seed + 1)
-    flow = torch.from_numpy((rng.standard_normal((b, 2, hh, ww)) * 3.0).astype(np.float32))
-    valid = torch.from_numpy((rng.uniform(size=(b, hh, ww)) > 0.1).astype(np.float32))
-    return im1, im2, flow, m1, m2, valid
 
 
 def host_model(device="cpu"):

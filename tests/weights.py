@@ -16,7 +16,10 @@ DAMPED_GAIN = 0.004    # sub-pixel updates per iteration, like a converged train
 LIVELY_GAIN = 0.05     # ~0.3 low-res px (2.5 full-res px) per iteration: multi-pixel motion, windows far from the grid
 
 
-def fill_state_dict(sd: dict, seed: int = 1234, flow_gain: float = DAMPED_GAIN) -> dict:
+PWC_GAINS = {"netSix.0.weight": 0.1, "netMain.12.weight": 0.1}    # FF-PWC flow heads: keep the coarse-to-fine flow O(1 px)
+
+
+def fill_state_dict(sd: dict, seed: int = 1234, flow_gain: float = DAMPED_GAIN, gains: dict = None) -> dict:
     """In-place, key-wise deterministic fill (kaiming-like scale so activations stay O(1)).
 
     `flow_gain` scales the last conv of the flow head: DAMPED_GAIN keeps the random-init refinement contractive
@@ -39,6 +42,9 @@ def fill_state_dict(sd: dict, seed: int = 1234, flow_gain: float = DAMPED_GAIN) 
             v = rng.randn(*shape) * np.sqrt(2.0 / fan_out)
             if key.endswith("flow_head.conv2.weight"):
                 v = v * flow_gain
+            for suffix, factor in (gains or {}).items():
+                if key.endswith(suffix):
+                    v = v * factor
         elif key.endswith("weight"):  # norm scale
             v = 1.0 + 0.05 * rng.randn(*shape)
         else:  # biases
@@ -80,3 +86,13 @@ def seeded_coords(seed: int, b: int, h: int, w: int, sigma: float, offset: float
     grid = np.repeat(np.stack([xs, ys], 0).astype(np.float32)[None], b, axis=0)
     noise = rng.standard_normal(grid.shape).astype(np.float32) * np.float32(sigma) if sigma else np.float32(0)
     return np.ascontiguousarray(grid + np.float32(offset) + noise, dtype=np.float32)
+
+
+def train_inputs(b: int, hh: int, ww: int, seed: int):
+    """Inputs of one training step (image1, image2, flow_gt, mask1, mask2, valid) as a pure function of the seed; shared
+    by oracle/make_golden.py (reference step), tests/test_training.py and bench.py --config 5."""
+    im1, im2, m1, m2 = synthetic_pair(b, hh, ww, seed=seed)
+    rng = np.random.RandomState(seed + 1)
+    flow = torch.from_numpy((rng.standard_normal((b, 2, hh, ww)) * 3.0).astype(np.float32))
+    valid = torch.from_numpy((rng.uniform(size=(b, hh, ww)) > 0.1).astype(np.float32))
+    return im1, im2, flow, m1, m2, valid

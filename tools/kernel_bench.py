@@ -275,7 +275,12 @@ if __name__ == "__main__":
     ap.add_argument("--stock", action="store_true", help="also time the same ops through stock PyTorch CUDA kernels")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--all-precisions", action="store_true")
+    ap.add_argument("--lib", default=None, help="path of an alternative build of libffcorr.so (kernel variants under test)")
     a = ap.parse_args()
+    if a.lib:
+        from focusflow_official_b200 import _lib as _L
+
+        _L.LIB_PATH = os.path.abspath(a.lib)
     if a.all_precisions:
         for pr in ("fp16", "tf32", "bf16x3"):
             time_kernels(a.config, a.iters, pr, sigma=a.sigma, verbose=True, warmup=a.warmup, smooth=a.smooth,
