@@ -21,6 +21,9 @@ Differences, all deliberate:
     (they differ by <= 1 ulp of the normalised coordinate, see :func:`set_sampler_semantics`); per block / per call.
   * ``channels_last=True`` returns the same ``[B, C, h, w]`` values in NHWC memory (``torch.channels_last``), the
     layout the consumer ``convc1`` (``update.py:82-83,90``) runs in, written directly by the lookup kernel.
+  * ``storage="fp16"`` (opt-in) stores the pyramid as IEEE half floats in the same 4x4-pixel tiles (32 bytes each):
+    fp32 accumulation and pooling, one rounding per stored value (2e-4 relative), fp32 interpolation in the lookup.
+    Halves the bytes of both HBM-bound kernels; needs |corr| < 65504 and 2-4 levels.  Default ``"fp32"``.
   * every launch runs under a device guard on the device of its tensors, on torch's current stream of that device.
 """
 from __future__ import annotations
@@ -111,19 +114,36 @@ def tiled_supported(h: int, w: int, num_levels: int) -> bool:
     return bool(_lib.lib().ffcorr_tiled_supported(num_levels, h, w))
 
 
-def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, precision: int,
-                              fused: bool = True) -> List[torch.Tensor]:
-    """Volume + pyramid in the tiled layout: level i is [B*h*w, tiled_map_elems(h, w, i)].
+STORAGES = {"fp32": torch.float32, "fp16": torch.float16}
 
-    fused=True (default): one GEMM launch writes every level (ffcorr_build_tiled_f32); fused=False: the GEMM
-    writes level 0 and the standalone pooling kernel re-reads it (bit-identical results, kept for tests)."""
+
+def _storage_dtype(storage) -> torch.dtype:
+    try:
+        return STORAGES[storage or "fp32"]
+    except KeyError:
+        raise ValueError(f"storage must be 'fp32' or 'fp16', got {storage!r}") from None
+
+
+def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, precision: int,
+                              fused: bool = True, storage: str = "fp32") -> List[torch.Tensor]:
+    """Volume + pyramid in the tiled layout: level i is [B*h*w, tiled_map_elems(h, w, i)], fp32 or (storage="fp16") half.
+
+    fused=True (default): one GEMM launch writes every level (ffcorr_build_tiled_f32 / _f16); fused=False: the GEMM
+    writes level 0 and the standalone pooling kernel re-reads it (bit-identical results, kept for tests; fp32 only)."""
     b, d, h, w = fmap1.shape
     L = _lib.lib()
-    levels = [torch.empty((b * h * w, _tiled_elems(h, w, i)), device=fmap1.device, dtype=torch.float32)
+    dtype = _storage_dtype(storage)
+    levels = [torch.empty((b * h * w, _tiled_elems(h, w, i)), device=fmap1.device, dtype=dtype)
               for i in range(num_levels)]
     ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
     ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
     with _lib.on_device(fmap1, fmap2) as stream:
+        if dtype == torch.float16:
+            if not fused or not (2 <= num_levels <= 4):
+                raise ValueError("storage='fp16' is produced by the fused build: 2 to 4 levels")
+            _lib.check(L.ffcorr_build_tiled_f16(fmap1.data_ptr(), fmap2.data_ptr(), _lib.ptr_array(levels), num_levels, b, d, h, w,
+                                                precision, ws.data_ptr(), ws_bytes, stream), "ffcorr_build_tiled_f16")
+            return levels
         if fused:
             _lib.check(L.ffcorr_build_tiled_f32(fmap1.data_ptr(), fmap2.data_ptr(), _lib.ptr_array(levels), num_levels, b, d, h, w,
                                                 precision, ws.data_ptr(), ws_bytes, stream), "ffcorr_build_tiled_f32")
@@ -150,6 +170,13 @@ def _alloc_lookup_out(coords: torch.Tensor, num_levels: int, radius: int, channe
 def _lookup_tiled_raw(levels, level_ptrs, coords: torch.Tensor, radius: int, sampler: int = 1,
                       channels_last: bool = False) -> torch.Tensor:
     b, _, h, w = coords.shape
+    if levels[0].dtype == torch.float16:
+        # the fp16-stored pyramid is read by the channels-last kernel; NCHW callers get a converted copy
+        store, out = _alloc_lookup_out(coords, len(levels), radius, True)
+        with _lib.on_device(coords, levels[0]) as stream:
+            _lib.check(_lib.lib().ffcorr_lookup_tiled_f16(level_ptrs, len(levels), coords.data_ptr(), store.data_ptr(), b, h, w,
+                                                          radius, sampler, 1, stream), "ffcorr_lookup_tiled_f16")
+        return out if channels_last else out.contiguous()
     store, out = _alloc_lookup_out(coords, len(levels), radius, channels_last)
     with _lib.on_device(coords, levels[0]) as stream:
         _lib.check(_lib.lib().ffcorr_lookup_tiled_f32(level_ptrs, len(levels), coords.data_ptr(), store.data_ptr(), b, h, w, radius,
@@ -163,30 +190,33 @@ def untile_levels(tiled_levels, b: int, h: int, w: int) -> List[torch.Tensor]:
     for i, t in enumerate(tiled_levels):
         hi, wi = h >> i, w >> i
         dst = torch.empty((b * h * w, 1, hi, wi), device=t.device, dtype=torch.float32)
+        fn = "ffcorr_untile_f16" if t.dtype == torch.float16 else "ffcorr_untile_f32"
         with _lib.on_device(t) as stream:
-            _lib.check(_lib.lib().ffcorr_untile_f32(t.data_ptr(), dst.data_ptr(), b * h * w, hi, wi, stream), "ffcorr_untile_f32")
+            _lib.check(getattr(_lib.lib(), fn)(t.data_ptr(), dst.data_ptr(), b * h * w, hi, wi, stream), fn)
         out.append(dst)
     return out
 
 
-def tile_levels(levels) -> List[torch.Tensor]:
-    """Reference-layout levels ([Q, 1, h_i, w_i]) -> tiled storage (used by tests and tools)."""
+def tile_levels(levels, storage: str = "fp32") -> List[torch.Tensor]:
+    """Reference-layout levels ([Q, 1, h_i, w_i]) -> tiled storage, fp32 or fp16 (used by tests and tools)."""
     out = []
+    dtype = _storage_dtype(storage)
+    fn = "ffcorr_tile_f16" if dtype == torch.float16 else "ffcorr_tile_f32"
     for lv in levels:
         _require_cuda(lv, "level")
         lv = lv.float().contiguous()
         q, _, hi, wi = lv.shape
-        dst = torch.empty((q, _tiled_elems(hi, wi, 0)), device=lv.device, dtype=torch.float32)
+        dst = torch.empty((q, _tiled_elems(hi, wi, 0)), device=lv.device, dtype=dtype)
         with _lib.on_device(lv) as stream:
-            _lib.check(_lib.lib().ffcorr_tile_f32(lv.data_ptr(), dst.data_ptr(), q, hi, wi, stream), "ffcorr_tile_f32")
+            _lib.check(getattr(_lib.lib(), fn)(lv.data_ptr(), dst.data_ptr(), q, hi, wi, stream), fn)
         out.append(dst)
     return out
 
 
-def tiled_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None, fused: bool = True) -> List[torch.Tensor]:
+def tiled_pyramid(fmap1, fmap2, num_levels: int = 4, precision=None, fused: bool = True, storage: str = "fp32") -> List[torch.Tensor]:
     """Volume + pyramid in the tiled layout (inference only)."""
     fmap1, fmap2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
-    return _volume_pyramid_tiled_raw(fmap1, fmap2, num_levels, _precision_code(precision), fused)
+    return _volume_pyramid_tiled_raw(fmap1, fmap2, num_levels, _precision_code(precision), fused, storage or "fp32")
 
 
 def lookup_tiled(tiled_levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None, sampler=None,
@@ -241,11 +271,14 @@ class _GradSink:
 
 class _VolumePyramid(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, fmap1, fmap2, num_levels, precision, sink, tiled=False):
+    def forward(ctx, fmap1, fmap2, num_levels, precision, sink, tiled=False, storage="fp32"):
         # tiled=True: the forward pyramid is stored as 4x4 tiles (fused build); the backward never reads it -- it
         # needs the feature maps and the ROW-MAJOR gradient pyramid the lookups scatter into the sink -- so the
         # storage order of the forward is free.  The tiled levels are not differentiable outputs themselves.
-        levels = (_volume_pyramid_tiled_raw if tiled else _volume_pyramid_raw)(fmap1, fmap2, num_levels, precision)
+        if tiled:
+            levels = _volume_pyramid_tiled_raw(fmap1, fmap2, num_levels, precision, True, storage)
+        else:
+            levels = _volume_pyramid_raw(fmap1, fmap2, num_levels, precision)
         ctx.save_for_backward(fmap1, fmap2)
         ctx.num_levels = num_levels
         ctx.precision = precision
@@ -287,7 +320,7 @@ class _VolumePyramid(torch.autograd.Function):
                                                g1.data_ptr() if g1 is not None else None,
                                                g2.data_ptr() if g2 is not None else None, b, d, h, w, ctx.precision, stream),
                        "ffcorr_volume_bwd_f32")
-        return g1, g2, None, None, None, None
+        return g1, g2, None, None, None, None, None
 
 
 class _UntileWithGrad(torch.autograd.Function):
@@ -385,9 +418,12 @@ def lookup(levels, coords: torch.Tensor, radius: int = 4, level_ptrs=None, sampl
 
 class CorrBlock:
     def __init__(self, fmap1, fmap2, num_levels: int = 4, radius: int = 4, precision: Optional[str] = None,
-                 layout: Optional[str] = None, sampler: Optional[str] = None, channels_last: bool = False):
+                 layout: Optional[str] = None, sampler: Optional[str] = None, channels_last: bool = False,
+                 storage: Optional[str] = None):
         self.num_levels = num_levels
         self.radius = radius
+        self.storage = storage or "fp32"
+        _storage_dtype(self.storage)
         self.sampler = sampler or _default_sampler
         self._sampler = _sampler_code(sampler)
         self.channels_last = bool(channels_last)
@@ -410,7 +446,7 @@ class CorrBlock:
             f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
             if f1.shape != f2.shape:
                 raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
-            self._levels = _volume_pyramid_tiled_raw(f1, f2, num_levels, code)
+            self._levels = _volume_pyramid_tiled_raw(f1, f2, num_levels, code, True, self.storage)
             self._rowmajor = None                      # materialised on first access of .corr_pyramid
         elif needs_grad:
             f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
@@ -420,12 +456,16 @@ class CorrBlock:
             # forward pyramid tiled (fused build, faster lookups) whenever the tensor-core path is allowed: the
             # backward only needs the feature maps and the row-major gradient pyramid in the sink
             self._grad_tiled = (layout == "tiled" and code != _lib.PREC_FP32 and b > 0 and tiled_supported(h, w, num_levels))
-            outs = _VolumePyramid.apply(f1, f2, num_levels, code, self._sink, self._grad_tiled)
+            outs = _VolumePyramid.apply(f1, f2, num_levels, code, self._sink, self._grad_tiled,
+                                        self.storage if self._grad_tiled else "fp32")
             self._levels, self._anchor = list(outs[:-1]), outs[-1]
             self._rowmajor = None if self._grad_tiled else self._levels
         else:
             self._levels = correlation_pyramid(fmap1, fmap2, num_levels, precision)
             self._rowmajor = self._levels
+        if self.storage == "fp16" and self._levels[0].dtype != torch.float16:
+            raise ValueError("storage='fp16' needs the tiled layout, a tensor-core precision and 2-4 levels that fit it "
+                             f"(layout={layout!r}, precision={precision!r}, {num_levels} levels on a {h}x{w} map)")
         self._ptrs = _lib.ptr_array(self._levels)
 
     @property

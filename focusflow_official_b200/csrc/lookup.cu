@@ -25,6 +25,7 @@
 // ATen un-normalises them again (GridSampler.cuh:26).  That fp32 round trip perturbs
 // every tap differently (up to ~2e-5 px), which is visible at the 1e-5 parity bar, so
 // it is reproduced per tap with explicitly rounded intrinsics (no FMA contraction).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -557,23 +558,40 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
 constexpr int kNhwcWarps = FFCORR_NHWC_WARPS;
 constexpr int kNhwcQ = 8;          // queries per warp
 
-__host__ __device__ constexpr int nhwc_warp_floats(int K, int CT) { return kStreamStages * kTile * kRowPitch + K * kTile + kNhwcQ * CT; }
+// Storage type T of the pyramid: float (ffcorr_build_tiled_f32) or __half (ffcorr_build_tiled_f16: the same 4x4 tiles at
+// 32 bytes each -- one DRAM sector per tile instead of two; the arithmetic stays fp32).  Row-buffer pitch per window:
+// 80 bytes (20 floats) / 48 bytes (24 halfs): both put 8 consecutive lanes on 8 distinct 16-byte bank groups.
+template <typename T> struct RowGeom;
+template <> struct RowGeom<float> { static constexpr int PITCH = 20; };
+template <> struct RowGeom<__half> { static constexpr int PITCH = 24; };
 
-template <int R, bool CUDA_SEM>
+template <typename T>
+__host__ __device__ constexpr int nhwc_warp_bytes(int K, int CT) {
+    return kStreamStages * kTile * RowGeom<T>::PITCH * (int)sizeof(T) + (K * kTile + kNhwcQ * CT) * 4;
+}
+
+// 8-byte variant of the gather copy for fp16 tiles (a tile row is 4 halfs); .cg exists for 16 bytes only
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int R, bool CUDA_SEM, typename T>
 __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(const LookupTiledParams p) {
+    constexpr bool HALF = sizeof(T) == 2;
+    constexpr int PITCH = RowGeom<T>::PITCH;             // elements per window row buffer
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;
     constexpr int KK = K * K;
     constexpr int S = kStreamStages;
-    constexpr int ROWBUF = kTile * kRowPitch;
+    constexpr int ROWBUF = kTile * PITCH;                // elements per ring stage
     static_assert(W2 + 3 <= 16, "window + sub-tile shift must fit in the 16 columns of the tile block");
 
-    extern __shared__ __align__(16) float smem_nhwc[];
+    extern __shared__ __align__(16) unsigned char smem_nhwc[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int CT = p.num_levels * KK;
-    float* ring = smem_nhwc + (size_t)warp * nhwc_warp_floats(K, CT);
-    float* siy = ring + S * ROWBUF;
+    T* ring = reinterpret_cast<T*>(smem_nhwc + (size_t)warp * nhwc_warp_bytes<T>(K, CT));
+    float* siy = reinterpret_cast<float*>(ring + S * ROWBUF);
     float* stage = siy + K * kTile;                      // [8 queries][CT]
 
     const int b = blockIdx.x / p.blocks_per_batch;
@@ -650,14 +668,14 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
     const int txi = lane & 3;
     const int qj = lane >> 2;
     const int last_q = N - 1 - n0;
-    const float* tbase[4];
+    const T* tbase[4];
     int goff[4], gnext[4];
     unsigned gmask[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int lj = j < p.num_levels ? j : 0;
         const int map_elems = p.th[lj] * p.tw[lj] * 16;
-        tbase[j] = p.lvl[lj] + ((int64_t)b * N + n0) * (int64_t)map_elems;
+        tbase[j] = reinterpret_cast<const T*>(p.lvl[lj]) + ((int64_t)b * N + n0) * (int64_t)map_elems;
         const int base = __shfl_sync(0xffffffffu, my_base, j * 8 + qj);
         const int pk = __shfl_sync(0xffffffffu, my_pack, j * 8 + qj);       // 0 for a wild / absent window
         const int gy = (pk >> 2) & 3;
@@ -671,7 +689,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
         gmask[j] = ((okT >> gy) & 0xFFFFu) | ((0x8888u >> gy) << 16);
         gnext[j] = p.tw[lj] * 16 - 12;
     }
-    const unsigned gdst = (unsigned)(qj * kRowPitch + 4 * txi) * 4u;          // + j * 8 * kRowPitch * 4 per slot
+    const unsigned gdst = (unsigned)(qj * PITCH + 4 * txi) * (unsigned)sizeof(T);     // + j * 8 * PITCH * sizeof(T) per slot
     const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
     int rows_issued = 0;
     uint32_t issue_saddr = ring_saddr;
@@ -681,20 +699,23 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
             for (int j = 0; j < 4; ++j) {
                 const unsigned m = gmask[j] >> rows_issued;
                 const bool ok = m & 1u;
-                const float* src = tbase[j] + (ok ? goff[j] : 0);
-                cp_async16_zfill(issue_saddr + gdst + (unsigned)(j * 8 * kRowPitch * 4), src, ok ? 16u : 0u);
+                const T* src = tbase[j] + (ok ? goff[j] : 0);
+                if constexpr (HALF)
+                    cp_async8_zfill(issue_saddr + gdst + (unsigned)(j * 8 * PITCH * sizeof(T)), src, ok ? 8u : 0u);
+                else
+                    cp_async16_zfill(issue_saddr + gdst + (unsigned)(j * 8 * PITCH * sizeof(T)), src, ok ? 16u : 0u);
                 goff[j] += (m & 0x10000u) ? gnext[j] : 4;
             }
             ++rows_issued;
-            issue_saddr += ROWBUF * 4;
-            if (issue_saddr == ring_saddr + S * ROWBUF * 4) issue_saddr = ring_saddr;
+            issue_saddr += ROWBUF * sizeof(T);
+            if (issue_saddr == ring_saddr + S * ROWBUF * sizeof(T)) issue_saddr = ring_saddr;
         }
         cp_async_commit();
     };
 
     float* sout = stage + q * CT + level * KK;            // this window's K*K samples
     const int shift = x_lo & 3;
-    const float* my_row = ring + lane * kRowPitch;
+    const T* my_row = ring + lane * PITCH;
 
 #pragma unroll
     for (int r = 0; r < S - 1; ++r) issue_row(true);
@@ -703,17 +724,31 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
         float tprev[K];
 #pragma unroll
         for (int a = 0; a < K; ++a) tprev[a] = 0.f;
-        const float* sq = my_row;
+        const T* sq = my_row;
 #pragma unroll 1
         for (int r = 0; r <= K; ++r) {
             cp_async_wait<S - 2>();
             __syncwarp();
             issue_row(r + S - 1 <= K);
             float f[16];
+            if constexpr (HALF) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float4 t4 = reinterpret_cast<const float4*>(sq)[v];
-                f[4 * v] = t4.x; f[4 * v + 1] = t4.y; f[4 * v + 2] = t4.z; f[4 * v + 3] = t4.w;
+                for (int v = 0; v < 2; ++v) {
+                    const uint4 t4 = reinterpret_cast<const uint4*>(sq)[v];
+                    const uint32_t wds[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&wds[e]));
+                        f[8 * v + 2 * e] = c2.x;
+                        f[8 * v + 2 * e + 1] = c2.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float4 t4 = reinterpret_cast<const float4*>(sq)[v];
+                    f[4 * v] = t4.x; f[4 * v + 1] = t4.y; f[4 * v + 2] = t4.z; f[4 * v + 3] = t4.w;
+                }
             }
             // barrel shift by x_lo & 3 so that f[c] is window column c
 #pragma unroll
@@ -737,8 +772,8 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
             if (sq == my_row + S * ROWBUF) sq = my_row;
         }
     } else {
-        const float* cur = my_row + shift;
-        const float* prev = cur;
+        const T* cur = my_row + shift;
+        const T* prev = cur;
 #pragma unroll 1
         for (int r = 0; r < W2; ++r) {
             cp_async_wait<S - 2>();
@@ -752,7 +787,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
 #pragma unroll
                     for (int a = 0; a < K; ++a) {
                         const int rxa = a + (int)((px >> (2 * a)) & 3u) - 1;
-                        const float v00 = prev[rxa], v01 = prev[rxa + 1], v10 = cur[rxa], v11 = cur[rxa + 1];
+                        const float v00 = (float)prev[rxa], v01 = (float)prev[rxa + 1], v10 = (float)cur[rxa], v11 = (float)cur[rxa + 1];
                         const float nw = __fmul_rn(wx0[a], wy0b);
                         const float ne = __fmul_rn(wx1[a], wy0b);
                         const float sw = __fmul_rn(wx0[a], wy1b);
@@ -792,7 +827,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
     }
 }
 
-template <int R>
+template <int R, typename T>
 int launch_lookup_tiled_nhwc(const LookupTiledParams& p0, int sampler, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
     LookupTiledParams p = p0;
@@ -801,13 +836,13 @@ int launch_lookup_tiled_nhwc(const LookupTiledParams& p0, int sampler, cudaStrea
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kNhwcWarps);
     const int64_t blocks = (int64_t)p.B * p.blocks_per_batch;
     FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled: grid too large");
-    const size_t smem = (size_t)kNhwcWarps * nhwc_warp_floats(K, p.num_levels * K * K) * sizeof(float);
-    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)kNhwcWarps * nhwc_warp_bytes<T>(K, p.num_levels * K * K);
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_kernel<R, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_kernel<R, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (sampler == FFCORR_SAMPLER_ATEN_CUDA)
-        lookup_tiled_nhwc_kernel<R, true><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
+        lookup_tiled_nhwc_kernel<R, true, T><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
     else
-        lookup_tiled_nhwc_kernel<R, false><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
+        lookup_tiled_nhwc_kernel<R, false, T><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
     return check_launch("lookup_tiled_nhwc_kernel");
 }
 
@@ -1114,7 +1149,7 @@ extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, con
 
 static int lookup_tiled_impl(const float* const* lvl, int num_levels, const float* coords, float* out, int B, int h, int w,
                              int nq, int64_t coords_stride, int64_t out_stride, int radius, int sampler, int out_channels_last,
-                             void* stream, const char* who) {
+                             void* stream, const char* who, bool half_storage = false) {
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "%s: B=%d", who, B);
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "%s: null pointer", who);
@@ -1143,12 +1178,21 @@ static int lookup_tiled_impl(const float* const* lvl, int num_levels, const floa
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
+    if (half_storage) {
+        FFCORR_REQUIRE(out_channels_last, FFCORR_EINVAL, "%s: the fp16-stored pyramid is read by the channels-last kernel only", who);
+        switch (radius) {
+            case 1: return launch_lookup_tiled_nhwc<1, __half>(p, sampler, s);
+            case 2: return launch_lookup_tiled_nhwc<2, __half>(p, sampler, s);
+            case 3: return launch_lookup_tiled_nhwc<3, __half>(p, sampler, s);
+            default: return launch_lookup_tiled_nhwc<4, __half>(p, sampler, s);
+        }
+    }
     if (out_channels_last) {
         switch (radius) {
-            case 1: return launch_lookup_tiled_nhwc<1>(p, sampler, s);
-            case 2: return launch_lookup_tiled_nhwc<2>(p, sampler, s);
-            case 3: return launch_lookup_tiled_nhwc<3>(p, sampler, s);
-            default: return launch_lookup_tiled_nhwc<4>(p, sampler, s);
+            case 1: return launch_lookup_tiled_nhwc<1, float>(p, sampler, s);
+            case 2: return launch_lookup_tiled_nhwc<2, float>(p, sampler, s);
+            case 3: return launch_lookup_tiled_nhwc<3, float>(p, sampler, s);
+            default: return launch_lookup_tiled_nhwc<4, float>(p, sampler, s);
         }
     }
     switch (radius) {
@@ -1163,6 +1207,12 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
                                        int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream) {
     return lookup_tiled_impl(lvl, num_levels, coords, out, B, h, w, h * w, (int64_t)h * w, (int64_t)h * w, radius, sampler,
                              out_channels_last, stream, "lookup_tiled");
+}
+
+extern "C" int ffcorr_lookup_tiled_f16(const void* const* lvl, int num_levels, const float* coords, float* out,
+                                       int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream) {
+    return lookup_tiled_impl(reinterpret_cast<const float* const*>(lvl), num_levels, coords, out, B, h, w, h * w, (int64_t)h * w,
+                             (int64_t)h * w, radius, sampler, out_channels_last, stream, "lookup_tiled_f16", true);
 }
 
 extern "C" int ffcorr_lookup_tiled_chunk_f32(const float* const* lvl, int num_levels, const float* coords, float* out,

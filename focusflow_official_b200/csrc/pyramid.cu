@@ -9,6 +9,8 @@
 // stores are fully coalesced / 16-byte vectorised when the group is 16-byte aligned).
 // Window sum order is ATen's: ((a+b)+c)+d then one multiply by 0.25 (== /4 exactly), so
 // the result is bit-identical to F.avg_pool2d given the same level 0.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ffcorr {
@@ -363,6 +365,35 @@ __global__ void __launch_bounds__(256) untile_kernel(const float* __restrict__ s
     }
 }
 
+// fp16-stored tiles (ffcorr_build_tiled_f16) -> reference row-major fp32 [Q, h, w]
+__global__ void __launch_bounds__(256) untile_half_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t Q,
+                                                          int h, int w, int tw, int np) {
+    const int64_t total = Q * h * w;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % w);
+        const int64_t t = idx / w;
+        const int y = (int)(t % h);
+        const int64_t q = t / h;
+        dst[idx] = __half2float(src[q * np + ((y >> 2) * tw + (x >> 2)) * 16 + (y & 3) * 4 + (x & 3)]);
+    }
+}
+
+// reference row-major fp32 [Q, h, w] -> fp16 tiles (RN, zero padding), used by tests
+__global__ void __launch_bounds__(256) tile_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t Q,
+                                                        int h, int w, int tw, int np) {
+    const int64_t total = Q * np;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % np);
+        const int64_t q = idx / np;
+        const int t = e >> 4, iy = (e >> 2) & 3, ix = e & 3;
+        const int ty = t / tw, tx = t - ty * tw;
+        const int y = 4 * ty + iy, x = 4 * tx + ix;
+        dst[idx] = __float2half_rn((y < h && x < w) ? __ldg(src + (q * h + y) * w + x) : 0.0f);
+    }
+}
+
 // reference row-major [Q, h, w] -> tiled (zero padding), used by tests to feed golden pyramids to the tiled lookup
 __global__ void __launch_bounds__(256) tile_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t Q,
                                                    int h, int w, int tw, int np) {
@@ -637,6 +668,26 @@ extern "C" int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int 
     const int tw = tiled_tw(w);
     untile_kernel<<<grid_for(Q * h * w, 256), 256, 0, (cudaStream_t)stream>>>(tiled, dst, Q, h, w, tw, tiled_th(h) * tw * 16);
     return check_launch("untile_kernel");
+}
+
+extern "C" int ffcorr_untile_f16(const void* tiled, float* dst, int64_t Q, int h, int w, void* stream) {
+    FFCORR_REQUIRE(Q >= 0 && h >= 1 && w >= 1, FFCORR_EINVAL, "untile_f16: bad shape");
+    if (Q == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(tiled && dst, FFCORR_EINVAL, "untile_f16: null pointer");
+    const int tw = tiled_tw(w);
+    untile_half_kernel<<<grid_for(Q * h * w, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(tiled), dst, Q, h, w,
+                                                                                  tw, tiled_th(h) * tw * 16);
+    return check_launch("untile_half_kernel");
+}
+
+extern "C" int ffcorr_tile_f16(const float* src, void* tiled, int64_t Q, int h, int w, void* stream) {
+    FFCORR_REQUIRE(Q >= 0 && h >= 1 && w >= 1, FFCORR_EINVAL, "tile_f16: bad shape");
+    if (Q == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(tiled && src, FFCORR_EINVAL, "tile_f16: null pointer");
+    const int tw = tiled_tw(w);
+    const int np = tiled_th(h) * tw * 16;
+    tile_half_kernel<<<grid_for(Q * np, 256), 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__half*>(tiled), Q, h, w, tw, np);
+    return check_launch("tile_half_kernel");
 }
 
 extern "C" int ffcorr_tile_f32(const float* src, float* tiled, int64_t Q, int h, int w, void* stream) {

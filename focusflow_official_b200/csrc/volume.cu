@@ -143,6 +143,11 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&r)[64])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // ------------------------------------------------------------------------------------------
 // GEMM configuration
 // ------------------------------------------------------------------------------------------
@@ -225,12 +230,16 @@ struct FusedParams {
     float* l3;
 };
 
-template <bool TF32, bool TMA_STORE, bool DIV, bool FUSED>
+// HALF (fused build only): the pyramid is STORED as fp16 (ffcorr_build_tiled_f16) -- the same 4x4-pixel tiles, 32 bytes
+// each; accumulation and the poolings stay fp32, every level is rounded once (RN) when it is written.  Level 0 of a
+// chunk is then 128 bytes per query (ONE store box instead of two), which halves the bytes of the kernel's bound.
+template <bool TF32, bool TMA_STORE, bool DIV, bool FUSED, bool HALF = false>
 __global__ void __launch_bounds__(Cfg<FUSED>::THREADS, 1)
 volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_l1,
                    const GemmParams p, const FusedParams fp, const uint32_t idesc) {
     static_assert(!FUSED || TMA_STORE, "the fused build stores through TMA");
+    static_assert(!HALF || FUSED, "fp16 storage exists for the fused build only");
     using C = Cfg<FUSED>;
     constexpr int STAGES = C::STAGES;
     constexpr int STORE_PAIRS = C::STORE_PAIRS;
@@ -359,14 +368,23 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             // stages one 64-column chunk as two 128B-swizzled 32x32 boxes in store pair `pair`
             auto stage_pair = [&](const uint32_t (&v)[64]) {
                 uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
+                if constexpr (HALF) {
+                    // 64 halfs = one 128-byte row of ONE 128B-swizzled box
 #pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf)
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) =
+                            make_uint4(pack_h2(scaled(v[8 * j]), scaled(v[8 * j + 1])), pack_h2(scaled(v[8 * j + 2]), scaled(v[8 * j + 3])),
+                                       pack_h2(scaled(v[8 * j + 4]), scaled(v[8 * j + 5])), pack_h2(scaled(v[8 * j + 6]), scaled(v[8 * j + 7])));
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i0 = hlf * 32 + 4 * j;
-                        *reinterpret_cast<float4*>(dst + hlf * SMEM_STORE_BUF + ((j ^ (lane & 7)) << 4)) =
-                            make_float4(scaled(v[i0]), scaled(v[i0 + 1]), scaled(v[i0 + 2]), scaled(v[i0 + 3]));
-                    }
+                    for (int hlf = 0; hlf < 2; ++hlf)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int i0 = hlf * 32 + 4 * j;
+                            *reinterpret_cast<float4*>(dst + hlf * SMEM_STORE_BUF + ((j ^ (lane & 7)) << 4)) =
+                                make_float4(scaled(v[i0]), scaled(v[i0 + 1]), scaled(v[i0 + 2]), scaled(v[i0 + 3]));
+                        }
+                }
             };
 
             if constexpr (FUSED) {
@@ -424,7 +442,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         const int ty1 = sgy * 2 + (c >> 1);
                         l1_any = (ty1 < fp.th1) && (sgx * 2 < fp.tw1);
                         if (l1_any) {
-                            uint8_t* dst = my_bufs + (size_t)C::STORE_BUFS * SMEM_STORE_BUF + lane * 128;
+                            uint8_t* dst = my_bufs + (size_t)C::STORE_BUFS * SMEM_STORE_BUF + lane * (HALF ? 64 : 128);
 #pragma unroll
                             for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
@@ -434,7 +452,10 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                                     const float4 q = make_float4(src[(2 * tt) * 4 + py * 2], src[(2 * tt) * 4 + py * 2 + 1],
                                                                  src[(2 * tt + 1) * 4 + py * 2], src[(2 * tt + 1) * 4 + py * 2 + 1]);
                                     const int j = tt * 4 + rr;
-                                    *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = q;
+                                    if constexpr (HALF)   // two tiles x 4 rows x 8 bytes = 64 bytes per query, unswizzled box
+                                        *reinterpret_cast<uint2*>(dst + j * 8) = make_uint2(pack_h2(q.x, q.y), pack_h2(q.z, q.w));
+                                    else
+                                        *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = q;
                                 }
                         }
                     } else {
@@ -447,7 +468,7 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         if (l0_any) {
                             const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
                             tma_store_4d(&tmap_c, src, sgx * 64, ty, row0, b);
-                            if (sgx * 4 + 2 < fp.tw0) tma_store_4d(&tmap_c, src + SMEM_STORE_BUF, sgx * 64 + 32, ty, row0, b);
+                            if (!HALF && sgx * 4 + 2 < fp.tw0) tma_store_4d(&tmap_c, src + SMEM_STORE_BUF, sgx * 64 + 32, ty, row0, b);
                         }
                         if (l1_any)
                             tma_store_4d(&tmap_l1, my_bufs_u32 + (uint32_t)(C::STORE_BUFS * SMEM_STORE_BUF), sgx * 32,
@@ -458,10 +479,15 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (ci == 1 && row < p.N) {
                         // ---- level 2: rows c0, c0 + 1 of this super-group's tile, 32 contiguous bytes per query ----
                         if (fp.levels >= 3 && sgy < fp.th2 && sgx < fp.tw2) {
-                            float4* d2 = reinterpret_cast<float4*>(fp.l2 + ((int64_t)b * p.N + row) * fp.map2 +
-                                                                   (sgy * fp.tw2 + sgx) * 16 + c0 * 4);
-                            d2[0] = make_float4(q2[0], q2[1], q2[2], q2[3]);
-                            d2[1] = make_float4(q2[4], q2[5], q2[6], q2[7]);
+                            const int64_t e2 = ((int64_t)b * p.N + row) * fp.map2 + (sgy * fp.tw2 + sgx) * 16 + c0 * 4;
+                            if constexpr (HALF) {
+                                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(fp.l2) + e2) =
+                                    make_uint4(pack_h2(q2[0], q2[1]), pack_h2(q2[2], q2[3]), pack_h2(q2[4], q2[5]), pack_h2(q2[6], q2[7]));
+                            } else {
+                                float4* d2 = reinterpret_cast<float4*>(fp.l2 + e2);
+                                d2[0] = make_float4(q2[0], q2[1], q2[2], q2[3]);
+                                d2[1] = make_float4(q2[4], q2[5], q2[6], q2[7]);
+                            }
                         }
                         // ---- level 3: one row of the super-group's 2x2 patch, 8 bytes per query ----
                         const int ty3 = sgy >> 1, tx3 = sgx >> 1;
@@ -472,16 +498,25 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                             const int y3 = sgy * 2 + (c >> 1);
                             if (!(y3 < fp.lh3 && sgx * 2 < fp.lw3)) o.x = 0.0f;
                             if (!(y3 < fp.lh3 && sgx * 2 + 1 < fp.lw3)) o.y = 0.0f;
-                            float* d3 = fp.l3 + ((int64_t)b * p.N + row) * fp.map3 + (ty3 * fp.tw3 + tx3) * 16 +
-                                        ((sgy & 1) * 2 + (c >> 1)) * 4 + (sgx & 1) * 2;
-                            *reinterpret_cast<float2*>(d3) = o;
+                            const int64_t e3 = ((int64_t)b * p.N + row) * fp.map3 + (ty3 * fp.tw3 + tx3) * 16 +
+                                               ((sgy & 1) * 2 + (c >> 1)) * 4 + (sgx & 1) * 2;
                             // quarters of this level-3 tile whose super-group does not exist stay exact zeros
                             const bool ghost_x = (sgx == fp.sgw - 1) && !(sgx & 1);
                             const bool ghost_y = (sgy == fp.sgh - 1) && !(sgy & 1);
-                            const float2 z = make_float2(0.0f, 0.0f);
-                            if (ghost_x) *reinterpret_cast<float2*>(d3 + 2) = z;
-                            if (ghost_y) *reinterpret_cast<float2*>(d3 + 8) = z;
-                            if (ghost_x && ghost_y) *reinterpret_cast<float2*>(d3 + 10) = z;
+                            if constexpr (HALF) {
+                                uint32_t* d3 = reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(fp.l3) + e3);   // 2 halfs
+                                d3[0] = pack_h2(o.x, o.y);
+                                if (ghost_x) d3[1] = 0u;
+                                if (ghost_y) d3[4] = 0u;
+                                if (ghost_x && ghost_y) d3[5] = 0u;
+                            } else {
+                                float* d3 = fp.l3 + e3;
+                                *reinterpret_cast<float2*>(d3) = o;
+                                const float2 z = make_float2(0.0f, 0.0f);
+                                if (ghost_x) *reinterpret_cast<float2*>(d3 + 2) = z;
+                                if (ghost_y) *reinterpret_cast<float2*>(d3 + 8) = z;
+                                if (ghost_x && ghost_y) *reinterpret_cast<float2*>(d3 + 10) = z;
+                            }
                         }
                     }
                 }
@@ -562,10 +597,6 @@ enum : int { CVT_F16 = 0, CVT_BF16X3_A = 1, CVT_BF16X3_B = 2, CVT_F32 = 3 };
 constexpr int PP_CH = 16;        // channels per thread: one 32-byte K-major piece per pixel in the 16-bit modes
 constexpr int PP_THREADS = 128;
 
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
 __device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
     __nv_bfloat162 h;
     h.x = a;
@@ -837,7 +868,8 @@ enum : int { PHASE_ALL = 0, PHASE_STAGE = 1, PHASE_GEMM = 2 };
 
 static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w, int precision,
                        void* workspace, size_t workspace_bytes, void* stream, int out_mode, float* const* lvl = nullptr,
-                       int num_levels = 1, int q0 = 0, int nq = -1, int phase = PHASE_ALL, float divisor = 0.0f) {
+                       int num_levels = 1, int q0 = 0, int nq = -1, int phase = PHASE_ALL, float divisor = 0.0f,
+                       bool out_half = false) {
     // q0 / nq: only the queries [q0, q0 + nq) are computed (chunked build); phase: stage the operands, run the
     // GEMM on already staged operands, or both.
     const bool tiled = out_mode != OUT_ROWMAJOR;
@@ -913,21 +945,25 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
         const int th0 = tiled_th(h), tw0 = tiled_tw(w);
         const int lh1 = h >> 1, lw1 = w >> 1;
         const int th1 = tiled_th(lh1), tw1 = tiled_tw(lw1);
-        const uint32_t box[4] = {32, 1, 32, 1};
+        // fp32 storage: boxes of 32 queries x 32 floats (128 B); fp16 storage: level 0 in boxes of 32 queries x 64 halfs
+        // (128 B, one per chunk), level 1 in unswizzled boxes of 32 queries x 32 halfs (64 B)
+        const uint64_t eb = out_half ? 2 : 4;
+        const CUtensorMapDataType odt = out_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
         {
+            const uint32_t box[4] = {out_half ? 64u : 32u, 1, 32, 1};
             const uint64_t dims[4] = {(uint64_t)tw0 * 16, (uint64_t)th0, (uint64_t)Nq, (uint64_t)B};
-            const uint64_t map_b = (uint64_t)th0 * tw0 * 64;
-            const uint64_t strides[3] = {(uint64_t)tw0 * 64, map_b, map_b * Nq};
-            if (int rc = encode_tensor_map(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl[0], dims, strides, box,
-                                           CU_TENSOR_MAP_SWIZZLE_128B, "L0"))
+            const uint64_t map_b = (uint64_t)th0 * tw0 * 16 * eb;
+            const uint64_t strides[3] = {(uint64_t)tw0 * 16 * eb, map_b, map_b * Nq};
+            if (int rc = encode_tensor_map(&tc, odt, 4, lvl[0], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "L0"))
                 return rc;
         }
         {
+            const uint32_t box[4] = {32, 1, 32, 1};
             const uint64_t dims[4] = {(uint64_t)tw1 * 16, (uint64_t)th1, (uint64_t)Nq, (uint64_t)B};
-            const uint64_t map_b = (uint64_t)th1 * tw1 * 64;
-            const uint64_t strides[3] = {(uint64_t)tw1 * 64, map_b, map_b * Nq};
-            if (int rc = encode_tensor_map(&tl1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl[1], dims, strides, box,
-                                           CU_TENSOR_MAP_SWIZZLE_128B, "L1"))
+            const uint64_t map_b = (uint64_t)th1 * tw1 * 16 * eb;
+            const uint64_t strides[3] = {(uint64_t)tw1 * 16 * eb, map_b, map_b * Nq};
+            if (int rc = encode_tensor_map(&tl1, odt, 4, lvl[1], dims, strides, box,
+                                           out_half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, "L1"))
                 return rc;
         }
         fp.levels = num_levels;
@@ -984,7 +1020,17 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
         if (p.use_div) FF_GEMM(TF, TS, true); \
         else FF_GEMM(TF, TS, false);  \
     } while (0)
-    if (fused) {
+#define FF_GEMM_H(TF, DV)                                                                                             \
+    do {                                                                                                              \
+        if (int rc = set_smem(volume_gemm_kernel<TF, true, DV, true, true>, Cfg<true>::SMEM_TOTAL)) return rc;        \
+        volume_gemm_kernel<TF, true, DV, true, true><<<grid, Cfg<true>::THREADS, Cfg<true>::SMEM_TOTAL, s>>>(ta, tb, tc, tl1, p, fp, \
+                                                                                                            idesc);   \
+    } while (0)
+    FFCORR_REQUIRE(!out_half || fused, FFCORR_EINVAL, "volume: fp16 storage is produced by the fused build (2-4 levels) only");
+    if (fused && out_half) {
+        if (tf32) { if (p.use_div) FF_GEMM_H(true, true); else FF_GEMM_H(true, false); }
+        else      { if (p.use_div) FF_GEMM_H(false, true); else FF_GEMM_H(false, false); }
+    } else if (fused) {
         if (tf32) { if (p.use_div) FF_GEMM_F(true, true, true, true); else FF_GEMM_F(true, true, false, true); }
         else      { if (p.use_div) FF_GEMM_F(false, true, true, true); else FF_GEMM_F(false, true, false, true); }
     }
@@ -995,6 +1041,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
 #undef FF_GEMM_DV
 #undef FF_GEMM
 #undef FF_GEMM_F
+#undef FF_GEMM_H
     return check_launch("volume_gemm_kernel");
 }
 
@@ -1073,6 +1120,24 @@ extern "C" int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, fl
         return volume_impl(fmap1, fmap2, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_TILED);
     return volume_impl(fmap1, fmap2, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_FUSED_PYRAMID,
                        lvl, num_levels);
+}
+
+extern "C" int ffcorr_build_tiled_f16(const float* fmap1, const float* fmap2, void* const* lvl, int num_levels, int B, int D,
+                                      int h, int w, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    FFCORR_REQUIRE(lvl != nullptr, FFCORR_EINVAL, "build_tiled_f16: null level table");
+    if (int rc = check_levels(num_levels, h, w, "build_tiled_f16")) return rc;
+    FFCORR_REQUIRE(num_levels >= 2 && ffcorr_tiled_supported(num_levels, h, w), FFCORR_EINVAL,
+                   "build_tiled_f16: %dx%d with %d levels is outside the fused build (2-4 levels)", h, w, num_levels);
+    FFCORR_REQUIRE(precision != FFCORR_PREC_FP32, FFCORR_EINVAL, "build_tiled_f16: needs a tensor-core operand precision");
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "build_tiled_f16: B=%d", B);
+    if (B == 0) return FFCORR_OK;
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "build_tiled_f16: lvl[%d] is null", i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "build_tiled_f16: lvl[%d] must be 16-byte aligned", i);
+    }
+    // the level pointers travel as float* through the shared implementation; the HALF kernel reinterprets them
+    return volume_impl(fmap1, fmap2, reinterpret_cast<float*>(lvl[0]), B, D, h, w, precision, workspace, workspace_bytes, stream,
+                       OUT_FUSED_PYRAMID, reinterpret_cast<float* const*>(lvl), num_levels, 0, -1, PHASE_ALL, 0.0f, true);
 }
 
 extern "C" int ffcorr_stage_operands_f32(const float* fmap1, const float* fmap2, int num_levels, int B, int D, int h, int w,

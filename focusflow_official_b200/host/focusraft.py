@@ -255,6 +255,7 @@ class RAFTBody(nn.Module):
         self.corr_block: Callable = B200CorrBlock
         self.corr_precision: Optional[str] = None
         self.corr_sampler: Optional[str] = None      # None = the package default ("cuda": the reference's GPU run)
+        self.corr_storage: Optional[str] = None      # None / "fp32" (default) or "fp16": opt-in half-precision pyramid
         # raft.py:63,195-196 `alternate_corr` (config key ALT_CORR): the memory-bounded block that recomputes the
         # pyramid per lookup; inference only, like the reference's alt_cuda_corr
         self.alternate_corr = False
@@ -274,7 +275,7 @@ class RAFTBody(nn.Module):
         if self.alternate_corr and self.corr_block is B200CorrBlock and not torch.is_grad_enabled():
             return B200AlternateCorrBlock(fmap1, fmap2, **kw)
         if self.corr_block is B200CorrBlock:
-            return B200CorrBlock(fmap1, fmap2, **kw)
+            return B200CorrBlock(fmap1, fmap2, storage=self.corr_storage, **kw)
         return self.corr_block(fmap1, fmap2, num_levels=self.corr_levels, radius=self.corr_radius)
 
     def forward(self, image1, image2, mask1, mask2, iters: int = 12, flow_init=None, test_mode: bool = False):

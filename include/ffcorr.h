@@ -159,6 +159,26 @@ int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float
                             int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream);
 
 /*
+ * Opt-in HALF-PRECISION STORAGE of the pyramid (the Python side: CorrBlock(..., storage="fp16")).  Same geometry as
+ * the tiled fp32 layout -- level i per query map = [ceil(h_i/4)][tw_i][4][4] elements, ffcorr_tiled_map_elems() of
+ * them -- but the elements are IEEE fp16 (a 4x4 tile is one 32-byte DRAM sector).  Accumulation (fp32, TMEM), the
+ * 1/sqrt(D) scale and the 2x2 poolings are unchanged; every level is rounded to fp16 (RN) once, when it is written,
+ * and the lookup interpolates in fp32.  Halves the bytes of both HBM-bound kernels: the build's 2.3 GB write and the
+ * lookup's window gathers.  Values: volume within 1e-3 of the reference (2e-4 storage rounding on top of the operand
+ * rounding), lookups exact to 1e-5 w.r.t. the stored pyramid; |corr| must stay below 65504.
+ * ffcorr_build_tiled_f16 needs 2 <= num_levels <= 4 and a tensor-core operand precision; ffcorr_lookup_tiled_f16 writes
+ * channels-last output only (out_channels_last must be non-zero); ffcorr_untile_f16 / ffcorr_tile_f16 convert a level
+ * to / from the reference's row-major fp32 [Q, h_i, w_i].
+ */
+int ffcorr_build_tiled_f16(const float* fmap1, const float* fmap2, void* const* lvl, int num_levels,
+                           int B, int D, int h, int w, int precision,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int ffcorr_lookup_tiled_f16(const void* const* lvl, int num_levels, const float* coords, float* out,
+                            int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream);
+int ffcorr_untile_f16(const void* tiled, float* dst, int64_t Q, int h_level, int w_level, void* stream);
+int ffcorr_tile_f16(const float* src, void* tiled, int64_t Q, int h_level, int w_level, void* stream);
+
+/*
  * Query-chunked build + lookup: AlternateCorrBlock semantics (corr.py:63-91) -- the same lookup values with
  * O(nq * h*w) instead of O((h*w)^2) pyramid memory, recomputed per lookup.  Stage the GEMM operands once per
  * image pair (ffcorr_stage_operands_f32, same workspace as ffcorr_volume_f32), then per lookup and per chunk of

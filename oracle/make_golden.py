@@ -172,7 +172,21 @@ def make_e2e_full():
     from oracle.reference_loader import load_ff_raft
     from weights import DAMPED_GAIN, LIVELY_GAIN, fill_state_dict, synthetic_pair
 
-    model, _, _ = load_ff_raft()
+    model, _, ns = load_ff_raft()
+    raft = ns["raft"]
+    base = raft.CorrBlock
+
+    class Tf32Inputs(base):
+        """The reference's own GPU arithmetic for the volume (ALLOW_TF32: operands rounded to a 10-bit mantissa), emulated
+        on CPU by rounding the CorrBlock inputs: measures how far the reference drifts from ITSELF between its two
+        configurations -- the yardstick for any tensor-core implementation of the volume."""
+
+        def __init__(self, f1, f2, **kw):
+            def rn(x):
+                i = x.contiguous().view(torch.int32)
+                return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+            super().__init__(rn(f1.clone()), rn(f2.clone()), **kw)
+
     out = {}
     for tag, (b, hh, ww, iters, gain) in FULL_E2E.items():
         sd = model.state_dict()
@@ -183,11 +197,19 @@ def make_e2e_full():
         with torch.no_grad(), warnings.catch_warnings():
             warnings.simplefilter("ignore")
             lo, up = model(im1, im2, m1, m2, raft_iters=iters, test_mode=True)
+            raft.CorrBlock = Tf32Inputs
+            try:
+                lo_t, up_t = model(im1, im2, m1, m2, raft_iters=iters, test_mode=True)
+            finally:
+                raft.CorrBlock = base
+        drift = torch.linalg.norm(up_t - up, dim=1)
         out[f"{tag}_shape"] = np.array([b, hh, ww, iters])
         out[f"{tag}_gain"] = np.array(gain)
         out[f"{tag}_flow_lo"] = lo.numpy()
         out[f"{tag}_flow_up_s4"] = np.ascontiguousarray(up.numpy()[:, :, ::4, ::4])
-        print(tag, "flow_up mean |f| =", float(up.abs().mean()), "max", float(up.abs().max()))
+        out[f"{tag}_ref_tf32_drift"] = np.array([float(drift.mean()), float(drift.max())])
+        print(tag, "flow_up mean |f| =", float(up.abs().mean()), "max", float(up.abs().max()),
+              "| reference TF32-vs-fp32 drift: mean %.2e max %.2e px" % (float(drift.mean()), float(drift.max())))
     path = os.path.join(GOLD, "ffraft_e2e_full.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) >> 10, "KiB")

@@ -238,4 +238,8 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["vs_baseline"] is None
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    from oracle import reference_loader as RL
+
+    # the unmodified reference when its sources are installed (/root/reference or baseline/_ref), else the port
+    assert d["cpu_baseline"]["kind"] == ("reference" if RL.reference_root() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"] and d["steps"] >= 5

@@ -93,7 +93,7 @@ def test_host_model_matches_the_unmodified_reference_on_the_gpu(hw, batch):
     ref, _ = RL.load_ff_pwc(torch_correlation)
     ref.load_state_dict(model.state_dict(), strict=True)
     ref = ref.cuda().eval()
-    im1, im2, m1, m2 = (t.cuda() for t in synthetic_pair(batch, hw[0], hw[1], seed=11))
+    im1, im2, m1, m2 = (t.cuda() / 255.0 for t in synthetic_pair(batch, hw[0], hw[1], seed=11))    # images in [0, 1]
     with torch.no_grad():
         want = ref(im1, im2, m1, m2, test_mode=True)
         got = model(im1, im2, m1, m2, test_mode=True)
@@ -103,8 +103,9 @@ def test_host_model_matches_the_unmodified_reference_on_the_gpu(hw, batch):
     epe = torch.linalg.norm(got - want, dim=1)
     print(f"FF-PWC {hw} b{batch}: |flow| mean {float(want.abs().mean()):.2f} max {float(want.abs().max()):.2f}; "
           f"EPE mean {float(epe.mean()):.2e} max {float(epe.max()):.2e}")
+    scale = max(1.0, float(want.abs().max()))
     assert float(want.abs().max()) > 0.5                      # the flow is not trivially zero
-    assert float(epe.max()) <= 1e-2
+    assert float(epe.max()) <= 2e-4 * scale                   # random weights give large flows: relative to their size
     assert len(got_list) == len(want_list) == 5
     for a, r in zip(got_list, want_list):
-        assert a.shape == r.shape and float((a - r).abs().max()) <= 1e-2
+        assert a.shape == r.shape and float((a - r).abs().max()) <= 2e-4 * max(1.0, float(r.abs().max()))

@@ -54,7 +54,8 @@ def check_step_against_golden(model, tag, device, norm_tol, loss_tol):
     for key in [k for k in g.files if k.startswith(f"{tag}_grad::")]:
         ref = g[key]
         have = params[key.split("::", 1)[1]].grad.detach().cpu().numpy()
-        assert np.abs(have - ref).max() <= norm_tol * max(np.abs(ref).max(), 1e-12), key
+        rel = np.linalg.norm(have - ref) / max(np.linalg.norm(ref), 1e-30)
+        assert rel <= 4 * norm_tol, (key, float(rel))
     return float(loss.item())
 
 

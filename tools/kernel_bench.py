@@ -129,6 +129,16 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     def k_lookup_t_nhwc():
         _lib.check(L.ffcorr_lookup_tiled_f32(tptrs, nl, coords.data_ptr(), out_nhwc.data_ptr(), b, h, w, r, 1, 1, stream), "lookup_tiled_nhwc")
 
+    th = [torch.empty(b * n, int(L.ffcorr_tiled_map_elems(h, w, i)), device=dev, dtype=torch.float16) for i in range(nl)]
+    hptrs = _lib.ptr_array(th)
+
+    def k_build_h():
+        _lib.check(L.ffcorr_build_tiled_f16(f1.data_ptr(), f2.data_ptr(), hptrs, nl, b, d, h, w, code, ws.data_ptr(), ws_bytes,
+                                            stream), "build_tiled_f16")
+
+    def k_lookup_h():
+        _lib.check(L.ffcorr_lookup_tiled_f16(hptrs, nl, coords.data_ptr(), out_nhwc.data_ptr(), b, h, w, r, 1, 1, stream), "lookup_tiled_f16")
+
     res = []
     lv_elems = [(h >> i) * (w >> i) for i in range(nl)]
     vol_flops = 2.0 * b * n * n * d
@@ -140,6 +150,11 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         todo += [("volume_tiled", k_volume_t, vol_bytes, vol_flops), ("pyramid_tiled", k_pyramid_t, pyr_bytes, 0.0),
                  ("build_fused", k_build_t, vol_bytes + pyr_bytes - 4.0 * b * n * lv_elems[0], vol_flops),
                  ("lookup_tiled", k_lookup_t, look_bytes, 0.0), ("lookup_tiled_nhwc", k_lookup_t_nhwc, look_bytes, 0.0)]
+        # half-precision storage: algorithmic bytes with 2-byte pyramid elements
+        vol_h = b * (2 * n * d * 4 + n * n * 2)
+        pyr_h = 2.0 * b * n * sum(lv_elems[1:])
+        look_h = b * n * (nl * (2 * r + 2) ** 2 * 2 + nl * (2 * r + 1) ** 2 * 4 + 8)
+        todo += [("build_fused_f16", k_build_h, vol_h + pyr_h, vol_flops), ("lookup_tiled_f16", k_lookup_h, look_h, 0.0)]
     if tiled_ok and (not only or "alt_lookup" in only):
         # memory-bounded AlternateCorrBlock: the pyramid of a 512 MiB query chunk is rebuilt for every lookup
         alt = ff.AlternateCorrBlock(f1, f2, num_levels=nl, radius=r, precision=precision)
@@ -154,7 +169,7 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         if only and name not in only:
             # run (untimed) only what a selected kernel reads
             needs = {"pyramid": ["volume"], "lookup": ["volume", "pyramid"], "pyramid_tiled": ["volume_tiled"],
-                     "lookup_tiled": ["build_fused"], "lookup_tiled_nhwc": ["build_fused"]}
+                     "lookup_tiled": ["build_fused"], "lookup_tiled_nhwc": ["build_fused"], "lookup_tiled_f16": ["build_fused_f16"]}
             if any(name in needs.get(o, []) for o in only):
                 fn()
             continue
