@@ -26,6 +26,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ffcorr {
@@ -210,7 +212,30 @@ struct GemmParams {
     int row_offset;       // first A row (query) of this launch: the chunked build computes rows [row_offset, row_offset + N)
     int out_transposed;   // non-TMA epilogue: write C^T, i.e. out[b][col][row] with row pitch ldc (backward GEMMs)
     int64_t ldc;
+    const uint32_t* amax_bits;   // fp16 operands: bit patterns of max|fmap1[b]| at [b], max|fmap2[b]| at [B + b]; else null
 };
+
+// Power-of-two block scaling of the fp16 operands (one exponent per batch item and operand).  The pre-pass multiplies a
+// feature map by 2^-k with k chosen so that its largest magnitude lands in [2^13, 2^14) -- inside fp16's range whatever
+// the activations' scale (|x| up to ~1e33 or down to ~1e-25) -- and the GEMM epilogue multiplies the accumulator by
+// 2^(k1 + k2).  Both are exact, so for data that was in range anyway the result is unchanged except that values that
+// used to fall into fp16's subnormals now keep their 10 bits.
+__host__ __device__ __forceinline__ int scale_exponent(uint32_t amax_bits) {
+    const int e = (int)((amax_bits >> 23) & 0xffu);
+    if (e == 0 || e == 255) return 0;                 // zero / subnormal / inf / nan: leave the data alone
+    const int k = (e - 127) - 13;
+    return k < -96 ? -96 : (k > 96 ? 96 : k);
+}
+__host__ __device__ __forceinline__ float exp2i(int k) {   // 2^k for k in [-126, 127]
+    k = k < -126 ? -126 : (k > 127 ? 127 : k);
+#ifdef __CUDA_ARCH__
+    return __int_as_float((127 + k) << 23);
+#else
+    union { uint32_t u; float f; } c;
+    c.u = (uint32_t)(127 + k) << 23;
+    return c.f;
+#endif
+}
 
 // Fused pyramid build (ffcorr_build_tiled_f32): the GEMM's N order is made of 16x16-pixel SUPER-GROUPS
 // (4x4 tiles of 4x4 pixels; one 256-column UMMA tile each), chunk c of the epilogue = tile row c of the
@@ -358,11 +383,16 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             const int row0 = m0 + quarter * 32;
+            // undo the operands' block scaling (fp16 mode): an exact power of two per batch item
+            float unscale = 1.0f;
+            if (p.amax_bits != nullptr)
+                unscale = exp2i(scale_exponent(__ldg(p.amax_bits + b)) + scale_exponent(__ldg(p.amax_bits + p.B + b)));
+            const float mul = DIV ? unscale : p.scale * unscale;
             // raw accumulators -> volume values, in place (fp32 bit patterns stay in the same registers)
             auto scale_chunk = [&](uint32_t (&v)[64]) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
-                    v[i] = __float_as_uint(DIV ? __fdiv_rn(__uint_as_float(v[i]), p.divisor) : __uint_as_float(v[i]) * p.scale);
+                    v[i] = __float_as_uint(DIV ? __fdiv_rn(__uint_as_float(v[i]) * mul, p.divisor) : __uint_as_float(v[i]) * mul);
             };
             auto scaled = [](uint32_t bits) { return __uint_as_float(bits); };
             // stages one 64-column chunk as two 128B-swizzled 32x32 boxes in store pair `pair`
@@ -620,11 +650,34 @@ struct TiledB {
     int np;        // padded pixel count = rows of the staged operand
 };
 
+// max |x| of every feature map (batch item x operand) as a float bit pattern (monotonic for non-negative floats):
+// amax_bits[which * B + b].  The maps were just written by the encoder, so most of this read hits L2.
+__global__ void __launch_bounds__(256) operand_amax_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                           uint32_t* __restrict__ amax_bits, int B, int64_t per_item) {
+    const int which = blockIdx.y / B, b = blockIdx.y - which * B;
+    const float* __restrict__ in = (which == 0 ? f1 : f2) + (int64_t)b * per_item;
+    uint32_t m = 0;
+    const bool vec = (per_item & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    if (vec) {
+        const float4* in4 = reinterpret_cast<const float4*>(in);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_item / 4; i += (int64_t)gridDim.x * blockDim.x) {
+            const float4 v = __ldg(in4 + i);
+            m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_item; i += (int64_t)gridDim.x * blockDim.x)
+            m = max(m, __float_as_uint(fabsf(__ldg(in + i))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(amax_bits + blockIdx.y, m);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(PP_THREADS) operand_prepass_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                                                                      void* __restrict__ o1, void* __restrict__ o2,
                                                                      int B, int D, int N, int Dp /* padded K per segment */,
-                                                                     const TiledB tb) {
+                                                                     const TiledB tb, const uint32_t* __restrict__ amax_bits = nullptr) {
     const int which = blockIdx.z / B;          // 0: fmap1 (A operand), 1: fmap2 (B operand)
     const int b = blockIdx.z - which * B;
     const float* __restrict__ in = (which == 0 ? f1 : f2) + (size_t)b * D * N;
@@ -653,6 +706,8 @@ __global__ void __launch_bounds__(PP_THREADS) operand_prepass_kernel(const float
         lim = (y < tb.h) ? tb.w - x : 0;
     }
     const bool vec_ok = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (!tiled || (tb.w & 3) == 0);
+    // fp16 mode: exact power-of-two block scaling into fp16's range (see scale_exponent)
+    const float pre = (MODE == CVT_F16 && amax_bits != nullptr) ? exp2i(-scale_exponent(__ldg(amax_bits + which * B + b))) : 1.0f;
 
     float4 v[PP_CH];                           // v[k] = channel d0 + k at the 4 pixels
 #pragma unroll
@@ -677,7 +732,10 @@ __global__ void __launch_bounds__(PP_THREADS) operand_prepass_kernel(const float
         if (j >= rows) break;
         float x[PP_CH];
 #pragma unroll
-        for (int k = 0; k < PP_CH; ++k) x[k] = j == 0 ? v[k].x : (j == 1 ? v[k].y : (j == 2 ? v[k].z : v[k].w));
+        for (int k = 0; k < PP_CH; ++k) {
+            x[k] = j == 0 ? v[k].x : (j == 1 ? v[k].y : (j == 2 ? v[k].z : v[k].w));
+            if (MODE == CVT_F16) x[k] *= pre;
+        }
         const size_t row = (size_t)b * Nout + n + j;
         if (MODE == CVT_F16) {
             __half* o = reinterpret_cast<__half*>(outp) + row * Dp + d0;
@@ -860,7 +918,8 @@ extern "C" size_t ffcorr_volume_workspace_bytes(int B, int D, int h, int w, int 
     const size_t Np = align_up((size_t)h, 16) * align_up((size_t)w, 16); // >= h*w; covers the tiled and super-group orders too
     const size_t Dp = align_up((size_t)D, pi.k_align);
     const size_t one = align_up((size_t)B * Np * Dp * pi.k_mult * pi.elem_bytes, 256);
-    return 2 * one;
+    // fp16 operands: + the block-scaling exponents' source, max|fmap| per batch item and operand (2*B words)
+    return 2 * one + (precision == FFCORR_PREC_FP16 ? align_up((size_t)2 * B * sizeof(uint32_t), 256) : 0);
 }
 
 enum : int { OUT_ROWMAJOR = 0, OUT_TILED = 1, OUT_FUSED_PYRAMID = 2 };
@@ -903,8 +962,11 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     const int Dp = (int)align_up((size_t)D, pi.k_align);
     const int Kt = Dp * pi.k_mult;  // total K in elements
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const size_t amax_bytes = precision == FFCORR_PREC_FP16 ? align_up((size_t)2 * B * sizeof(uint32_t), 256) : 0;
+    const size_t one_op = (need - amax_bytes) / 2;
     void* opA = ws;
-    void* opB = ws + need / 2;
+    void* opB = ws + one_op;
+    uint32_t* amax_bits = amax_bytes ? reinterpret_cast<uint32_t*>(ws + 2 * one_op) : nullptr;
 
     // ---- 1. operand pre-pass ----
     TiledB tlb{};
@@ -918,8 +980,14 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
         // rows of the larger operand in groups of 4 per thread; row-major A (N rows) and B (Ncols >= N rows) share the grid
         dim3 grid(ceil_div(ceil_div(Ncols > N ? Ncols : N, 4), PP_THREADS), Dp / PP_CH, 2 * B);
         FFCORR_REQUIRE(grid.y < 65536 && grid.z < 65536, FFCORR_EINVAL, "volume: pre-pass grid too large");
-        if (precision == FFCORR_PREC_FP16)
-            operand_prepass_kernel<CVT_F16><<<grid, PP_THREADS, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
+        if (precision == FFCORR_PREC_FP16) {
+            FFCORR_CUDA(cudaMemsetAsync(amax_bits, 0, (size_t)2 * B * sizeof(uint32_t), s));
+            const int64_t per_item = (int64_t)D * N;
+            const int bx = (int)std::min<int64_t>(ceil_div64(per_item, 256 * 4 * 4), 64);
+            operand_amax_kernel<<<dim3((unsigned)bx, (unsigned)(2 * B)), 256, 0, s>>>(fmap1, fmap2, amax_bits, B, per_item);
+            if (int rc = check_launch("operand_amax_kernel")) return rc;
+            operand_prepass_kernel<CVT_F16><<<grid, PP_THREADS, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb, amax_bits);
+        }
         else if (precision == FFCORR_PREC_TF32)
             operand_prepass_kernel<CVT_F32><<<grid, PP_THREADS, 0, s>>>(fmap1, fmap2, opA, opB, B, D, N, Dp, tlb);
         else
@@ -1002,6 +1070,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
     p.use_div = (mant == 0.5f) ? 0 : 1;  // sqrt(D) a power of two -> exact reciprocal multiply
     p.scale = 1.0f / sqrt_d;
     p.out = lvl0;
+    p.amax_bits = amax_bits;
     // instruction descriptor: D=f32, A/B format, K-major both, N>>3, M>>4
     const uint32_t fmt = tf32 ? 2u : (precision == FFCORR_PREC_FP16 ? 0u : 1u);
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);

@@ -7,7 +7,14 @@
   9x9 bilinear window lookup of ``cost_maps [B*h*w, heads, h, w]`` -> ``[B, heads*81, h, w]``; the same tap order and
   ``bilinear_sampler`` as RAFT's ``CorrBlock.__call__``.
 
-Both run the kernels of :mod:`focusflow_official_b200.corr`; inference only.
+* ``reverse_cost_tokens(cost_maps, coords0, coords1)``  <- ``ReverseCostExtractor.forward`` (``decoder.py:119-149``):
+  every query's cost map is re-sampled at ``coords1`` (one bilinear sample per target position, which turns the maps
+  "query -> targets" into maps "position -> queries"), then a 9x9 window around ``coords0`` is read from those.  The
+  first step is a bilinear blend of four ROWS of the transposed volume, so the whole operation is four window lookups
+  on the transposed cost maps (the map index comes from the four taps of ``coords1``) blended with the tap weights.
+
+All run the kernels of :mod:`focusflow_official_b200.corr`; inference only.  Pinned by ``tests/golden/flowformer_ops.npz``:
+outputs of the reference's own functions (``oracle/make_golden_flowformer.py``).
 """
 from __future__ import annotations
 
@@ -61,3 +68,42 @@ def encode_flow_token(cost_maps: torch.Tensor, coords: torch.Tensor, radius: int
         lv = [cost_maps[:, j:j + 1].detach().float().contiguous()]
         outs.append(_lookup_raw(lv, _lib.ptr_array(lv), coords, radius))
     return torch.cat(outs, dim=1).view(b, heads * k2, h1, w1)
+
+
+def _align_corners_taps(coord: torch.Tensor, size: int):
+    """Source index and corner weights of ``bilinear_sampler`` (``utils.py``: x -> 2x/(size-1) - 1 -> grid_sample with
+    align_corners=True un-normalising ((g+1)/2)*(size-1)), fp32 step by step like ATen's CUDA kernel."""
+    sm1 = float(size - 1)
+    g = 2 * coord / sm1 - 1
+    ix = ((g + 1) / 2) * sm1
+    i0 = torch.floor(ix)
+    return i0.long(), (i0 + 1) - ix, ix - i0
+
+
+def reverse_cost_tokens(cost_maps: torch.Tensor, coords0: torch.Tensor, coords1: torch.Tensor, radius: int = 4) -> torch.Tensor:
+    """``ReverseCostExtractor.forward`` (``decoder.py:119-149``): ``[B, heads*81, h, w]``."""
+    _require_cuda(cost_maps, "cost_maps")
+    b, two, h, w = coords1.shape
+    q, heads, h2, w2 = cost_maps.shape
+    if two != 2 or coords0.shape != coords1.shape or q != b * h * w or (h2, w2) != (h, w):
+        raise ValueError(f"cost_maps {tuple(cost_maps.shape)} / coords {tuple(coords0.shape)}, {tuple(coords1.shape)} do not match")
+    n = h * w
+    k2 = (2 * radius + 1) ** 2
+    # maps "target position -> queries": the volume transposed per batch item and head, [B*N(j), heads, h, w] over p
+    ct = cost_maps.detach().float().view(b, n, heads, n).permute(0, 3, 2, 1).contiguous().view(b * n, heads, h, w)
+    c1 = coords1.detach().float()
+    ix0, wx0, wx1 = _align_corners_taps(c1[:, 0], w)          # [B, h, w]
+    iy0, wy0, wy1 = _align_corners_taps(c1[:, 1], h)
+    base = (torch.arange(b, device=ct.device) * n).view(b, 1, 1)
+    c0 = coords0.detach().float().contiguous()
+    out = None
+    for dy, wy in ((0, wy0), (1, wy1)):
+        for dx, wx in ((0, wx0), (1, wx1)):
+            jx, jy = ix0 + dx, iy0 + dy
+            ok = (jx >= 0) & (jx < w) & (jy >= 0) & (jy < h)            # zeros padding: the tap contributes nothing outside
+            idx = (base + jy.clamp(0, h - 1) * w + jx.clamp(0, w - 1)).view(-1)
+            maps = ct.index_select(0, idx)                              # the re-sampled row of the transposed volume
+            tok = encode_flow_token(maps, c0, radius)                   # [B, heads*81, h, w]
+            wgt = (wx * wy * ok).view(b, 1, h, w)
+            out = tok * wgt if out is None else out + tok * wgt
+    return out.view(b, heads * k2, h, w)

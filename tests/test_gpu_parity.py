@@ -1162,3 +1162,54 @@ def test_fp16_storage_end_to_end_and_full_size():
     bq = m.CorrBlock(f1, f2, channels_last=True, storage="fp16")(coords)
     assert float((a - bq).abs().max()) <= 1e-3 * float(a.abs().max())      # one fp16 rounding of every stored value
     assert float((a - bq).norm() / a.norm()) <= 3e-4
+
+
+@pytest.mark.parametrize("scale1,scale2", [(1e5, 1e5), (1e-6, 1e-6), (3e7, 2e-7), (1e15, 1e-3), (4.4, 4.4)])
+@pytest.mark.parametrize("layout", ["tiled", "rowmajor"])
+def test_fp16_operands_are_block_scaled_into_range(scale1, scale2, layout):
+    """fp16 operands used to need |fmap| < 65504 (1e5 became inf, 1e-6 flushed to zero).  The
+    pre-pass now scales every feature map by an exact power of two into fp16's range (one exponent per batch item and
+    operand, from max|fmap|) and the GEMM epilogue undoes it: the volume keeps the 1e-3 bar for activations of any
+    magnitude, also when the two maps -- or the items of a batch -- differ by 20 orders of magnitude."""
+    m = ff()
+    rng = np.random.default_rng(3)
+    b, d, h, w = 2, 64, 16, 24
+    f1 = (rng.standard_normal((b, d, h, w)) * scale1).astype(np.float32)
+    f2 = (rng.standard_normal((b, d, h, w)) * scale2).astype(np.float32)
+    f1[1] *= np.float32(1e-3)                      # per-item exponents: the second pair lives 3 decades lower
+    ref = co.volume_f64(f1, f2)
+    blk = m.CorrBlock(t(f1), t(f2), precision="fp16", layout=layout)
+    got = blk.corr_pyramid[0][:, 0].cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    n = h * w
+    for item in range(b):
+        sl = slice(item * n, (item + 1) * n)
+        assert rel_fro(got[sl], ref[sl]) <= 1e-3, (item, rel_fro(got[sl], ref[sl]))
+    # and the pooled levels / a lookup stay finite and consistent with the volume
+    out = blk(m.coords_grid(b, h, w, DEV) + 0.4)
+    assert torch.isfinite(out).all()
+
+
+# ---------------------------------------------------------------- FlowFormer operations against the reference's own functions
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_flowformer_ops_against_reference_golden(tag):
+    """tests/golden/flowformer_ops.npz = outputs of the UNMODIFIED MemoryEncoder.corr (encoder.py:337-348),
+    MemoryDecoder.encode_flow_token (decoder.py:185-203) and ReverseCostExtractor.forward (decoder.py:119-149), run on CPU
+    by oracle/make_golden_flowformer.py.  cost volume <= 1e-3 (tensor-core operands) / 2e-6 (fp32); the two lookups
+    <= 1e-5 of max|ref| on the reference's own cost maps."""
+    from focusflow_official_b200 import flowformer as fl
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "flowformer_ops.npz"))
+    b, dim, h, w, heads = [int(v) for v in g[f"{tag}_shape"]]
+    f1, f2 = t(g[f"{tag}_fmap1"]), t(g[f"{tag}_fmap2"])
+    ref_cost = g[f"{tag}_cost"]
+    for prec, tol in (("fp16", 1e-3), ("tf32", 1e-3), ("fp32", 2e-6)):
+        got = fl.cost_volume(f1, f2, heads=heads, precision=prec).cpu().numpy()
+        assert got.shape == ref_cost.shape and rel_fro(got, ref_cost) <= tol, (prec, rel_fro(got, ref_cost))
+    cost_maps = t(ref_cost).permute(0, 2, 3, 1, 4, 5).reshape(b * h * w, heads, h, w).contiguous()
+    c0, c1 = t(g[f"{tag}_coords0"]), t(g[f"{tag}_coords1"])
+    tok = fl.encode_flow_token(cost_maps, c1).cpu().numpy()
+    assert tok.shape == g[f"{tag}_flow_token"].shape and max_rel(tok, g[f"{tag}_flow_token"]) <= 1e-5
+    rev = fl.reverse_cost_tokens(cost_maps, c0, c1).cpu().numpy()
+    assert rev.shape == g[f"{tag}_reverse"].shape
+    assert max_rel(rev, g[f"{tag}_reverse"]) <= 1e-5, max_rel(rev, g[f"{tag}_reverse"])

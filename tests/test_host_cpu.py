@@ -83,7 +83,8 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert L.ffcorr_lookup_f32(ptrs, 4, 1, 1, 1, 4, 4, 4, 1, 0, None) == -1    # map too small for 4 levels
     assert L.ffcorr_pyramid_f32(ptrs, 99, 1, 8, 8, None) == -1
     assert L.ffcorr_volume_f32(1, 1, 1, 1, 0, 8, 8, 0, None, 0, None) == -1    # D = 0
-    assert L.ffcorr_volume_workspace_bytes(8, 256, 47, 156, 0) == 2 * 8 * (48 * 160) * 256 * 2  # padded to 16x16 super-groups
+    assert L.ffcorr_volume_workspace_bytes(8, 256, 47, 156, 0) == 2 * 8 * (48 * 160) * 256 * 2 + 256  # padded to 16x16 super-groups; + the fp16 block-scaling words
+    assert L.ffcorr_volume_workspace_bytes(8, 256, 47, 156, 3) == 2 * 8 * (48 * 160) * 256 * 4        # tf32: fp32 operands, no scaling
     # tiled geometry: 4x4 tiles, even number of tiles per row
     assert L.ffcorr_tiled_map_elems(47, 156, 0) == 12 * 40 * 16
     assert L.ffcorr_tiled_map_elems(47, 156, 1) == 6 * 20 * 16
