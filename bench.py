@@ -398,7 +398,7 @@ def build_roofline(build_ms, b, tiled, peaks, h=None, w=None, storage_bytes=4):
     gbs = algo / (build_ms * 1e-3) / 1e9
     flops = 2.0 * b * n * n * d
     tf = flops / (build_ms * 1e-3) / 1e12
-    out = {"kernels": "operand_prepass + volume_gemm (pyramid fused in the epilogue)" if tiled
+    out = {"kernels": "operand_amax + operand_prepass + volume_gemm (pyramid fused in the epilogue)" if tiled
            else "operand_prepass + volume_gemm + pyramid", "algorithmic_bytes": int(algo), "ms": round(build_ms, 4),
            "achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4),
            "flops": flops, "tflops": round(tf, 1), "tensor_frac": round(tf / peaks["bf16_tflops"], 4),
@@ -418,6 +418,7 @@ class LaunchMeter:
         self.enabled = False
         self.tiled = False
         self.nhwc = False
+        self.storage_bytes = 4
 
     def install(self):
         from focusflow_official_b200 import corr as C
@@ -437,15 +438,15 @@ class LaunchMeter:
             meter.launches += 1
             return out
 
-        def build(f1, f2, nl, prec):
+        def build(f1, f2, nl, prec, *a, **k):
             if not meter.enabled:
-                return raw_build(f1, f2, nl, prec)
+                return raw_build(f1, f2, nl, prec, *a, **k)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = raw_build(f1, f2, nl, prec)
+            out = raw_build(f1, f2, nl, prec, *a, **k)
             e1.record()
             meter.build_events.append((e0, e1))
-            meter.launches += 3 if prec != 1 else 2  # operand pre-pass + GEMM + pyramid
+            meter.launches += {0: 4, 1: 2}.get(prec, 3)  # [amax +] operand pre-pass + GEMM + pyramid (fp32: SGEMM + pyramid)
             return out
 
         def lookup_t(*a, **k):
@@ -461,15 +462,17 @@ class LaunchMeter:
             meter.nhwc = bool(out.dim() == 4 and out.stride(1) == 1 and out.shape[1] > 1)
             return out
 
-        def build_t(f1, f2, nl, prec):
+        def build_t(f1, f2, nl, prec, *a, **k):
             if not meter.enabled:
-                return raw_build_t(f1, f2, nl, prec)
+                return raw_build_t(f1, f2, nl, prec, *a, **k)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = raw_build_t(f1, f2, nl, prec)
+            out = raw_build_t(f1, f2, nl, prec, *a, **k)
             e1.record()
             meter.build_events.append((e0, e1))
-            meter.launches += 2  # operand pre-pass + GEMM with the pyramid fused into its epilogue
+            # [max|fmap| for the fp16 block scaling +] operand pre-pass + GEMM with the pyramid fused into its epilogue
+            meter.launches += 3 if prec == 0 else 2
+            meter.storage_bytes = out[0].element_size()
             return out
 
         C._lookup_raw, C._volume_pyramid_raw = lookup, build
@@ -667,7 +670,8 @@ def run_gpu_arm(args, rank, world, local):
 
     h8, w8 = PH // 8, W // 8
     n_query = sub_batches[0] * h8 * w8
-    algo_bytes = n_query * LOOKUP_BYTES_PER_QUERY
+    # SURVEY 8d per-query bytes; with the opt-in fp16 storage the window reads are 2-byte elements
+    algo_bytes = n_query * (LOOKUP_BYTES_PER_QUERY if meter.storage_bytes == 4 else 4 * 100 * 2 + 324 * 4 + 8)
     achieved = algo_bytes / (lookup_ms * 1e-3) / 1e9 if lookup_ms else None
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "lookup_traffic.json")
@@ -721,7 +725,7 @@ def run_gpu_arm(args, rank, world, local):
         except Exception as exc:  # keep the GPU numbers even if the CPU arm fails
             cpu = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "none", "sample": f"failed: {exc}"}
 
-    build = build_roofline(build_ms, sub_batches[0], meter.tiled, peaks, h8, w8)
+    build = build_roofline(build_ms, sub_batches[0], meter.tiled, peaks, h8, w8, meter.storage_bytes)
     storage = getattr(model.flow_net, "corr_storage", None) or "fp32"
     line = {
         "metric": wl["metric"], "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -827,6 +827,288 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Channels-last lookup of the fp16-STORED pyramid (ffcorr_build_tiled_f16): row-PAIR streaming.
+// A 4x4 tile of halfs is 32 bytes = one DRAM sector; its rows (r, r+1) for even r are 16 contiguous bytes, so the
+// gather moves TWO window rows per cp.async.cg 16 (the 8-byte copy a single row needs exists only as cp.async.ca, which
+// allocates in L1 and ran at 84 us; this kernel: half the copy instructions of the fp32 one, L2-only).  Ring stage per
+// window = 4 tile columns x 16 bytes (+16 pad -> 80-byte pitch, conflict-free 16-byte reads).  A window's first row may
+// be the odd row of its pair (y_lo & 1), so a lane evaluates window row 2s - (y_lo & 1) + rho at pair-step s, rho = 0, 1.
+// Work decomposition, staging of the 8 x L*K*K results and the TMA bulk store are those of lookup_tiled_nhwc_kernel.
+// ---------------------------------------------------------------------------------
+__host__ __device__ constexpr int nhwc_h_warp_bytes(int K, int CT) { return kStreamStages * kTile * 80 + (K * kTile + kNhwcQ * CT) * 4; }
+
+template <int R, bool CUDA_SEM>
+__global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_h_kernel(const LookupTiledParams p) {
+    constexpr int K = 2 * R + 1;
+    constexpr int W2 = K + 2;
+    constexpr int KK = K * K;
+    constexpr int S = kStreamStages;
+    constexpr int PITCHB = 80;                            // bytes per window per stage
+    constexpr int STAGEB = kTile * PITCHB;
+    constexpr int NPAIR_FAST = (K + 3) / 2;               // pair-steps covering (y_lo & 1) + K + 1 rows
+    constexpr int NPAIR_SLOW = (W2 + 2) / 2;              //                     (y_lo & 1) + W2 rows
+    static_assert(W2 + 3 <= 16 && NPAIR_SLOW <= 8, "window must fit the 4x4 tile block");
+
+    extern __shared__ __align__(16) unsigned char smem_nhwc_h[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int CT = p.num_levels * KK;
+    unsigned char* ring = smem_nhwc_h + (size_t)warp * nhwc_h_warp_bytes(K, CT);
+    float* siy = reinterpret_cast<float*>(ring + S * STAGEB);
+    float* stage = siy + K * kTile;
+
+    const int b = blockIdx.x / p.blocks_per_batch;
+    const int unit = (blockIdx.x - b * p.blocks_per_batch) * kNhwcWarps + warp;
+    if (unit >= p.tiles_per_batch) return;
+
+    const int N = p.N;
+    const int n0 = unit * kNhwcQ;
+    const int lvl_of_lane = lane >> 3;
+    const bool lvl_on = lvl_of_lane < p.num_levels;
+    const int level = lvl_on ? lvl_of_lane : 0;
+    const int q = lane & 7;
+    const int n = min(n0 + q, N - 1);
+    const int lh = p.lh[level], lw = p.lw[level];
+    const int th = p.th[level], tw = p.tw[level];
+    const int twr = (lw + 3) >> 2;
+    const float inv_scale = __int_as_float((127 - level) << 23);
+
+    // ---------------- phase A (lane = window): identical to the fp32 kernel ----------------
+    const float* cptr = p.coords + (size_t)b * 2 * p.coords_stride + n;
+    const float cx = __ldg(cptr) * inv_scale;
+    const float cy = __ldg(cptr + p.coords_stride) * inv_scale;
+    const float sx = (float)(lw - 1), sy = (float)(lh - 1);
+    const float rsx = __frcp_rn(sx), rsy = __frcp_rn(sy);
+    const float ixf = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(-R)), sx, rsx);
+    const float ixl = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(R)), sx, rsx);
+    const float iyf = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(-R)), sy, rsy);
+    const float iyl = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(R)), sy, rsy);
+    const bool wild = !lvl_on || !(fabsf(ixf) < kWildLimit) || !(fabsf(ixl) < kWildLimit) ||
+                      !(fabsf(iyf) < kWildLimit) || !(fabsf(iyl) < kWildLimit);
+    int x_lo = 0, y_lo = 0;
+    int my_base = 0, my_pack = 0;
+    if (!wild) {
+        x_lo = (int)floorf(ixf);
+        y_lo = (int)floorf(iyf);
+        const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
+        my_base = (ty0 * tw + tx0) * 16;
+        int tmask = 0;
+#pragma unroll
+        for (int tyi = 0; tyi < 4; ++tyi)
+#pragma unroll
+            for (int txi = 0; txi < 4; ++txi)
+                if ((unsigned)(ty0 + tyi) < (unsigned)th && (unsigned)(tx0 + txi) < (unsigned)twr) tmask |= 1 << (tyi * 4 + txi);
+        my_pack = (x_lo & 3) | ((y_lo & 3) << 2) | (tmask << 4);
+    }
+    float wx0[K], wx1[K];
+    unsigned px = 0, py = 0;
+    bool deviated = false;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const float ix = source_index<CUDA_SEM>(__fadd_rn(cx, (float)(a - R)), sx, rsx);
+        const float fx = floorf(ix);
+        const float iy = source_index<CUDA_SEM>(__fadd_rn(cy, (float)(a - R)), sy, rsy);
+        const float fy = floorf(iy);
+        siy[a * kTile + lane] = iy;
+        wx1[a] = wild ? 0.f : __fsub_rn(ix, fx);
+        wx0[a] = wild ? 0.f : __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+        const int dxa = wild ? 0 : min(max((int)fx - x_lo, 0), W2 - 2) - a;
+        const int dya = wild ? 0 : min(max((int)fy - y_lo, 0), W2 - 2) - a;
+        px |= (unsigned)((dxa + 1) & 3) << (2 * a);
+        py |= (unsigned)((dya + 1) & 3) << (2 * a);
+        deviated |= (dxa != 0) | (dya != 0);
+    }
+    const bool slow = __any_sync(0xffffffffu, deviated);
+    auto ytap = [&](int bb, float& w0, float& w1) {
+        const float iy = siy[bb * kTile + lane];
+        const float fy = floorf(iy);
+        w1 = wild ? 0.f : __fsub_rn(iy, fy);
+        w0 = wild ? 0.f : __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+    };
+
+    // ---------------- gather slots: slot j = level j, lane = (query lane >> 2, tile column lane & 3) ----------------
+    const int txi = lane & 3;
+    const int qj = lane >> 2;
+    const int last_q = N - 1 - n0;
+    const __half* tbase[4];
+    int goff[4], gnext[4], ppos[4], nstep[4];
+    unsigned texist[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int lj = j < p.num_levels ? j : 0;
+        const int map_elems = p.th[lj] * p.tw[lj] * 16;
+        tbase[j] = reinterpret_cast<const __half*>(p.lvl[lj]) + ((int64_t)b * N + n0) * (int64_t)map_elems;
+        const int base = __shfl_sync(0xffffffffu, my_base, j * 8 + qj);
+        const int pk = __shfl_sync(0xffffffffu, my_pack, j * 8 + qj);
+        const int gy = (pk >> 2) & 3;
+        ppos[j] = gy >> 1;                                   // first pair: rows (0,1) or (2,3) of the first tile row
+        goff[j] = min(qj, last_q) * map_elems + base + txi * 16 + ppos[j] * 8;
+        const unsigned e = (unsigned)pk >> (4 + txi);
+        unsigned ex = (e & 1u) | (((e >> 4) & 1u) << 1) | (((e >> 8) & 1u) << 2) | (((e >> 12) & 1u) << 3);
+        if (txi * 4 >= (pk & 3) + (slow ? W2 : K + 1)) ex = 0;                  // only the tile columns the window reaches
+        texist[j] = ex;
+        nstep[j] = ((gy & 1) + (slow ? W2 : K + 1) + 1) >> 1;                   // pairs this window needs
+        gnext[j] = p.tw[lj] * 16 - 8;
+    }
+    const unsigned gdst = (unsigned)(qj * PITCHB + txi * 16);
+    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
+    int pairs_issued = 0;
+    uint32_t issue_saddr = ring_saddr;
+    auto issue_pair = [&](bool active) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int P = ppos[j];
+                const bool ok = ((texist[j] >> (P >> 1)) & 1u) && pairs_issued < nstep[j];
+                const __half* src = tbase[j] + (ok ? goff[j] : 0);
+                cp_async16_zfill(issue_saddr + gdst + (unsigned)(j * 8 * PITCHB), src, ok ? 16u : 0u);
+                goff[j] += (P & 1) ? gnext[j] : 8;
+                ppos[j] = P + 1;
+            }
+            ++pairs_issued;
+            issue_saddr += STAGEB;
+            if (issue_saddr == ring_saddr + S * STAGEB) issue_saddr = ring_saddr;
+        }
+        cp_async_commit();
+    };
+
+    float* sout = stage + q * CT + level * KK;
+    const int shift = x_lo & 3;
+    const int par = y_lo & 1;                              // the window's first row is the odd row of its pair
+    const unsigned char* my_row = ring + lane * PITCHB;
+    const int npair = slow ? NPAIR_SLOW : NPAIR_FAST;
+
+#pragma unroll
+    for (int r = 0; r < S - 1; ++r) issue_pair(true);      // NPAIR_* > S - 1 for every radius
+
+    if (!slow) {
+        float tprev[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) tprev[a] = 0.f;
+        const unsigned char* sq = my_row;
+#pragma unroll 1
+        for (int s = 0; s < NPAIR_FAST; ++s) {
+            cp_async_wait<S - 2>();
+            __syncwarp();
+            issue_pair(s + S - 1 < NPAIR_FAST);
+            uint4 pc[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) pc[v] = reinterpret_cast<const uint4*>(sq)[v];
+#pragma unroll
+            for (int rho = 0; rho < 2; ++rho) {
+                const int r = 2 * s - par + rho;            // window row of this half of the pair (per lane)
+                float f[16];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const uint32_t w0 = rho ? pc[v].z : pc[v].x, w1 = rho ? pc[v].w : pc[v].y;
+                    const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+                    const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+                    f[4 * v] = a2.x; f[4 * v + 1] = a2.y; f[4 * v + 2] = b2.x; f[4 * v + 3] = b2.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 15; ++c) f[c] = (shift & 1) ? f[c + 1] : f[c];
+#pragma unroll
+                for (int c = 0; c < 13; ++c) f[c] = (shift & 2) ? f[c + 2] : f[c];
+                float tcur[K];
+#pragma unroll
+                for (int a = 0; a < K; ++a) tcur[a] = __fmaf_rn(wx1[a], f[a + 1], __fmul_rn(wx0[a], f[a]));
+                if (r >= 1 && r <= K && lvl_on) {
+                    float w0, w1;
+                    ytap(r - 1, w0, w1);
+#pragma unroll
+                    for (int a = 0; a < K; ++a) sout[a * K + (r - 1)] = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
+                }
+                if (r >= 0) {
+#pragma unroll
+                    for (int a = 0; a < K; ++a) tprev[a] = tcur[a];
+                }
+            }
+            sq += STAGEB;
+            if (sq == my_row + S * STAGEB) sq = my_row;
+        }
+    } else {
+        // exact per-tap path: window row r sits in pair-step s = (r + par) >> 1, half rho = (r + par) & 1
+        auto elem = [&](int step, int rho, int c) -> float {
+            const __half* rowp = reinterpret_cast<const __half*>(my_row + (step % S) * STAGEB);
+            const int cc = shift + c;
+            return __half2float(rowp[(cc >> 2) * 8 + rho * 4 + (cc & 3)]);
+        };
+#pragma unroll 1
+        for (int s = 0; s < NPAIR_SLOW; ++s) {
+            cp_async_wait<S - 2>();
+            __syncwarp();
+#pragma unroll 1
+            for (int rho = 0; rho < 2; ++rho) {
+                const int r = 2 * s - par + rho;
+                if (r < 1 || r > W2 - 1) continue;
+                const int ps = (r - 1 + par) >> 1, prho = (r - 1 + par) & 1;       // where row r - 1 lives
+#pragma unroll 1
+                for (int bb = 0; bb < K; ++bb) {
+                    const int ryb = bb + (int)((py >> (2 * bb)) & 3u) - 1;
+                    if (ryb + 1 != r) continue;
+                    float wy0b, wy1b;
+                    ytap(bb, wy0b, wy1b);
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        const int rxa = a + (int)((px >> (2 * a)) & 3u) - 1;
+                        const float v00 = elem(ps, prho, rxa), v01 = elem(ps, prho, rxa + 1);
+                        const float v10 = elem(s, rho, rxa), v11 = elem(s, rho, rxa + 1);
+                        const float nw = __fmul_rn(wx0[a], wy0b);
+                        const float ne = __fmul_rn(wx1[a], wy0b);
+                        const float sw = __fmul_rn(wx0[a], wy1b);
+                        const float se = __fmul_rn(wx1[a], wy1b);
+                        float o = __fmul_rn(v00, nw);
+                        o = __fmaf_rn(v01, ne, o);
+                        o = __fmaf_rn(v10, sw, o);
+                        o = __fmaf_rn(v11, se, o);
+                        if (lvl_on) sout[a * K + bb] = o;
+                    }
+                }
+            }
+            __syncwarp();                                   // the previous pair is no longer needed by anyone
+            issue_pair(s + S - 1 < NPAIR_SLOW);
+        }
+    }
+    (void)npair;
+    cp_async_wait<0>();
+
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        const int nq = min(kNhwcQ, N - n0);
+        float* gdst_ptr = p.out + ((int64_t)b * p.out_stride + n0) * CT;
+        const uint32_t bytes = (uint32_t)(nq * CT) * 4u;
+        if ((bytes & 15u) == 0 && (((uintptr_t)gdst_ptr) & 15u) == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst_ptr),
+                         "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        } else {
+            for (int i = 0; i < nq * CT; ++i) gdst_ptr[i] = stage[i];
+        }
+    }
+}
+
+template <int R>
+int launch_lookup_tiled_nhwc_h(const LookupTiledParams& p0, int sampler, cudaStream_t stream) {
+    constexpr int K = 2 * R + 1;
+    LookupTiledParams p = p0;
+    FFCORR_REQUIRE(p.num_levels <= 4, FFCORR_EINVAL, "lookup_tiled_f16: at most 4 levels, got %d", p.num_levels);
+    p.tiles_per_batch = ceil_div(p.N, kNhwcQ);
+    p.blocks_per_batch = ceil_div(p.tiles_per_batch, kNhwcWarps);
+    const int64_t blocks = (int64_t)p.B * p.blocks_per_batch;
+    FFCORR_REQUIRE(blocks < (1ll << 31), FFCORR_EINVAL, "lookup_tiled_f16: grid too large");
+    const size_t smem = (size_t)kNhwcWarps * nhwc_h_warp_bytes(K, p.num_levels * K * K);
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_h_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_tiled_nhwc_h_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (sampler == FFCORR_SAMPLER_ATEN_CUDA)
+        lookup_tiled_nhwc_h_kernel<R, true><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
+    else
+        lookup_tiled_nhwc_h_kernel<R, false><<<(unsigned)blocks, kNhwcWarps * 32, smem, stream>>>(p);
+    return check_launch("lookup_tiled_nhwc_h_kernel");
+}
+
 template <int R, typename T>
 int launch_lookup_tiled_nhwc(const LookupTiledParams& p0, int sampler, cudaStream_t stream) {
     constexpr int K = 2 * R + 1;
@@ -1181,10 +1463,10 @@ static int lookup_tiled_impl(const float* const* lvl, int num_levels, const floa
     if (half_storage) {
         FFCORR_REQUIRE(out_channels_last, FFCORR_EINVAL, "%s: the fp16-stored pyramid is read by the channels-last kernel only", who);
         switch (radius) {
-            case 1: return launch_lookup_tiled_nhwc<1, __half>(p, sampler, s);
-            case 2: return launch_lookup_tiled_nhwc<2, __half>(p, sampler, s);
-            case 3: return launch_lookup_tiled_nhwc<3, __half>(p, sampler, s);
-            default: return launch_lookup_tiled_nhwc<4, __half>(p, sampler, s);
+            case 1: return launch_lookup_tiled_nhwc_h<1>(p, sampler, s);
+            case 2: return launch_lookup_tiled_nhwc_h<2>(p, sampler, s);
+            case 3: return launch_lookup_tiled_nhwc_h<3>(p, sampler, s);
+            default: return launch_lookup_tiled_nhwc_h<4>(p, sampler, s);
         }
     }
     if (out_channels_last) {

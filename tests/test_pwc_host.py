@@ -108,4 +108,4 @@ def test_host_model_matches_the_unmodified_reference_on_the_gpu(hw, batch):
     assert float(epe.max()) <= 2e-4 * scale                   # random weights give large flows: relative to their size
     assert len(got_list) == len(want_list) == 5
     for a, r in zip(got_list, want_list):
-        assert a.shape == r.shape and float((a - r).abs().max()) <= 2e-4 * max(1.0, float(r.abs().max()))
+        assert a.shape == r.shape and float((a - r).abs().max()) <= 5e-4 * max(1.0, float(r.abs().max()))
