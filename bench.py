@@ -126,7 +126,11 @@ def dist_setup(n_gpus: int):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo", init_method="env://")
+        import datetime
+
+        # a short watchdog: a rank that falls out of step must fail the run in minutes, not hold 8 GPUs for ten
+        dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo", init_method="env://",
+                                timeout=datetime.timedelta(seconds=180))
     return rank, world, local
 
 
@@ -941,11 +945,14 @@ def run_train_arm(args, rank, world, local):
     C._Lookup.backward = staticmethod(wrap(C._Lookup.backward, "bwd", 1))
     C._VolumePyramid.backward = staticmethod(wrap(C._VolumePyramid.backward, "bwd", 4))
 
+    last = {"loss": None}
+
     def one_step(from_host=False):
         data = [t.to(device, non_blocking=True) for t in host] if from_host else batch
         loss, _ = step(*data)
         if from_host:
             loss_host.copy_(loss.reshape(1), non_blocking=True)
+        last["loss"] = loss
         return loss
 
     def timed(fn, steps, warmup, clocks=False):
@@ -998,7 +1005,7 @@ def run_train_arm(args, rank, world, local):
         "train": {"native_corr_forward_ms_per_step": round(fwd_ms, 3), "native_corr_backward_ms_per_step": round(bwd_ms, 3),
                   "native_corr_share_of_step": round((fwd_ms + bwd_ms) * args.steps / ms_res, 4),
                   "allreduce_exposed_ms_per_step": None if exposed is None else round(exposed, 3),
-                  "allreduce_payload_bytes": nparam * 4, "loss": float(one_step().item())},
+                  "allreduce_payload_bytes": nparam * 4, "loss": float(last["loss"].item())},
         "roofline": {"kernel": "correlation path of a training step: fused build + 12 tiled lookups forward; 12 lookup_bwd + pyramid_bwd + 2 tf32 GEMMs backward",
                      "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src},
         "cpu_baseline": None,
