@@ -164,3 +164,57 @@ def test_training_step_with_native_kernels_matches_the_reference(tag):
     for prec, tol in (("fp32", 5e-3), ("fp16", 2e-2)):
         model.flow_net.corr_precision = prec
         check_step_against_golden(model, tag, "cuda:0", norm_tol=tol, loss_tol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ DDP under gloo, world 2
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from corr_torch_cpu import TorchCorrBlock
+    from focusflow_official_b200.host import TrainStep
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    model = host_model()
+    model.flow_net.corr_block = TorchCorrBlock
+    ddp = DDP(model)                                           # what parallel_model() returns on a GPU rank (common.py:45-50)
+    step = TrainStep(ddp, world_size=world, iters=2, num_steps=100)
+    batch = train_inputs(1, 128, 128, 40 + rank)               # every rank its own pair
+    loss, _ = step(*batch)
+    loss2, _ = step(*batch)                                    # every rank takes the SAME number of steps (bench.py lesson)
+    w = model.flow_net.update_block.flow_head.conv2.weight.detach()
+    gathered = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(gathered, w.contiguous())
+    q.put((rank, float(loss), float(loss2), bool(torch.equal(gathered[0], gathered[1])), float(step.grad_norm)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_training_step_under_ddp_gloo_world2():
+    """The N > 1 training path on CPU: stock DDP (gloo) around the host model, `loss *= world_size` (train.py:313-314),
+    gradients all-reduced during backward, identical weights on both ranks after the optimizer steps."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[0] for r in res] == [0, 1]
+    assert all(np.isfinite(r[1]) and np.isfinite(r[2]) for r in res)
+    assert all(r[3] for r in res), "ranks diverged: the gradients were not all-reduced"
+    assert res[0][1] != res[1][1]                              # different data per rank ...
+    assert abs(res[0][4] - res[1][4]) < 1e-6 * max(1.0, res[0][4])   # ... but one (averaged x world) gradient
