@@ -303,14 +303,11 @@ pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_consta
         for (int s = 0; s < pre; ++s) issue(s);
     }
 
-    // Accumulators as PAIRS of horizontally adjacent pixels: Blackwell's FFMA2 (fma.rn.f32x2, two independent IEEE
-    // fp32 FMAs per instruction) halves the time on the FMA pipe, which issues a 3-register FFMA only every other cycle
-    // per scheduler -- with scalar FFMAs this loop was FMA-pipe bound (72 x 2 cycles per channel and warp).
-    float2 acc2[4][9];
+    float acc[8][9];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 9; ++j) acc2[i][j] = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < 9; ++j) acc[i][j] = 0.0f;
 
 #pragma unroll 1
     for (int st = 0; st < nstage; ++st) {
@@ -328,33 +325,17 @@ pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_consta
             const float4 t1 = *reinterpret_cast<const float4*>(tp + 4);
             const float4 t2 = *reinterpret_cast<const float4*>(tp + 8);
             const float4 t3 = *reinterpret_cast<const float4*>(tp + 12);
-            const float2 a[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
-            // te[m] = (t[2m], t[2m+1]): the pairs as they come out of the 16-byte loads; to[m] = (t[2m+1], t[2m+2])
-            const float2 te[8] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w),
-                                  make_float2(t2.x, t2.y), make_float2(t2.z, t2.w), make_float2(t3.x, t3.y), make_float2(t3.z, t3.w)};
-            float2 to[7];
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float t[16] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w,
+                                 t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
 #pragma unroll
-            for (int m = 0; m < 7; ++m) to[m] = make_float2(te[m].y, te[m + 1].x);
+            for (int px = 0; px < 8; ++px)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int dx = 0; dx < 9; ++dx) {
-                    // pixels px = 2i, 2i + 1 against two[px + dx]: the pair starts at k = 2i + dx
-                    const int k = 2 * i + dx;
-                    acc2[i][dx] = __ffma2_rn(a[i], (k & 1) ? to[k >> 1] : te[k >> 1], acc2[i][dx]);
-                }
+                for (int dx = 0; dx < 9; ++dx) acc[px][dx] = fmaf(a[px], t[px + dx], acc[px][dx]);
         }
         __syncthreads();  // every warp is done with this slot
         if (tid == 0 && st + TMA_STAGES < nstage) issue(st + TMA_STAGES);
     }
-    float acc[8][9];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int dx = 0; dx < 9; ++dx) {
-            acc[2 * i][dx] = acc2[i][dx].x;
-            acc[2 * i + 1][dx] = acc2[i][dx].y;
-        }
 
     if (csize > 1) {
         // Deterministic reduce-scatter through distributed shared memory: every CTA publishes its 72
@@ -493,11 +474,11 @@ pwc81_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
         issue_g(1);
     }
 
-    float2 acc2[BW_CT][4];      // pixel pairs: FFMA2 (see pwc81_tma_kernel)
+    float acc[BW_CT][8];
 #pragma unroll
     for (int j = 0; j < BW_CT; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc2[j][i] = make_float2(0.0f, 0.0f);
+        for (int px = 0; px < 8; ++px) acc[j][px] = 0.0f;
 
     pw_mbar_wait(bar_t, 0);
     const float* Ts = reinterpret_cast<const float*>(base) + (size_t)(cg * BW_CT) * S2 + c8;
@@ -533,21 +514,11 @@ pwc81_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
 #pragma unroll
             for (int j = 0; j < BW_CT; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    acc2[j][i] = __ffma2_rn(make_float2(g8[2 * i], g8[2 * i + 1]),
-                                            make_float2(t[j][2 * i + sh], t[j][2 * i + sh + 1]), acc2[j][i]);
+                for (int px = 0; px < 8; ++px) acc[j][px] = fmaf(g8[px], t[j][px + sh], acc[j][px]);
         }
         __syncthreads();                           // everyone is done with this gradient slot
         if (tid == 0 && dyi + 2 < 9) issue_g(dyi + 2);
     }
-    float acc[BW_CT][8];
-#pragma unroll
-    for (int j = 0; j < BW_CT; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            acc[j][2 * i] = acc2[j][i].x;
-            acc[j][2 * i + 1] = acc2[j][i].y;
-        }
 
     const int gy = y0 + row, gx = x0 + c8;
     if (gy >= H || gx >= W) return;
