@@ -1219,3 +1219,90 @@ def test_flowformer_ops_against_reference_golden(tag):
     rev = fl.reverse_cost_tokens(cost_maps, c0, c1).cpu().numpy()
     assert rev.shape == g[f"{tag}_reverse"].shape
     assert max_rel(rev, g[f"{tag}_reverse"]) <= 1e-5, max_rel(rev, g[f"{tag}_reverse"])
+
+
+# ---------------------------------------------------------------- channels-last (NHWC) lookups: SURVEY 8b / 8f N3
+@pytest.mark.parametrize("shape,radius,nl", [((1, 46, 62), 4, 4), ((2, 17, 21), 4, 4), ((1, 24, 40), 3, 4), ((2, 12, 9), 2, 3),
+                                             ((1, 9, 33), 1, 2), ((3, 8, 8), 4, 1), ((1, 47, 156), 4, 4), ((2, 13, 11), 1, 1)])
+def test_channels_last_lookup_is_the_same_values_in_nhwc_memory(shape, radius, nl):
+    """out_channels_last = 1 (include/ffcorr.h): [B, h, w, L*K*K] storage, the same values, for the row-major
+    kernel, the tiled kernel (8 queries x all levels per warp, TMA bulk store) and the chunked (AlternateCorrBlock)
+    entry point; query counts that are not multiples of 8 / 32, 1-4 levels, radii 1-4, every coordinate regime."""
+    m = ff()
+    b, h, w = shape
+    rng = np.random.default_rng(5)
+    q = b * h * w
+    k2 = (2 * radius + 1) ** 2
+    pyr = [rng.standard_normal((q, h >> i, w >> i)).astype(np.float32) for i in range(nl)]
+    levels = [t(p[:, None]) for p in pyr]
+    tl = m.tile_levels(levels)
+    for name, c in _coords_cases(rng, b, h, w).items():
+        cd = t(c)
+        ref = co.lookup(pyr, c, radius)
+        for fn, lv in ((m.lookup, levels), (m.lookup_tiled, tl)):
+            nchw = fn(lv, cd, radius)
+            nhwc = fn(lv, cd, radius, channels_last=True)
+            assert nhwc.shape == (b, nl * k2, h, w) and nhwc.is_contiguous(memory_format=torch.channels_last) or nl * k2 == 1
+            assert nhwc.permute(0, 2, 3, 1).is_contiguous()
+            # same values: bit-identical per evaluation path; a warp takes the exact per-tap path when ANY of its 32
+            # windows sits on an integer coordinate, and the two kernels group windows differently (32 queries of one
+            # level vs 8 queries x all levels), so single windows may differ by the ~1e-7 between the two paths
+            scale = max(float(nchw.abs().max()), 1e-20)
+            assert float((nhwc - nchw).abs().max()) <= 2e-6 * scale, (fn.__name__, name)
+            if nl == 1:
+                assert torch.equal(nhwc.contiguous(), nchw), (fn.__name__, name)
+            assert max_rel(nhwc.cpu().numpy(), ref) <= 1e-5, (fn.__name__, name)
+
+
+def test_channels_last_blocks_and_the_host_model_use_no_layout_copy():
+    m = ff()
+    torch.manual_seed(3)
+    f1, f2 = torch.randn(2, 64, 24, 40, device=DEV), torch.randn(2, 64, 24, 40, device=DEV)
+    coords = m.coords_grid(2, 24, 40, DEV) + torch.randn(2, 2, 24, 40, device=DEV) * 2
+    a = m.CorrBlock(f1, f2)(coords)
+    for blk in (m.CorrBlock(f1, f2, channels_last=True), m.AlternateCorrBlock(f1, f2, channels_last=True, chunk=200),
+                m.CorrBlock(f1, f2, channels_last=True, precision="fp32")):
+        out = blk(coords)
+        assert out.is_contiguous(memory_format=torch.channels_last)
+        assert out.contiguous(memory_format=torch.channels_last).data_ptr() == out.data_ptr()     # no copy for convc1
+        if blk.__class__.__name__ != "CorrBlock" or blk._tiled:
+            assert float((out - a).abs().max()) <= 2e-6 * float(a.abs().max())
+    # autograd through a channels-last block == through the NCHW one
+    g = torch.randn_like(a)
+    grads = []
+    for cl in (False, True):
+        x1, x2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+        out = m.CorrBlock(x1, x2, channels_last=cl)(coords)
+        (out * g).sum().backward()
+        grads.append((x1.grad, x2.grad))
+    for ga, gb in zip(grads[0], grads[1]):
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_launches_follow_the_tensors_device_not_the_current_one():
+    """with cuda:0 current and the model on cuda:1, kernels, TMA descriptors and the stream must be those of
+    cuda:1 (ATen guards the device the same way); mixing devices in one call is a ValueError."""
+    m = ff()
+    assert torch.cuda.current_device() == 0
+    dev1 = torch.device("cuda", 1)
+    torch.manual_seed(9)
+    f1, f2 = torch.randn(1, 64, 24, 32), torch.randn(1, 64, 24, 32)
+    coords = m.coords_grid(1, 24, 32, "cpu") + torch.randn(1, 2, 24, 32)
+    ref = m.CorrBlock(f1.to(DEV), f2.to(DEV))(coords.to(DEV))
+    side = torch.cuda.Stream(device=dev1)
+    with torch.cuda.stream(side):                       # current stream of cuda:1 only; current device stays 0
+        pass
+    blk = m.CorrBlock(f1.to(dev1), f2.to(dev1))
+    out = blk(coords.to(dev1))
+    assert out.device == dev1 and torch.cuda.current_device() == 0
+    assert torch.equal(out.cpu(), ref.cpu())
+    cv = m.FunctionCorrelation(f1.to(dev1), f2.to(dev1))
+    assert torch.equal(cv.cpu(), m.FunctionCorrelation(f1.to(DEV), f2.to(DEV)).cpu())
+    x1 = f1.to(dev1).requires_grad_(True)
+    m.CorrBlock(x1, f2.to(dev1))(coords.to(dev1)).sum().backward()
+    assert x1.grad is not None and x1.grad.device == dev1 and torch.isfinite(x1.grad).all()
+    with pytest.raises(ValueError):
+        m.CorrBlock(f1.to(DEV), f2.to(dev1))
+    with pytest.raises(ValueError):
+        blk(coords.to(DEV))
