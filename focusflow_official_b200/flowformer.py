@@ -14,7 +14,7 @@
   on the transposed cost maps (the map index comes from the four taps of ``coords1``) blended with the tap weights.
 
 All run the kernels of :mod:`focusflow_official_b200.corr`; inference only.  Pinned by ``tests/golden/flowformer_ops.npz``:
-outputs of the reference's own functions (``oracle/make_golden_flowformer.py``).
+outputs of the reference's own functions, recorded by the FlowFormer golden-vector generator of the test infrastructure.
 """
 from __future__ import annotations
 
