@@ -56,6 +56,11 @@ _PROTOS = {
     "ffcorr_lookup_tiled_f16": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_untile_f16": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_tile_f16": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
+    "ffcorr_build_grouped_f32": (_i, [_vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
+    "ffcorr_lookup_grouped_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ffcorr_grouped_level_elems": (ctypes.c_int64, [_i, _i, _i, _i, _i]),
+    "ffcorr_ungroup_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ffcorr_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ffcorr_backwarp_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]),
 }
 SYMBOLS = tuple(_PROTOS)

@@ -125,7 +125,7 @@ def _storage_dtype(storage) -> torch.dtype:
 
 
 def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int, precision: int,
-                              fused: bool = True, storage: str = "fp32") -> List[torch.Tensor]:
+                              fused: bool = True, storage: str = "fp32", grouped: bool = False) -> List[torch.Tensor]:
     """Volume + pyramid in the tiled layout: level i is [B*h*w, tiled_map_elems(h, w, i)], fp32 or (storage="fp16") half.
 
     fused=True (default): one GEMM launch writes every level (ffcorr_build_tiled_f32 / _f16); fused=False: the GEMM
@@ -133,6 +133,19 @@ def _volume_pyramid_tiled_raw(fmap1: torch.Tensor, fmap2: torch.Tensor, num_leve
     b, d, h, w = fmap1.shape
     L = _lib.lib()
     dtype = _storage_dtype(storage)
+    if grouped:
+        # "G32": [B * groups of 32 queries, tiles, 32 queries x 16 floats] -- recognised by its three dimensions
+        if dtype != torch.float32 or not fused or not (2 <= num_levels <= 4):
+            raise ValueError("layout='grouped' is produced by the fp32 fused build: 2 to 4 levels")
+        ng = (h * w + 31) // 32
+        levels = [torch.empty((b * ng, _tiled_elems(h, w, i) // 16, 512), device=fmap1.device, dtype=torch.float32)
+                  for i in range(num_levels)]
+        ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
+        ws = torch.empty(max(ws_bytes, 1), device=fmap1.device, dtype=torch.uint8)
+        with _lib.on_device(fmap1, fmap2) as stream:
+            _lib.check(L.ffcorr_build_grouped_f32(fmap1.data_ptr(), fmap2.data_ptr(), _lib.ptr_array(levels), num_levels, b, d, h, w,
+                                                  precision, ws.data_ptr(), ws_bytes, stream), "ffcorr_build_grouped_f32")
+        return levels
     levels = [torch.empty((b * h * w, _tiled_elems(h, w, i)), device=fmap1.device, dtype=dtype)
               for i in range(num_levels)]
     ws_bytes = L.ffcorr_volume_workspace_bytes(b, d, h, w, precision)
@@ -178,18 +191,24 @@ def _lookup_tiled_raw(levels, level_ptrs, coords: torch.Tensor, radius: int, sam
                                                           radius, sampler, 1, stream), "ffcorr_lookup_tiled_f16")
         return out if channels_last else out.contiguous()
     store, out = _alloc_lookup_out(coords, len(levels), radius, channels_last)
+    fn = "ffcorr_lookup_grouped_f32" if levels[0].dim() == 3 else "ffcorr_lookup_tiled_f32"
     with _lib.on_device(coords, levels[0]) as stream:
-        _lib.check(_lib.lib().ffcorr_lookup_tiled_f32(level_ptrs, len(levels), coords.data_ptr(), store.data_ptr(), b, h, w, radius,
-                                                      sampler, int(channels_last), stream), "ffcorr_lookup_tiled_f32")
+        _lib.check(getattr(_lib.lib(), fn)(level_ptrs, len(levels), coords.data_ptr(), store.data_ptr(), b, h, w, radius,
+                                           sampler, int(channels_last), stream), fn)
     return out
 
 
 def untile_levels(tiled_levels, b: int, h: int, w: int) -> List[torch.Tensor]:
-    """Tiled levels -> the reference's [B*h*w, 1, h>>i, w>>i] tensors."""
+    """Tiled (fp32 / fp16) or grouped levels -> the reference's [B*h*w, 1, h>>i, w>>i] tensors."""
     out = []
     for i, t in enumerate(tiled_levels):
         hi, wi = h >> i, w >> i
         dst = torch.empty((b * h * w, 1, hi, wi), device=t.device, dtype=torch.float32)
+        if t.dim() == 3:
+            with _lib.on_device(t) as stream:
+                _lib.check(_lib.lib().ffcorr_ungroup_f32(t.data_ptr(), dst.data_ptr(), b, h * w, hi, wi, stream), "ffcorr_ungroup_f32")
+            out.append(dst)
+            continue
         fn = "ffcorr_untile_f16" if t.dtype == torch.float16 else "ffcorr_untile_f32"
         with _lib.on_device(t) as stream:
             _lib.check(getattr(_lib.lib(), fn)(t.data_ptr(), dst.data_ptr(), b * h * w, hi, wi, stream), fn)
@@ -434,8 +453,11 @@ class CorrBlock:
         self._sink = None
         self._grad_tiled = False
         layout = layout or DEFAULT_LAYOUT
-        if layout not in ("tiled", "rowmajor"):
-            raise ValueError(f"layout must be 'tiled' or 'rowmajor', got {layout!r}")
+        if layout not in ("tiled", "rowmajor", "grouped"):
+            raise ValueError(f"layout must be 'tiled', 'grouped' or 'rowmajor', got {layout!r}")
+        self._grouped = layout == "grouped"
+        if self._grouped:
+            layout = "tiled"        # same kernels, same values; only the storage order of the tiles differs
         needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
         code = _precision_code(precision)
         if (h >> (num_levels - 1)) < 1 or (w >> (num_levels - 1)) < 1:
@@ -446,7 +468,8 @@ class CorrBlock:
             f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
             if f1.shape != f2.shape:
                 raise ValueError(f"fmap shapes differ: {tuple(f1.shape)} vs {tuple(f2.shape)}")
-            self._levels = _volume_pyramid_tiled_raw(f1, f2, num_levels, code, True, self.storage)
+            self._levels = _volume_pyramid_tiled_raw(f1, f2, num_levels, code, True, self.storage,
+                                                     self._grouped and 2 <= num_levels <= 4 and self.storage == "fp32")
             self._rowmajor = None                      # materialised on first access of .corr_pyramid
         elif needs_grad:
             f1, f2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")

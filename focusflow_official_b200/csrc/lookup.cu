@@ -260,6 +260,11 @@ struct LookupTiledParams {
     int blocks_per_batch;
     int64_t coords_stride;   // floats between the x and y planes of coords (N, or the full map size for a query chunk)
     int64_t out_stride;      // floats between output channels (N, or the full map size for a query chunk)
+    // Storage order of the tiles.  grouped == 0 ("T4"): every query owns a contiguous map [th][tw][16].  grouped == 1
+    // ("G32", ffcorr_build_grouped_f32): 32 consecutive queries share one tile grid, [group][th*tw][32 queries][16] -- the
+    // same tile of neighbouring queries (whose windows overlap under any smooth flow) is contiguous in memory.
+    int grouped;
+    int NG;                  // groups of 32 queries per batch item (grouped only)
 };
 
 // ---------------------------------------------------------------------------------
@@ -332,6 +337,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
     const int th = p.th[level], tw = p.tw[level];
     const int twr = (lw + 3) >> 2;      // tile columns that hold pixels; the column that evens the pitch is never read
     const int map_elems = th * tw * 16;
+    const int TS = p.grouped ? 16 * kTile : 16;                  // floats between horizontally adjacent tiles
+    const int QS = p.grouped ? 16 : map_elems;                   // floats between the same tile of consecutive queries
     const float* __restrict__ lvl = p.lvl[level];
     const float inv_scale = __int_as_float((127 - level) << 23);
 
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         x_lo = (int)floorf(ixf);
         y_lo = (int)floorf(iyf);
         const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
-        my_base = (ty0 * tw + tx0) * 16;
+        my_base = (ty0 * tw + tx0) * TS;
         int tmask = 0;
 #pragma unroll
         for (int tyi = 0; tyi < 4; ++tyi)
@@ -407,7 +414,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
 
     // ---------------- gather slots (lane = (query qj, tile column txi), j = 0..3) ----------------
     const int txi = lane & 3;
-    const float* __restrict__ tile_base = lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
+    // n0 is a multiple of 32: the warp's queries are exactly one group of the grouped layout
+    const float* __restrict__ tile_base = p.grouped ? lvl + ((int64_t)b * p.NG + (n0 >> 5)) * (int64_t)map_elems * kTile
+                                                    : lvl + ((int64_t)b * N + n0) * (int64_t)map_elems;
     int goff[4];        // float offset from tile_base of the slot's 16-byte piece in the current window row
     unsigned gmask[4];  // bit r: the tile under window row r exists; bit 16+r: row r is the last row of its tile
     unsigned gdst[4];   // byte offset of the slot inside a row buffer
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         const int base = __shfl_sync(0xffffffffu, my_base, qj);
         const int pk = __shfl_sync(0xffffffffu, my_pack, qj);
         const int gy = (pk >> 2) & 3;
-        goff[j] = min(qj, last_q) * map_elems + base + txi * 16 + gy * 4;    // < 2^31 (host check: 32 maps)
+        goff[j] = min(qj, last_q) * QS + base + txi * TS + gy * 4;    // < 2^31 (host check: 32 maps)
         const unsigned e = (unsigned)pk >> (4 + txi);
         unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
                        (((e >> 12) & 1u) * 0xF000u);
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
         gmask[j] = ((okT >> gy) & 0xFFFFu) | ((0x8888u >> gy) << 16);
         gdst[j] = (unsigned)(slot_of(qj) * kRowPitch + 4 * txi) * 4u;
     }
-    const int next_tile_row = tw * 16 - 12;     // from in-tile row 3 to row 0 of the tile below
+    const int next_tile_row = tw * TS - 12;     // from in-tile row 3 to row 0 of the tile below
     const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
     int rows_issued = 0;
     uint32_t issue_saddr = ring_saddr;          // stage the next issued row lands in
@@ -628,7 +637,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
         x_lo = (int)floorf(ixf);
         y_lo = (int)floorf(iyf);
         const int tx0 = x_lo >> 2, ty0 = y_lo >> 2;
-        my_base = (ty0 * tw + tx0) * 16;
+        my_base = (ty0 * tw + tx0) * (p.grouped ? 16 * kTile : 16);
         int tmask = 0;
 #pragma unroll
         for (int tyi = 0; tyi < 4; ++tyi)
@@ -675,11 +684,14 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
     for (int j = 0; j < 4; ++j) {
         const int lj = j < p.num_levels ? j : 0;
         const int map_elems = p.th[lj] * p.tw[lj] * 16;
-        tbase[j] = reinterpret_cast<const T*>(p.lvl[lj]) + ((int64_t)b * N + n0) * (int64_t)map_elems;
+        const int TS = p.grouped ? 16 * kTile : 16, QS = p.grouped ? 16 : map_elems;
+        // grouped: the warp's 8 queries sit inside group n0 >> 5 at slots (n0 & 31) ..
+        tbase[j] = p.grouped ? reinterpret_cast<const T*>(p.lvl[lj]) + ((int64_t)b * p.NG + (n0 >> 5)) * (int64_t)map_elems * kTile + (n0 & 31) * 16
+                             : reinterpret_cast<const T*>(p.lvl[lj]) + ((int64_t)b * N + n0) * (int64_t)map_elems;
         const int base = __shfl_sync(0xffffffffu, my_base, j * 8 + qj);
         const int pk = __shfl_sync(0xffffffffu, my_pack, j * 8 + qj);       // 0 for a wild / absent window
         const int gy = (pk >> 2) & 3;
-        goff[j] = min(qj, last_q) * map_elems + base + txi * 16 + gy * 4;
+        goff[j] = min(qj, last_q) * QS + base + txi * TS + gy * 4;
         const unsigned e = (unsigned)pk >> (4 + txi);
         unsigned okT = ((e & 1u) * 0xFu) | (((e >> 4) & 1u) * 0xF0u) | (((e >> 8) & 1u) * 0xF00u) |
                        (((e >> 12) & 1u) * 0xF000u);
@@ -687,7 +699,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
         if (txi * 4 >= (pk & 3) + (slow ? W2 : K + 1)) okT = 0;       // only the tile columns the window reaches
 #endif
         gmask[j] = ((okT >> gy) & 0xFFFFu) | ((0x8888u >> gy) << 16);
-        gnext[j] = p.tw[lj] * 16 - 12;
+        gnext[j] = p.tw[lj] * TS - 12;
     }
     const unsigned gdst = (unsigned)(qj * PITCH + 4 * txi) * (unsigned)sizeof(T);     // + j * 8 * PITCH * sizeof(T) per slot
     const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(ring);
@@ -1431,7 +1443,7 @@ extern "C" int ffcorr_lookup_bwd_f32(float* const* grad_lvl, int num_levels, con
 
 static int lookup_tiled_impl(const float* const* lvl, int num_levels, const float* coords, float* out, int B, int h, int w,
                              int nq, int64_t coords_stride, int64_t out_stride, int radius, int sampler, int out_channels_last,
-                             void* stream, const char* who, bool half_storage = false) {
+                             void* stream, const char* who, bool half_storage = false, bool grouped = false) {
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "%s: B=%d", who, B);
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(lvl && coords && out, FFCORR_EINVAL, "%s: null pointer", who);
@@ -1457,6 +1469,9 @@ static int lookup_tiled_impl(const float* const* lvl, int num_levels, const floa
     p.coords_stride = coords_stride;
     p.out_stride = out_stride;
     p.num_levels = num_levels;
+    p.grouped = grouped ? 1 : 0;
+    p.NG = ceil_div(nq, kTile);
+    FFCORR_REQUIRE(!(grouped && half_storage), FFCORR_EINVAL, "%s: the grouped layout stores fp32", who);
     p.tiles_per_batch = ceil_div(p.N, kTile);
     p.blocks_per_batch = ceil_div(p.tiles_per_batch, kWarpsPerBlock);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1495,6 +1510,12 @@ extern "C" int ffcorr_lookup_tiled_f16(const void* const* lvl, int num_levels, c
                                        int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream) {
     return lookup_tiled_impl(reinterpret_cast<const float* const*>(lvl), num_levels, coords, out, B, h, w, h * w, (int64_t)h * w,
                              (int64_t)h * w, radius, sampler, out_channels_last, stream, "lookup_tiled_f16", true);
+}
+
+extern "C" int ffcorr_lookup_grouped_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                                         int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream) {
+    return lookup_tiled_impl(lvl, num_levels, coords, out, B, h, w, h * w, (int64_t)h * w, (int64_t)h * w, radius, sampler,
+                             out_channels_last, stream, "lookup_grouped", false, true);
 }
 
 extern "C" int ffcorr_lookup_tiled_chunk_f32(const float* const* lvl, int num_levels, const float* coords, float* out,

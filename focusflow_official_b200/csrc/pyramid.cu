@@ -365,6 +365,41 @@ __global__ void __launch_bounds__(256) untile_kernel(const float* __restrict__ s
     }
 }
 
+// Grouped ("G32") layout <-> reference row-major [B*N, h, w].  Level storage: [B][NG][th*tw][32 queries][4][4] floats,
+// NG = ceil(N / 32): the same tile of 32 consecutive queries is contiguous (ffcorr_build_grouped_f32).
+__global__ void __launch_bounds__(256) ungroup_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int N,
+                                                      int h, int w, int tw, int ntiles) {
+    const int64_t total = (int64_t)B * N * h * w;
+    const int NG = (N + 31) >> 5;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % w);
+        const int64_t t = idx / w;
+        const int y = (int)(t % h);
+        const int64_t bq = t / h;
+        const int b = (int)(bq / N), q = (int)(bq - (int64_t)b * N);
+        const int64_t tile = ((int64_t)b * NG + (q >> 5)) * ntiles + (y >> 2) * tw + (x >> 2);
+        dst[idx] = __ldg(src + (tile * 32 + (q & 31)) * 16 + (y & 3) * 4 + (x & 3));
+    }
+}
+
+__global__ void __launch_bounds__(256) group_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int N,
+                                                    int h, int w, int tw, int ntiles) {
+    const int NG = (N + 31) >> 5;
+    const int64_t total = (int64_t)B * NG * ntiles * 512;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx & 15), ql = (int)((idx >> 4) & 31);
+        const int64_t tile_g = idx >> 9;
+        const int tile = (int)(tile_g % ntiles);
+        const int64_t bg = tile_g / ntiles;
+        const int b = (int)(bg / NG), q = (int)(bg - (int64_t)b * NG) * 32 + ql;
+        const int ty = tile / tw, tx = tile - ty * tw;
+        const int y = 4 * ty + (e >> 2), x = 4 * tx + (e & 3);
+        dst[idx] = (q < N && y < h && x < w) ? __ldg(src + (((int64_t)b * N + q) * h + y) * w + x) : 0.0f;
+    }
+}
+
 // fp16-stored tiles (ffcorr_build_tiled_f16) -> reference row-major fp32 [Q, h, w]
 __global__ void __launch_bounds__(256) untile_half_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t Q,
                                                           int h, int w, int tw, int np) {
@@ -668,6 +703,32 @@ extern "C" int ffcorr_untile_f32(const float* tiled, float* dst, int64_t Q, int 
     const int tw = tiled_tw(w);
     untile_kernel<<<grid_for(Q * h * w, 256), 256, 0, (cudaStream_t)stream>>>(tiled, dst, Q, h, w, tw, tiled_th(h) * tw * 16);
     return check_launch("untile_kernel");
+}
+
+extern "C" int64_t ffcorr_grouped_level_elems(int h, int w, int level, int B, int nq) {
+    if (h < 1 || w < 1 || level < 0 || level >= FFCORR_MAX_LEVELS || B < 0 || nq < 0) return 0;
+    const int lh = h >> level, lw = w >> level;
+    if (lh < 1 || lw < 1) return 0;
+    return (int64_t)B * ceil_div(nq, 32) * tiled_th(lh) * tiled_tw(lw) * 512;
+}
+
+extern "C" int ffcorr_ungroup_f32(const float* grouped, float* dst, int B, int N, int h, int w, void* stream) {
+    FFCORR_REQUIRE(B >= 0 && N >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "ungroup: bad shape");
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(grouped && dst, FFCORR_EINVAL, "ungroup: null pointer");
+    const int tw = tiled_tw(w);
+    ungroup_kernel<<<grid_for((int64_t)B * N * h * w, 256), 256, 0, (cudaStream_t)stream>>>(grouped, dst, B, N, h, w, tw, tiled_th(h) * tw);
+    return check_launch("ungroup_kernel");
+}
+
+extern "C" int ffcorr_group_f32(const float* src, float* grouped, int B, int N, int h, int w, void* stream) {
+    FFCORR_REQUIRE(B >= 0 && N >= 1 && h >= 1 && w >= 1, FFCORR_EINVAL, "group: bad shape");
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(grouped && src, FFCORR_EINVAL, "group: null pointer");
+    const int tw = tiled_tw(w);
+    const int ntiles = tiled_th(h) * tw;
+    group_kernel<<<grid_for((int64_t)B * ceil_div(N, 32) * ntiles * 512, 256), 256, 0, (cudaStream_t)stream>>>(src, grouped, B, N, h, w, tw, ntiles);
+    return check_launch("group_kernel");
 }
 
 extern "C" int ffcorr_untile_f16(const void* tiled, float* dst, int64_t Q, int h, int w, void* stream) {

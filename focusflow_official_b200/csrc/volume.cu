@@ -88,6 +88,11 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
                  ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -253,18 +258,25 @@ struct FusedParams {
     int map2, map3;             // floats per query map, levels 2 and 3
     float* l2;
     float* l3;
+    int ng;                     // GROUPED layout only: groups of 32 queries per batch item
 };
 
 // HALF (fused build only): the pyramid is STORED as fp16 (ffcorr_build_tiled_f16) -- the same 4x4-pixel tiles, 32 bytes
 // each; accumulation and the poolings stay fp32, every level is rounded once (RN) when it is written.  Level 0 of a
 // chunk is then 128 bytes per query (ONE store box instead of two), which halves the bytes of the kernel's bound.
-template <bool TF32, bool TMA_STORE, bool DIV, bool FUSED, bool HALF = false>
+// GROUPED (fused build only, fp32): the levels are stored [group of 32 queries][tile][query][4][4] (ffcorr_build_grouped_f32).
+// An epilogue warp owns 32 consecutive accumulator rows = exactly one group, so what it writes per chunk is CONTIGUOUS:
+// 8 KB of level 0 (4 tiles x 32 queries x 64 B), 4 KB of level 1, 1 KB / 256 B regions of levels 2 / 3 -- instead of 32
+// pieces 30 KB apart.  Staged [tile][query][16 floats] in 64-byte rows (SWIZZLE_64B) and stored through 2-D tensor maps
+// over the level viewed as rows of one tile-of-one-query each.
+template <bool TF32, bool TMA_STORE, bool DIV, bool FUSED, bool HALF = false, bool GROUPED = false>
 __global__ void __launch_bounds__(Cfg<FUSED>::THREADS, 1)
 volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_l1,
                    const GemmParams p, const FusedParams fp, const uint32_t idesc) {
     static_assert(!FUSED || TMA_STORE, "the fused build stores through TMA");
     static_assert(!HALF || FUSED, "fp16 storage exists for the fused build only");
+    static_assert(!GROUPED || (FUSED && !HALF), "the grouped layout is written by the fp32 fused build");
     using C = Cfg<FUSED>;
     constexpr int STAGES = C::STAGES;
     constexpr int STORE_PAIRS = C::STORE_PAIRS;
@@ -398,7 +410,20 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             // stages one 64-column chunk as two 128B-swizzled 32x32 boxes in store pair `pair`
             auto stage_pair = [&](const uint32_t (&v)[64]) {
                 uint8_t* dst = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF + lane * 128;
-                if constexpr (HALF) {
+                if constexpr (GROUPED) {
+                    // tile t of the chunk -> box t >> 1, row (t & 1) * 32 + lane of 64 bytes; 16-byte piece j = tile row j
+                    uint8_t* gb = my_bufs + (size_t)(pair * 2) * SMEM_STORE_BUF;
+#pragma unroll
+                    for (int tt = 0; tt < 4; ++tt) {
+                        const int r = (tt & 1) * 32 + lane;
+                        uint8_t* rowp = gb + (tt >> 1) * SMEM_STORE_BUF + r * 64;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4*>(rowp + ((j ^ ((r >> 1) & 3)) << 4)) =
+                                make_float4(scaled(v[tt * 16 + 4 * j]), scaled(v[tt * 16 + 4 * j + 1]),
+                                            scaled(v[tt * 16 + 4 * j + 2]), scaled(v[tt * 16 + 4 * j + 3]));
+                    }
+                } else if constexpr (HALF) {
                     // 64 halfs = one 128-byte row of ONE 128B-swizzled box
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -482,7 +507,11 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                                     const float4 q = make_float4(src[(2 * tt) * 4 + py * 2], src[(2 * tt) * 4 + py * 2 + 1],
                                                                  src[(2 * tt + 1) * 4 + py * 2], src[(2 * tt + 1) * 4 + py * 2 + 1]);
                                     const int j = tt * 4 + rr;
-                                    if constexpr (HALF)   // two tiles x 4 rows x 8 bytes = 64 bytes per query, unswizzled box
+                                    if constexpr (GROUPED) {   // level-1 tile tt of this query = row tt * 32 + lane, piece rr
+                                        const int r = tt * 32 + lane;
+                                        *reinterpret_cast<float4*>(my_bufs + (size_t)C::STORE_BUFS * SMEM_STORE_BUF + r * 64 +
+                                                                   ((rr ^ ((r >> 1) & 3)) << 4)) = q;
+                                    } else if constexpr (HALF)   // two tiles x 4 rows x 8 bytes = 64 bytes per query, unswizzled box
                                         *reinterpret_cast<uint2*>(dst + j * 8) = make_uint2(pack_h2(q.x, q.y), pack_h2(q.z, q.w));
                                     else
                                         *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = q;
@@ -495,21 +524,36 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (l0_any) {
-                            const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
-                            tma_store_4d(&tmap_c, src, sgx * 64, ty, row0, b);
-                            if (!HALF && sgx * 4 + 2 < fp.tw0) tma_store_4d(&tmap_c, src + SMEM_STORE_BUF, sgx * 64 + 32, ty, row0, b);
+                        if constexpr (GROUPED) {
+                            const int grp = b * fp.ng + (row0 >> 5);
+                            if (l0_any) {
+                                const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
+                                const int r0 = (grp * (fp.th0 * fp.tw0) + ty * fp.tw0 + 4 * sgx) * 32;     // < 2^31 (host check)
+                                tma_store_2d(&tmap_c, src, 0, r0);
+                                if (sgx * 4 + 2 < fp.tw0) tma_store_2d(&tmap_c, src + SMEM_STORE_BUF, 0, r0 + 64);
+                            }
+                            if (l1_any)
+                                tma_store_2d(&tmap_l1, my_bufs_u32 + (uint32_t)(C::STORE_BUFS * SMEM_STORE_BUF), 0,
+                                             (grp * (fp.th1 * fp.tw1) + (sgy * 2 + (c >> 1)) * fp.tw1 + 2 * sgx) * 32);
+                        } else {
+                            if (l0_any) {
+                                const uint32_t src = my_bufs_u32 + (uint32_t)(pair * 2 * SMEM_STORE_BUF);
+                                tma_store_4d(&tmap_c, src, sgx * 64, ty, row0, b);
+                                if (!HALF && sgx * 4 + 2 < fp.tw0) tma_store_4d(&tmap_c, src + SMEM_STORE_BUF, sgx * 64 + 32, ty, row0, b);
+                            }
+                            if (l1_any)
+                                tma_store_4d(&tmap_l1, my_bufs_u32 + (uint32_t)(C::STORE_BUFS * SMEM_STORE_BUF), sgx * 32,
+                                             sgy * 2 + (c >> 1), row0, b);
                         }
-                        if (l1_any)
-                            tma_store_4d(&tmap_l1, my_bufs_u32 + (uint32_t)(C::STORE_BUFS * SMEM_STORE_BUF), sgx * 32,
-                                         sgy * 2 + (c >> 1), row0, b);
                         tma_store_commit();
                     }
                     pair = (pair + 1) % STORE_PAIRS;
                     if (ci == 1 && row < p.N) {
                         // ---- level 2: rows c0, c0 + 1 of this super-group's tile, 32 contiguous bytes per query ----
                         if (fp.levels >= 3 && sgy < fp.th2 && sgx < fp.tw2) {
-                            const int64_t e2 = ((int64_t)b * p.N + row) * fp.map2 + (sgy * fp.tw2 + sgx) * 16 + c0 * 4;
+                            const int64_t e2 = GROUPED
+                                ? ((((int64_t)b * fp.ng + (row >> 5)) * (fp.th2 * fp.tw2) + sgy * fp.tw2 + sgx) * 32 + (row & 31)) * 16 + c0 * 4
+                                : ((int64_t)b * p.N + row) * fp.map2 + (sgy * fp.tw2 + sgx) * 16 + c0 * 4;
                             if constexpr (HALF) {
                                 *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(fp.l2) + e2) =
                                     make_uint4(pack_h2(q2[0], q2[1]), pack_h2(q2[2], q2[3]), pack_h2(q2[4], q2[5]), pack_h2(q2[6], q2[7]));
@@ -528,7 +572,9 @@ volume_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                             const int y3 = sgy * 2 + (c >> 1);
                             if (!(y3 < fp.lh3 && sgx * 2 < fp.lw3)) o.x = 0.0f;
                             if (!(y3 < fp.lh3 && sgx * 2 + 1 < fp.lw3)) o.y = 0.0f;
-                            const int64_t e3 = ((int64_t)b * p.N + row) * fp.map3 + (ty3 * fp.tw3 + tx3) * 16 +
+                            const int64_t e3 = (GROUPED
+                                ? ((((int64_t)b * fp.ng + (row >> 5)) * (fp.th3 * fp.tw3) + ty3 * fp.tw3 + tx3) * 32 + (row & 31)) * 16
+                                : ((int64_t)b * p.N + row) * fp.map3 + (ty3 * fp.tw3 + tx3) * 16) +
                                                ((sgy & 1) * 2 + (c >> 1)) * 4 + (sgx & 1) * 2;
                             // quarters of this level-3 tile whose super-group does not exist stay exact zeros
                             const bool ghost_x = (sgx == fp.sgw - 1) && !(sgx & 1);
@@ -928,7 +974,7 @@ enum : int { PHASE_ALL = 0, PHASE_STAGE = 1, PHASE_GEMM = 2 };
 static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int B, int D, int h, int w, int precision,
                        void* workspace, size_t workspace_bytes, void* stream, int out_mode, float* const* lvl = nullptr,
                        int num_levels = 1, int q0 = 0, int nq = -1, int phase = PHASE_ALL, float divisor = 0.0f,
-                       bool out_half = false) {
+                       bool out_half = false, bool grouped = false) {
     // q0 / nq: only the queries [q0, q0 + nq) are computed (chunked build); phase: stage the operands, run the
     // GEMM on already staged operands, or both.
     const bool tiled = out_mode != OUT_ROWMAJOR;
@@ -1017,6 +1063,21 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
         // (128 B, one per chunk), level 1 in unswizzled boxes of 32 queries x 32 halfs (64 B)
         const uint64_t eb = out_half ? 2 : 4;
         const CUtensorMapDataType odt = out_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        if (grouped) {
+            // levels 0 and 1 as 2-D arrays of 64-byte rows (one tile of one query each): [B*NG*th*tw*32][16 floats]
+            FFCORR_REQUIRE(!out_half, FFCORR_EINVAL, "volume: the grouped layout stores fp32");
+            const int64_t ng = ceil_div(Nq, 32);
+            const int64_t rows0 = (int64_t)B * ng * th0 * tw0 * 32, rows1 = (int64_t)B * ng * th1 * tw1 * 32;
+            FFCORR_REQUIRE(rows0 < (1ll << 31), FFCORR_EINVAL, "volume: grouped level 0 has too many tile rows (%lld)", (long long)rows0);
+            const uint32_t box[2] = {16, 64};
+            const uint64_t strides[1] = {64};
+            const uint64_t d0[2] = {16, (uint64_t)rows0}, d1[2] = {16, (uint64_t)rows1};
+            if (int rc = encode_tensor_map(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, lvl[0], d0, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, "G0"))
+                return rc;
+            if (int rc = encode_tensor_map(&tl1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, lvl[1], d1, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, "G1"))
+                return rc;
+            fp.ng = (int)ng;
+        } else {
         {
             const uint32_t box[4] = {out_half ? 64u : 32u, 1, 32, 1};
             const uint64_t dims[4] = {(uint64_t)tw0 * 16, (uint64_t)th0, (uint64_t)Nq, (uint64_t)B};
@@ -1033,6 +1094,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
             if (int rc = encode_tensor_map(&tl1, odt, 4, lvl[1], dims, strides, box,
                                            out_half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, "L1"))
                 return rc;
+        }
         }
         fp.levels = num_levels;
         fp.sgw = tlb.tw;
@@ -1096,7 +1158,17 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
                                                                                                             idesc);   \
     } while (0)
     FFCORR_REQUIRE(!out_half || fused, FFCORR_EINVAL, "volume: fp16 storage is produced by the fused build (2-4 levels) only");
-    if (fused && out_half) {
+    FFCORR_REQUIRE(!grouped || fused, FFCORR_EINVAL, "volume: the grouped layout is produced by the fused build (2-4 levels) only");
+#define FF_GEMM_G(TF, DV)                                                                                             \
+    do {                                                                                                              \
+        if (int rc = set_smem(volume_gemm_kernel<TF, true, DV, true, false, true>, Cfg<true>::SMEM_TOTAL)) return rc; \
+        volume_gemm_kernel<TF, true, DV, true, false, true><<<grid, Cfg<true>::THREADS, Cfg<true>::SMEM_TOTAL, s>>>(ta, tb, tc, tl1, p, fp, \
+                                                                                                                   idesc);   \
+    } while (0)
+    if (fused && grouped) {
+        if (tf32) { if (p.use_div) FF_GEMM_G(true, true); else FF_GEMM_G(true, false); }
+        else      { if (p.use_div) FF_GEMM_G(false, true); else FF_GEMM_G(false, false); }
+    } else if (fused && out_half) {
         if (tf32) { if (p.use_div) FF_GEMM_H(true, true); else FF_GEMM_H(true, false); }
         else      { if (p.use_div) FF_GEMM_H(false, true); else FF_GEMM_H(false, false); }
     } else if (fused) {
@@ -1111,6 +1183,7 @@ static int volume_impl(const float* fmap1, const float* fmap2, float* lvl0, int 
 #undef FF_GEMM
 #undef FF_GEMM_F
 #undef FF_GEMM_H
+#undef FF_GEMM_G
     return check_launch("volume_gemm_kernel");
 }
 
@@ -1207,6 +1280,23 @@ extern "C" int ffcorr_build_tiled_f16(const float* fmap1, const float* fmap2, vo
     // the level pointers travel as float* through the shared implementation; the HALF kernel reinterprets them
     return volume_impl(fmap1, fmap2, reinterpret_cast<float*>(lvl[0]), B, D, h, w, precision, workspace, workspace_bytes, stream,
                        OUT_FUSED_PYRAMID, reinterpret_cast<float* const*>(lvl), num_levels, 0, -1, PHASE_ALL, 0.0f, true);
+}
+
+extern "C" int ffcorr_build_grouped_f32(const float* fmap1, const float* fmap2, float* const* lvl, int num_levels, int B, int D,
+                                        int h, int w, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    FFCORR_REQUIRE(lvl != nullptr, FFCORR_EINVAL, "build_grouped: null level table");
+    if (int rc = check_levels(num_levels, h, w, "build_grouped")) return rc;
+    FFCORR_REQUIRE(num_levels >= 2 && ffcorr_tiled_supported(num_levels, h, w), FFCORR_EINVAL,
+                   "build_grouped: %dx%d with %d levels is outside the fused build (2-4 levels)", h, w, num_levels);
+    FFCORR_REQUIRE(precision != FFCORR_PREC_FP32, FFCORR_EINVAL, "build_grouped: needs a tensor-core operand precision");
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "build_grouped: B=%d", B);
+    if (B == 0) return FFCORR_OK;
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "build_grouped: lvl[%d] is null", i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "build_grouped: lvl[%d] must be 16-byte aligned", i);
+    }
+    return volume_impl(fmap1, fmap2, lvl[0], B, D, h, w, precision, workspace, workspace_bytes, stream, OUT_FUSED_PYRAMID, lvl,
+                       num_levels, 0, -1, PHASE_ALL, 0.0f, false, true);
 }
 
 extern "C" int ffcorr_stage_operands_f32(const float* fmap1, const float* fmap2, int num_levels, int B, int D, int h, int w,

@@ -179,6 +179,25 @@ int ffcorr_untile_f16(const void* tiled, float* dst, int64_t Q, int h_level, int
 int ffcorr_tile_f16(const float* src, void* tiled, int64_t Q, int h_level, int w_level, void* stream);
 
 /*
+ * Grouped ("G32") tile order (the Python side: CorrBlock(..., layout="grouped")).  Same 4x4-pixel tiles, same values,
+ * but 32 consecutive queries share one tile grid: level i = [B][NG = ceil(N/32)][th_i * tw_i][32 queries][4][4] floats,
+ * ffcorr_grouped_level_elems() of them.  Neighbouring queries' windows overlap under any smooth flow, so the tiles a
+ * lookup warp gathers -- and the pieces an epilogue warp of the build writes (8 KB of level 0, 4 KB of level 1 per chunk)
+ * -- are contiguous in memory instead of one map (~30 KB) apart.  ffcorr_build_grouped_f32 / ffcorr_lookup_grouped_f32
+ * take the arguments of ffcorr_build_tiled_f32 / ffcorr_lookup_tiled_f32 and return the same values (2 <= num_levels
+ * <= 4, tensor-core precisions); ffcorr_ungroup_f32 / ffcorr_group_f32 convert a level to / from the reference's
+ * row-major [B*N, h_i, w_i].
+ */
+int64_t ffcorr_grouped_level_elems(int h, int w, int level, int B, int num_queries);
+int ffcorr_build_grouped_f32(const float* fmap1, const float* fmap2, float* const* lvl, int num_levels,
+                             int B, int D, int h, int w, int precision,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int ffcorr_lookup_grouped_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
+                              int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream);
+int ffcorr_ungroup_f32(const float* grouped, float* dst, int B, int N, int h_level, int w_level, void* stream);
+int ffcorr_group_f32(const float* src, float* grouped, int B, int N, int h_level, int w_level, void* stream);
+
+/*
  * Query-chunked build + lookup: AlternateCorrBlock semantics (corr.py:63-91) -- the same lookup values with
  * O(nq * h*w) instead of O((h*w)^2) pyramid memory, recomputed per lookup.  Stage the GEMM operands once per
  * image pair (ffcorr_stage_operands_f32, same workspace as ffcorr_volume_f32), then per lookup and per chunk of

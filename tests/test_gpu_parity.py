@@ -1306,3 +1306,29 @@ def test_launches_follow_the_tensors_device_not_the_current_one():
         m.CorrBlock(f1.to(DEV), f2.to(dev1))
     with pytest.raises(ValueError):
         blk(coords.to(DEV))
+
+
+# ---------------------------------------------------------------- grouped ("G32") tile order
+@pytest.mark.parametrize("shape,nl,radius", [((1, 256, 46, 62), 4, 4), ((2, 64, 17, 21), 4, 4), ((1, 64, 47, 156), 4, 4),
+                                             ((2, 32, 24, 40), 3, 3), ((1, 40, 16, 24), 2, 2), ((3, 48, 33, 47), 4, 1)])
+@pytest.mark.parametrize("precision", ["fp16", "tf32"])
+def test_grouped_layout_is_the_tiled_layout_reordered(shape, nl, radius, precision):
+    """CorrBlock(layout="grouped"): [group of 32 queries][tile][query][4][4] storage written by the fused build's epilogue
+    in contiguous 8 KB / 4 KB pieces.  Same GEMM, same pooling, same lookup code -- only addresses differ -- so every level
+    and every lookup (both output layouts, every coordinate regime, query counts that are not multiples of 32) must be
+    BIT-identical to the tiled block's."""
+    m = ff()
+    b, d, h, w = shape
+    rng = np.random.default_rng(123)
+    f1 = t((rng.standard_normal(shape) * 4.4).astype(np.float32))
+    f2 = t((rng.standard_normal(shape) * 4.4).astype(np.float32))
+    ref = m.CorrBlock(f1, f2, num_levels=nl, radius=radius, precision=precision, layout="tiled")
+    for cl in (False, True):
+        blk = m.CorrBlock(f1, f2, num_levels=nl, radius=radius, precision=precision, layout="grouped", channels_last=cl)
+        assert blk._levels[0].dim() == 3 and blk._levels[0].shape[0] == b * ((h * w + 31) // 32)
+        ref.channels_last = cl
+        for i in range(nl):
+            assert torch.equal(blk.corr_pyramid[i], ref.corr_pyramid[i]), (cl, i)
+        for name, c in _coords_cases(rng, b, h, w).items():
+            got, want = blk(t(c)), ref(t(c))
+            assert got.shape == want.shape and torch.equal(got, want), (cl, name, int((got != want).sum()))

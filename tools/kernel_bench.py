@@ -139,6 +139,20 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
     def k_lookup_h():
         _lib.check(L.ffcorr_lookup_tiled_f16(hptrs, nl, coords.data_ptr(), out_nhwc.data_ptr(), b, h, w, r, 1, 1, stream), "lookup_tiled_f16")
 
+    ng = (n + 31) // 32
+    tg = [torch.empty(int(L.ffcorr_grouped_level_elems(h, w, i, b, n)), device=dev) for i in range(nl)]
+    gptrs = _lib.ptr_array(tg)
+
+    def k_build_g():
+        _lib.check(L.ffcorr_build_grouped_f32(f1.data_ptr(), f2.data_ptr(), gptrs, nl, b, d, h, w, code, ws.data_ptr(), ws_bytes,
+                                              stream), "build_grouped")
+
+    def k_lookup_g():
+        _lib.check(L.ffcorr_lookup_grouped_f32(gptrs, nl, coords.data_ptr(), out.data_ptr(), b, h, w, r, 1, 0, stream), "lookup_grouped")
+
+    def k_lookup_g_nhwc():
+        _lib.check(L.ffcorr_lookup_grouped_f32(gptrs, nl, coords.data_ptr(), out_nhwc.data_ptr(), b, h, w, r, 1, 1, stream), "lookup_grouped_nhwc")
+
     res = []
     lv_elems = [(h >> i) * (w >> i) for i in range(nl)]
     vol_flops = 2.0 * b * n * n * d
@@ -155,6 +169,8 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         pyr_h = 2.0 * b * n * sum(lv_elems[1:])
         look_h = b * n * (nl * (2 * r + 2) ** 2 * 2 + nl * (2 * r + 1) ** 2 * 4 + 8)
         todo += [("build_fused_f16", k_build_h, vol_h + pyr_h, vol_flops), ("lookup_tiled_f16", k_lookup_h, look_h, 0.0)]
+        todo += [("build_grouped", k_build_g, vol_bytes + pyr_bytes - 4.0 * b * n * lv_elems[0], vol_flops),
+                 ("lookup_grouped", k_lookup_g, look_bytes, 0.0), ("lookup_grouped_nhwc", k_lookup_g_nhwc, look_bytes, 0.0)]
     if tiled_ok and (not only or "alt_lookup" in only):
         # memory-bounded AlternateCorrBlock: the pyramid of a 512 MiB query chunk is rebuilt for every lookup
         alt = ff.AlternateCorrBlock(f1, f2, num_levels=nl, radius=r, precision=precision)
@@ -169,7 +185,8 @@ def time_kernels(config=2, iters=10, precision="fp16", dev="cuda:0", sigma=3.0, 
         if only and name not in only:
             # run (untimed) only what a selected kernel reads
             needs = {"pyramid": ["volume"], "lookup": ["volume", "pyramid"], "pyramid_tiled": ["volume_tiled"],
-                     "lookup_tiled": ["build_fused"], "lookup_tiled_nhwc": ["build_fused"], "lookup_tiled_f16": ["build_fused_f16"]}
+                     "lookup_tiled": ["build_fused"], "lookup_tiled_nhwc": ["build_fused"], "lookup_tiled_f16": ["build_fused_f16"],
+                     "lookup_grouped": ["build_grouped"], "lookup_grouped_nhwc": ["build_grouped"]}
             if any(name in needs.get(o, []) for o in only):
                 fn()
             continue
