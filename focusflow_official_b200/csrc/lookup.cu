@@ -567,26 +567,21 @@ __global__ void __launch_bounds__(kStreamWarps * 32) lookup_tiled_stream_kernel(
 constexpr int kNhwcWarps = FFCORR_NHWC_WARPS;
 constexpr int kNhwcQ = 8;          // queries per warp
 
-// Storage type T of the pyramid: float (ffcorr_build_tiled_f32) or __half (ffcorr_build_tiled_f16: the same 4x4 tiles at
-// 32 bytes each -- one DRAM sector per tile instead of two; the arithmetic stays fp32).  Row-buffer pitch per window:
-// 80 bytes (20 floats) / 48 bytes (24 halfs): both put 8 consecutive lanes on 8 distinct 16-byte bank groups.
+// Storage type T of the pyramid: float here; the fp16-stored pyramid (ffcorr_build_tiled_f16) has its own row-pair
+// kernel below.  Row-buffer pitch per window: 80 bytes (20 floats), which puts 8 consecutive lanes on 8 distinct 16-byte
+// bank groups.
 template <typename T> struct RowGeom;
 template <> struct RowGeom<float> { static constexpr int PITCH = 20; };
-template <> struct RowGeom<__half> { static constexpr int PITCH = 24; };
 
 template <typename T>
 __host__ __device__ constexpr int nhwc_warp_bytes(int K, int CT) {
     return kStreamStages * kTile * RowGeom<T>::PITCH * (int)sizeof(T) + (K * kTile + kNhwcQ * CT) * 4;
 }
 
-// 8-byte variant of the gather copy for fp16 tiles (a tile row is 4 halfs); .cg exists for 16 bytes only
-__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-
 template <int R, bool CUDA_SEM, typename T>
 __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(const LookupTiledParams p) {
-    constexpr bool HALF = sizeof(T) == 2;
+    static_assert(sizeof(T) == 4, "fp32 tiles; see lookup_tiled_nhwc_h_kernel for fp16 storage");
+    constexpr bool HALF = false;
     constexpr int PITCH = RowGeom<T>::PITCH;             // elements per window row buffer
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;
@@ -712,10 +707,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
                 const unsigned m = gmask[j] >> rows_issued;
                 const bool ok = m & 1u;
                 const T* src = tbase[j] + (ok ? goff[j] : 0);
-                if constexpr (HALF)
-                    cp_async8_zfill(issue_saddr + gdst + (unsigned)(j * 8 * PITCH * sizeof(T)), src, ok ? 8u : 0u);
-                else
-                    cp_async16_zfill(issue_saddr + gdst + (unsigned)(j * 8 * PITCH * sizeof(T)), src, ok ? 16u : 0u);
+                cp_async16_zfill(issue_saddr + gdst + (unsigned)(j * 8 * PITCH * sizeof(T)), src, ok ? 16u : 0u);
                 goff[j] += (m & 0x10000u) ? gnext[j] : 4;
             }
             ++rows_issued;

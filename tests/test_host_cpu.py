@@ -102,6 +102,15 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert L.ffcorr_volume_scaled_f32(1, 1, 1, 1, 8, 8, 8, 0, ctypes.c_float(0.0), None, 0, None) == -1
     assert b"divisor" in L.ffcorr_last_error()
     assert L.ffcorr_stage_operands_f32(1, 1, 9, 1, 8, 8, 8, 0, None, 0, None) == -1                 # 9 levels
+    # round-2 entry points: fp16 storage, grouped tile order, backwarp
+    assert L.ffcorr_build_tiled_f16(1, 1, ptrs, 1, 1, 256, 16, 16, 0, None, 0, None) == -1           # needs 2-4 levels
+    assert L.ffcorr_build_tiled_f16(1, 1, ptrs, 4, 1, 256, 16, 16, 1, None, 0, None) == -1           # no fp32-operand variant
+    assert L.ffcorr_build_grouped_f32(1, 1, ptrs, 5, 1, 256, 64, 64, 0, None, 0, None) == -1         # > 4 levels
+    assert L.ffcorr_lookup_tiled_f16(ptrs, 4, 1, 1, 1, 16, 16, 4, 1, 0, None) == -1                  # NCHW output: channels-last only
+    assert L.ffcorr_grouped_level_elems(47, 156, 0, 8, 7332) == 8 * 230 * 12 * 40 * 512
+    assert L.ffcorr_grouped_level_elems(47, 156, 3, 1, 33) == 2 * 2 * 6 * 512
+    assert L.ffcorr_backwarp_f32(1, 1, 1, 1, 1, 1, 0, 8, 8, ctypes.c_float(1.0), None) == -1         # C = 0
+    assert L.ffcorr_backwarp_f32(None, None, None, None, None, 0, 32, 8, 8, ctypes.c_float(1.0), None) == 0   # empty batch
     # empty batches are a no-op, even with null pointers
     assert L.ffcorr_lookup_f32(None, 4, None, None, 0, 16, 16, 4, 1, 1, None) == 0
     assert L.ffcorr_build_tiled_f32(None, None, ptrs, 4, 0, 256, 16, 16, 0, None, 0, None) == 0
