@@ -227,10 +227,7 @@ __global__ void __launch_bounds__(PWC_THREADS, 1) pwc81_kernel(const float* __re
 // (`two` tile + halo, `one` tile; out-of-image and past-C elements are zero-filled by the TMA unit),
 // so the 288 compute threads spend no instructions or registers on staging.  3-stage mbarrier ring.
 // ------------------------------------------------------------------------------------------
-constexpr int TMA_STAGE_BYTES = STAGE_FLOATS * 4;                       // 31744 = 248 * 128
-constexpr int TMA_STAGES = 3;
-constexpr size_t PWC_TMA_SMEM = (size_t)TMA_STAGES * TMA_STAGE_BYTES + 1024 + 64;
-static_assert((PCC * S2 * 4) % 128 == 0 && TMA_STAGE_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
+constexpr int TMA_STAGES = 3;        // stage sizes depend on the tile height: PwcGeom<TY>
 
 __device__ __forceinline__ void pw_mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -256,10 +253,27 @@ __device__ __forceinline__ void pw_tma_load_4d(uint32_t dst, const void* tmap, u
         : "memory");
 }
 
-template <bool POW2>
-__global__ void __launch_bounds__(PWC_THREADS, 2)
+// Tile height TY: 8 (9 warps, a warp = one dy, lanes = 8 rows x 4 strips) for levels with enough tiles to fill the SMs;
+// 4 (5 warps, a warp = TWO dy, lanes = dy-half x 4 rows x 4 strips; the tenth dy slot idles) for the small levels:
+// twice the CTAs at a third less shared memory each, so 28x64 and below -- latency-bound at <= 128 tiles for 148 SMs --
+// run two to three CTAs per SM instead of one.
+template <int TY> struct PwcGeom {
+    static constexpr int PH = TY + 2 * PHALO;                 // rows of `two` per tile
+    static constexpr int SZ2 = PH * PITCH2;                   // floats per channel, `two` tile + halo
+    static constexpr int SZ1 = TY * PITCH1;                   // floats per channel, `one` tile
+    static constexpr int STAGE_BYTES = PCC * (SZ2 + SZ1) * 4;
+    static constexpr int THREADS = TY == 8 ? 9 * 32 : 5 * 32;
+    static constexpr size_t SMEM = (size_t)TMA_STAGES * STAGE_BYTES + 1024 + 64;
+    static_assert((PCC * SZ2 * 4) % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(72 * THREADS * 4 <= TMA_STAGES * STAGE_BYTES, "the cluster reduce reuses the stage ring");
+};
+
+template <bool POW2, int TY>
+__global__ void __launch_bounds__(PwcGeom<TY>::THREADS, TY == 8 ? 2 : 3)
 pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_constant__ CUtensorMap tm_two,
                  float* __restrict__ out, int C, int H, int W, float inv_c, float leaky_slope) {
+    using G = PwcGeom<TY>;
+    constexpr int S2 = G::SZ2, S1 = G::SZ1, TMA_STAGE_BYTES = G::STAGE_BYTES, PWC_THREADS = G::THREADS, PT_Y = TY;
     // NOTE: index the extern array directly -- rounding the pointer up through uintptr_t makes the
     // compiler lose the shared address space and emit generic LD.E instead of LDS for the hot loop.
     extern __shared__ __align__(1024) uint8_t base[];
@@ -276,9 +290,10 @@ pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_consta
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * PT_Y, x0 = (blockIdx.x / csize) * PT_X;
     const int tid = threadIdx.x;
-    const int dyi = tid >> 5;
     const int lane = tid & 31;
-    const int row = lane >> 2;
+    const int dyi = TY == 8 ? (tid >> 5) : (tid >> 5) * 2 + (lane >> 4);      // TY == 4: dy slot 9 does not exist
+    const bool dy_on = dyi < 9;
+    const int row = TY == 8 ? (lane >> 2) : ((lane >> 2) & 3);
     const int c8 = (lane & 3) * 8;
     const int nstage_all = (C + PCC - 1) / PCC;
     const int nstage = (nstage_all - (int)crank + (int)csize - 1) / (int)csize;   // my share
@@ -318,7 +333,7 @@ pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_consta
 #pragma unroll 1
         for (int c = 0; c < PCC; ++c) {
             const float* ap = s1 + c * S1 + row * PITCH1 + c8;
-            const float* tp = s2 + c * S2 + (row + dyi) * PITCH2 + c8;
+            const float* tp = s2 + c * S2 + (row + (dy_on ? dyi : 8)) * PITCH2 + c8;   // the idle slot reads a valid row
             const float4 a0 = *reinterpret_cast<const float4*>(ap);
             const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
             const float4 t0 = *reinterpret_cast<const float4*>(tp);
@@ -364,7 +379,7 @@ pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_consta
             }
             const int px = k / 9, dx = k - px * 9;
             const int gx = x0 + c8 + px;
-            if (gy < H && gx < W) {
+            if (dy_on && gy < H && gx < W) {
                 float v = POW2 ? sum * inv_c : __fdiv_rn(sum, fc);
                 if (leaky_slope >= 0.0f) v = v > 0.0f ? v : v * leaky_slope;
                 out[(((size_t)b * 81 + (size_t)dyi * 9 + dx) * H + gy) * W + gx] = v;
@@ -378,7 +393,7 @@ pwc81_tma_kernel(const __grid_constant__ CUtensorMap tm_one, const __grid_consta
     // ---- epilogue: /C (exact reciprocal multiply when C is a power of two, else a true division like
     //      correlation.py:97), optional fused leaky_relu ----
     const int gy = y0 + row;
-    if (gy >= H) return;
+    if (gy >= H || !dy_on) return;
     const float fc = (float)C;
     const int gx = x0 + c8;
     const size_t plane = (size_t)H * W;
@@ -604,24 +619,31 @@ extern "C" int ffcorr_pwc81_f32(const float* one, const float* two, float* out, 
         CUtensorMap tm_one, tm_two;
         const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
         const uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)C * H * W * 4};
-        const uint32_t box_two[4] = {PITCH2, PH2, PCC, 1};
-        const uint32_t box_one[4] = {PITCH1, PT_Y, PCC, 1};
+        // small levels: half-height tiles (see PwcGeom)
+        const bool half_tiles = num_tiles <= (int64_t)sm_count() * 7 / 2 && H > 4;
+        const int ty = half_tiles ? 4 : 8;
+        const int tiles_y_k = ceil_div(H, ty);
+        const int64_t tiles_k = (int64_t)tiles_x * tiles_y_k * B;
+        const uint32_t box_two[4] = {PITCH2, (uint32_t)(ty + 2 * PHALO), PCC, 1};
+        const uint32_t box_one[4] = {PITCH1, (uint32_t)ty, PCC, 1};
         if (int rc = encode_tensor_map(&tm_two, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, two, dims, strides, box_two,
                                        CU_TENSOR_MAP_SWIZZLE_NONE, "pwc two")) return rc;
         if (int rc = encode_tensor_map(&tm_one, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, one, dims, strides, box_one,
                                        CU_TENSOR_MAP_SWIZZLE_NONE, "pwc one")) return rc;
-        // channel split across a cluster only while the grid stays within ONE CTA per SM: the DSMEM reduce-scatter
-        // and its two cluster barriers cost more than a few extra channel stages (28x64, C=96: split 4 = 47 us,
-        // no split = 128 CTAs x 12 stages), so splitting pays only for the levels that would leave most SMs idle.
+        // channel split across a cluster only while the grid stays within ONE CTA per SM (two for the half-height
+        // tiles, which fit three): the DSMEM reduce-scatter and its two cluster barriers cost more than a few extra
+        // channel stages (28x64, C=96: split 4 = 47 us, no split = 128 CTAs x 12 stages), so splitting pays only for
+        // the levels that would leave most SMs idle.
         const int nstage_all = ceil_div(C, PCC);
+        const int64_t cta_cap = (int64_t)sm_count() * (half_tiles ? 2 : 1);
         int split = 1;
-        while (split < 8 && (int64_t)num_tiles * split * 2 <= sm_count() && split * 2 <= nstage_all) split *= 2;
+        while (split < 8 && tiles_k * split * 2 <= cta_cap && split * 2 <= nstage_all) split *= 2;
         const bool pow2 = (C & (C - 1)) == 0;
         const float inv_c = 1.0f / (float)C;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(tiles_x * split, tiles_y, B);
-        cfg.blockDim = dim3(PWC_THREADS);
-        cfg.dynamicSmemBytes = PWC_TMA_SMEM;
+        cfg.gridDim = dim3(tiles_x * split, tiles_y_k, B);
+        cfg.blockDim = dim3(half_tiles ? PwcGeom<4>::THREADS : PwcGeom<8>::THREADS);
+        cfg.dynamicSmemBytes = half_tiles ? PwcGeom<4>::SMEM : PwcGeom<8>::SMEM;
         cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -630,13 +652,15 @@ extern "C" int ffcorr_pwc81_f32(const float* one, const float* two, float* out, 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (pow2) {
-            FFCORR_CUDA(cudaFuncSetAttribute(pwc81_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWC_TMA_SMEM));
-            FFCORR_CUDA(cudaLaunchKernelEx(&cfg, pwc81_tma_kernel<true>, tm_one, tm_two, out, C, H, W, inv_c, leaky_slope));
-        } else {
-            FFCORR_CUDA(cudaFuncSetAttribute(pwc81_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWC_TMA_SMEM));
-            FFCORR_CUDA(cudaLaunchKernelEx(&cfg, pwc81_tma_kernel<false>, tm_one, tm_two, out, C, H, W, inv_c, leaky_slope));
-        }
+#define FF_PWC_LAUNCH(P2, TYV)                                                                                                  \
+    do {                                                                                                                        \
+        FFCORR_CUDA(cudaFuncSetAttribute(pwc81_tma_kernel<P2, TYV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                                         (int)PwcGeom<TYV>::SMEM));                                                             \
+        FFCORR_CUDA(cudaLaunchKernelEx(&cfg, pwc81_tma_kernel<P2, TYV>, tm_one, tm_two, out, C, H, W, inv_c, leaky_slope));     \
+    } while (0)
+        if (half_tiles) { if (pow2) FF_PWC_LAUNCH(true, 4); else FF_PWC_LAUNCH(false, 4); }
+        else            { if (pow2) FF_PWC_LAUNCH(true, 8); else FF_PWC_LAUNCH(false, 8); }
+#undef FF_PWC_LAUNCH
         return check_launch("pwc81_tma_kernel");
     }
     if (aligned) {
