@@ -422,6 +422,7 @@ class LaunchMeter:
         self.enabled = False
         self.tiled = False
         self.nhwc = False
+        self.fused_conv = False
         self.storage_bytes = 4
 
     def install(self):
@@ -479,8 +480,23 @@ class LaunchMeter:
             meter.storage_bytes = out[0].element_size()
             return out
 
+        raw_lookup_conv = C.CorrBlock.lookup_conv
+
+        def lookup_conv(blk, coords, conv):
+            if not meter.enabled:
+                return raw_lookup_conv(blk, coords, conv)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = raw_lookup_conv(blk, coords, conv)
+            e1.record()
+            meter.lookup_events.append((e0, e1))
+            meter.launches += 1
+            meter.tiled = meter.nhwc = meter.fused_conv = True
+            return out
+
         C._lookup_raw, C._volume_pyramid_raw = lookup, build
         C._lookup_tiled_raw, C._volume_pyramid_tiled_raw = lookup_t, build_t
+        C.CorrBlock.lookup_conv = lookup_conv
 
     def mean_ms(self, events):
         if not events:
@@ -561,6 +577,8 @@ def run_gpu_arm(args, rank, world, local):
         model.flow_net.update_channels_last = True
     if args.storage:
         model.flow_net.corr_storage = args.storage
+    if args.fuse_convc1:
+        model.flow_net.fuse_convc1 = True
     meter = LaunchMeter()
     meter.install()
 
@@ -676,10 +694,12 @@ def run_gpu_arm(args, rank, world, local):
     n_query = sub_batches[0] * h8 * w8
     # SURVEY 8d per-query bytes; with the opt-in fp16 storage the window reads are 2-byte elements
     algo_bytes = n_query * (LOOKUP_BYTES_PER_QUERY if meter.storage_bytes == 4 else 4 * 100 * 2 + 324 * 4 + 8)
+    if meter.fused_conv:      # the fused lookup + convc1 writes 256 outputs per query instead of the 324 samples
+        algo_bytes = n_query * (4 * 100 * 4 + 256 * 4 + 8)
     achieved = algo_bytes / (lookup_ms * 1e-3) / 1e9 if lookup_ms else None
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "lookup_traffic.json")
-    if os.path.exists(tpath) and args.config == 2 and b == BATCH:
+    if os.path.exists(tpath) and args.config == 2 and b == BATCH and not meter.fused_conv:
         try:
             tj = json.load(open(tpath))
             key = "nhwc" if meter.nhwc else "nchw"
@@ -737,7 +757,8 @@ def run_gpu_arm(args, rank, world, local):
         "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32 (fp16 GEMM operands, fp32 accumulate; TF32 host convs)", "data": "synthetic",
         "config": {"workload": wl["name"].format(b=b, w=world), "batch_per_gpu": b, "pairs_this_rank_per_step": my_pairs, "iters": ITERS,
                    "corr_precision": "fp16 operands, fp32 accumulate", "pyramid_layout": "tiled 4x4" if meter.tiled else "row-major",
-                   "pyramid_storage": storage, "lookup_output": "channels_last (NHWC), written by the kernel" if meter.nhwc else "NCHW",
+                   "pyramid_storage": storage, "lookup_output": ("none: convc1 + ReLU fused into the lookup kernel" if meter.fused_conv else
+                                     "channels_last (NHWC), written by the kernel" if meter.nhwc else "NCHW"),
                    "host_convs": "PyTorch/cuDNN TF32 (reference ALLOW_TF32)", "channels_last": bool(args.channels_last), "update_block_channels_last": bool(args.update_cl),
                    "l2": "per-step working set (2.3 GB pyramid + activations) >> 126 MB L2, no flush needed",
                    "sharding": "by image pair, no data-path collective",
@@ -746,7 +767,8 @@ def run_gpu_arm(args, rank, world, local):
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": ("lookup_tiled_nhwc_kernel<4> (ffcorr_lookup_tiled_f32, out_channels_last)" if meter.nhwc else
+        "roofline": {"kernel": "lookup_convc1_kernel (ffcorr_lookup_convc1_tiled_f32: lookup + convc1 + ReLU)" if meter.fused_conv else
+                               ("lookup_tiled_nhwc_kernel<4> (ffcorr_lookup_tiled_f32, out_channels_last)" if meter.nhwc else
                                 "lookup_tiled_stream_kernel<4> (ffcorr_lookup_tiled_f32)") if meter.tiled else "lookup_kernel<4> (ffcorr_lookup_f32)",
                      "bound": "hbm",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -1024,6 +1046,7 @@ def main():
                     help="BASELINE.json config: 2 = KITTI inference (the headline, default), 3 = FF-PWC forward batch 16, "
                          "4 = Sintel 32-iteration inference, 64 pairs sharded over the ranks, 5 = training step with DDP")
     ap.add_argument("--storage", default=None, choices=[None, "fp32", "fp16"], help="pyramid storage of the CorrBlock (opt-in fp16)")
+    ap.add_argument("--fuse-convc1", action="store_true", help="lookup + convc1 + ReLU in one kernel (CorrBlock.lookup_conv)")
     ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch / reference-on-this-GPU comparison")
     ap.add_argument("--no-pwc", action="store_true", help="skip the config-3 cost-volume roofline entry")
     ap.add_argument("--no-cudnn-benchmark", dest="no_cudnn_benchmark", action="store_true", default=False,

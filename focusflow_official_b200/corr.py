@@ -29,6 +29,7 @@ Differences, all deliberate:
 from __future__ import annotations
 
 import os
+import weakref
 from typing import List, Optional
 
 import torch
@@ -517,9 +518,56 @@ class CorrBlock:
             return lookup_tiled(self._levels, coords, self.radius, self._ptrs, self.sampler, self.channels_last)
         return lookup(self._levels, coords, self.radius, self._ptrs, self.sampler, self.channels_last)
 
+    def supports_lookup_conv(self, conv) -> bool:
+        """Whether :meth:`lookup_conv` can replace ``relu(conv(self(coords)))`` for this block and this 1x1 convolution."""
+        w = getattr(conv, "weight", None)
+        return bool(self._tiled and not self._grouped and self._levels[0].dtype == torch.float32 and self.num_levels == 4
+                    and self.radius == 4 and w is not None and tuple(w.shape) == (256, 324, 1, 1) and conv.bias is not None
+                    and w.device == self._levels[0].device and w.dtype == torch.float32 and not torch.is_grad_enabled())
+
+    def lookup_conv(self, coords: torch.Tensor, conv) -> torch.Tensor:
+        """``relu(conv(self(coords)))`` for ``conv = BasicMotionEncoder.convc1`` (``update.py:82-83,90``) in ONE launch:
+        the 324 samples per query go straight into the tensor cores and never reach global memory.  Returns
+        ``[B, 256, h, w]`` fp32 in channels_last storage.  Inference only; fp16 operands, fp32 accumulate."""
+        b, two, h, w = coords.shape
+        if (b, h, w) != self._shape or two != 2:
+            raise ValueError(f"coords {tuple(coords.shape)} does not match the volume built for B,h,w={self._shape}")
+        if not self.supports_lookup_conv(conv):
+            raise ValueError("lookup_conv needs the fp32 tiled pyramid (4 levels, radius 4), a Conv2d(324, 256, 1) with bias "
+                             "on the same device, and no autograd")
+        _require_cuda(coords, "coords")
+        coords = coords.float().contiguous()
+        packed = _packed_convc1(conv)
+        bias = conv.bias.detach().contiguous()
+        store = torch.empty((b, h, w, 256), device=coords.device, dtype=torch.float32)
+        with _lib.on_device(coords, self._levels[0], packed, bias) as stream:
+            _lib.check(_lib.lib().ffcorr_lookup_convc1_tiled_f32(self._ptrs, 4, coords.data_ptr(), packed.data_ptr(), bias.data_ptr(),
+                                                                 store.data_ptr(), b, h, w, 4, self._sampler, stream),
+                       "ffcorr_lookup_convc1_tiled_f32")
+        return store.permute(0, 3, 1, 2)
+
     @staticmethod
     def corr(fmap1, fmap2, precision: Optional[str] = None):
         return correlation_volume(fmap1, fmap2, precision)
+
+
+_packed_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _packed_convc1(conv) -> torch.Tensor:
+    """convc1.weight in the fused kernel's operand order (fp16), re-packed only when the weight tensor changes."""
+    w = conv.weight
+    hit = _packed_cache.get(conv)
+    if hit is not None and hit[0] == (w.data_ptr(), w._version, w.device):
+        return hit[1]
+    L = _lib.lib()
+    packed = torch.empty(L.ffcorr_convc1_packed_bytes(), device=w.device, dtype=torch.uint8)
+    w2 = w.detach().reshape(w.shape[0], w.shape[1]).contiguous()
+    with _lib.on_device(w2) as stream:
+        _lib.check(L.ffcorr_pack_convc1_weight(w2.data_ptr(), w2.shape[0], w2.shape[1], packed.data_ptr(), stream),
+                   "ffcorr_pack_convc1_weight")
+    _packed_cache[conv] = ((w.data_ptr(), w._version, w.device), packed)
+    return packed
 
 
 class AlternateCorrBlock:

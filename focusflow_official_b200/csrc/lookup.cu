@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace ffcorr {
 
@@ -578,32 +579,39 @@ __host__ __device__ constexpr int nhwc_warp_bytes(int K, int CT) {
     return kStreamStages * kTile * RowGeom<T>::PITCH * (int)sizeof(T) + (K * kTile + kNhwcQ * CT) * 4;
 }
 
-template <int R, bool CUDA_SEM, typename T>
-__global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(const LookupTiledParams p) {
-    static_assert(sizeof(T) == 4, "fp32 tiles; see lookup_tiled_nhwc_h_kernel for fp16 storage");
+// Samples of one window, as the unit function below produces them: row() hands over the K samples (a = 0 .. K-1) of one
+// window row bb (fast path), tap() a single sample (exact per-tap path).  Output channel of (a, bb) is a*K + bb (corr.py:37-43).
+struct StageSink {                 // the fp32 [8 queries][CT] staging block of lookup_tiled_nhwc_kernel
+    float* sout;                   // this window's K*K samples
+    template <int K>
+    __device__ __forceinline__ void row(int bb, const float (&v)[K]) {
+#pragma unroll
+        for (int a = 0; a < K; ++a) sout[a * K + bb] = v[a];
+    }
+    template <int K>
+    __device__ __forceinline__ void tap(int a, int bb, float v) { sout[a * K + bb] = v; }
+};
+struct StageSinks {
+    float* stage;
+    int CT, KK;
+    __device__ __forceinline__ StageSink make(int q, int level) const { return StageSink{stage + q * CT + level * KK}; }
+};
+
+// One unit of work of the channels-last lookups: 8 consecutive queries [n0, n0 + 8) of batch item b x all levels, by one
+// warp (lane = level * 8 + query), streamed row by row through the warp's cp.async ring.  `ring` = S row buffers
+// of 32 windows x PITCH floats, `siy` = K x 32 floats of scratch.  All cp.async groups are drained on return.
+template <int R, bool CUDA_SEM, int S = kStreamStages, typename Sinks>
+__device__ __forceinline__ void nhwc_lookup_unit(const LookupTiledParams& p, const int b, const int n0, float* ring, float* siy,
+                                                 const int lane, const Sinks& sinks) {
+    using T = float;
     constexpr bool HALF = false;
     constexpr int PITCH = RowGeom<T>::PITCH;             // elements per window row buffer
     constexpr int K = 2 * R + 1;
     constexpr int W2 = K + 2;
-    constexpr int KK = K * K;
-    constexpr int S = kStreamStages;
     constexpr int ROWBUF = kTile * PITCH;                // elements per ring stage
     static_assert(W2 + 3 <= 16, "window + sub-tile shift must fit in the 16 columns of the tile block");
 
-    extern __shared__ __align__(16) unsigned char smem_nhwc[];
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int CT = p.num_levels * KK;
-    T* ring = reinterpret_cast<T*>(smem_nhwc + (size_t)warp * nhwc_warp_bytes<T>(K, CT));
-    float* siy = reinterpret_cast<float*>(ring + S * ROWBUF);
-    float* stage = siy + K * kTile;                      // [8 queries][CT]
-
-    const int b = blockIdx.x / p.blocks_per_batch;
-    const int unit = (blockIdx.x - b * p.blocks_per_batch) * kNhwcWarps + warp;
-    if (unit >= p.tiles_per_batch) return;               // warp-uniform; no block-level sync below
-
     const int N = p.N;
-    const int n0 = unit * kNhwcQ;
     const int lvl_of_lane = lane >> 3;
     const bool lvl_on = lvl_of_lane < p.num_levels;
     const int level = lvl_on ? lvl_of_lane : 0;
@@ -717,7 +725,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
         cp_async_commit();
     };
 
-    float* sout = stage + q * CT + level * KK;            // this window's K*K samples
+    auto sink = sinks.make(q, level);                     // where this window's K*K samples go
     const int shift = x_lo & 3;
     const T* my_row = ring + lane * PITCH;
 
@@ -766,8 +774,10 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
                 float w0, w1;
                 ytap(r - 1, w0, w1);
                 if (lvl_on) {
+                    float o[K];
 #pragma unroll
-                    for (int a = 0; a < K; ++a) sout[a * K + (r - 1)] = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
+                    for (int a = 0; a < K; ++a) o[a] = __fmaf_rn(w1, tcur[a], __fmul_rn(w0, tprev[a]));
+                    sink.template row<K>(r - 1, o);
                 }
             }
 #pragma unroll
@@ -800,7 +810,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
                         o = __fmaf_rn(v01, ne, o);
                         o = __fmaf_rn(v10, sw, o);
                         o = __fmaf_rn(v11, se, o);
-                        if (lvl_on) sout[a * K + bb] = o;
+                        if (lvl_on) sink.template tap<K>(a, bb, o);
                     }
                 }
             }
@@ -812,6 +822,32 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(cons
         }
     }
     cp_async_wait<0>();
+}
+
+template <int R, bool CUDA_SEM, typename T>
+__global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_kernel(const LookupTiledParams p) {
+    static_assert(sizeof(T) == 4, "fp32 tiles; see lookup_tiled_nhwc_h_kernel for fp16 storage");
+    constexpr int PITCH = RowGeom<T>::PITCH;
+    constexpr int K = 2 * R + 1;
+    constexpr int KK = K * K;
+    constexpr int S = kStreamStages;
+    constexpr int ROWBUF = kTile * PITCH;
+
+    extern __shared__ __align__(16) unsigned char smem_nhwc[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int CT = p.num_levels * KK;
+    T* ring = reinterpret_cast<T*>(smem_nhwc + (size_t)warp * nhwc_warp_bytes<T>(K, CT));
+    float* siy = reinterpret_cast<float*>(ring + S * ROWBUF);
+    float* stage = siy + K * kTile;                      // [8 queries][CT]
+
+    const int b = blockIdx.x / p.blocks_per_batch;
+    const int unit = (blockIdx.x - b * p.blocks_per_batch) * kNhwcWarps + warp;
+    if (unit >= p.tiles_per_batch) return;               // warp-uniform; no block-level sync below
+    const int N = p.N;
+    const int n0 = unit * kNhwcQ;
+
+    nhwc_lookup_unit<R, CUDA_SEM>(p, b, n0, ring, siy, lane, StageSinks{stage, CT, KK});
 
     // ---------------- flush: the warp's 8 x CT block is contiguous in the NHWC output ----------------
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA engine
@@ -1092,6 +1128,273 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) lookup_tiled_nhwc_h_kernel(co
             for (int i = 0; i < nq * CT; ++i) gdst_ptr[i] = stage[i];
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------
+// Lookup fused with its consumer: cor = relu(convc1(lookup(coords)))  -- BasicMotionEncoder,
+// update.py:82-83,90: a 1x1 convolution 324 -> 256 + ReLU over the lookup result, i.e. per query a [256 x 324] x [324]
+// product.  The 324 samples of a query never leave the SM: the gather warps write them as fp16 into a UMMA operand
+// tile in shared memory, the 5th-gen tensor cores multiply by the weights, and only the 256 outputs per query are written
+// (NHWC, what the next convolution of the update block reads).  Saves the 76 MB lookup result round trip and the
+// convolution launch per refinement iteration.
+//
+//   D^T[256 ch x 64 queries] = W'[256 x K'] * V^T[K' x 64 queries],  K' = 384 (360 used)
+//   * W' (A operand) lives in TENSOR MEMORY for the whole kernel: 2 halves of 128 channels x 192 columns (two fp16 per
+//     32-bit column), loaded once per CTA with tcgen05.st; the accumulators take the other 128 columns (512 in total, so
+//     one persistent CTA per SM).  No weight traffic per tile.
+//   * V (B operand): [64 queries][K'] fp16, K-major, 128B swizzle (6 atoms of 8 KB), double buffered.  K' orders the
+//     samples [level][window row bb][a] with 10 slots per (level, bb) (9 samples + a zero), so the row-streaming lookup
+//     emits one window row as five aligned half2 stores; the weights are permuted the same way on the host side
+//     (ffcorr_pack_convc1_weight).  Precision: fp16 operands (11 significant bits, like the TF32 convolution the
+//     reference runs under ALLOW_TF32), fp32 accumulate; samples saturate at +-65504.
+//   * warps 0-7: gather (one unit of 8 queries each per tile, nhwc_lookup_unit); warps 8-11: epilogue (TMEM -> +bias -> ReLU
+//     -> global; lane = channel, so a warp writes 128 contiguous bytes per query); warp 12: MMA issue (one thread).
+// ---------------------------------------------------------------------------------
+constexpr int kMoQ = 64;                       // queries per tile == UMMA N
+constexpr int kMoGatherWarps = kMoQ / kNhwcQ;  // 8
+constexpr int kMoEpiWarps = 4;
+constexpr int kMoThreads = (kMoGatherWarps + kMoEpiWarps + 1) * 32;   // 416
+constexpr int kMoSlots = 10;                   // K' slots per (level, window row): 9 samples + 1 zero
+constexpr int kMoKLevel = 9 * kMoSlots;        // 90
+constexpr int kMoK = 384;                      // padded K'
+constexpr int kMoKSteps = 23;                  // k-steps of 16 that hold data (K' < 368)
+constexpr int kMoCout = 256;
+constexpr int kMoAtomBytes = kMoQ * 128;       // one 64-wide K atom of the sample tile
+constexpr int kMoVBytes = (kMoK / 64) * kMoAtomBytes;                 // 48 KB
+#ifndef FFCORR_MO_STAGES
+#define FFCORR_MO_STAGES 4
+#endif
+constexpr int kMoStages = FFCORR_MO_STAGES;    // 8 gather warps per SM (the plain kernel has 10): one more row in flight per warp
+constexpr int kMoRingBytes = kMoStages * kTile * RowGeom<float>::PITCH * 4 + 9 * kTile * 4;   // ring + siy per gather warp
+constexpr int kMoOffRing = 2 * kMoVBytes;
+constexpr int kMoOffBar = kMoOffRing + kMoGatherWarps * kMoRingBytes;
+constexpr int kMoSmem = kMoOffBar + 64;
+constexpr int kMoWCols = kMoK / 2;             // TMEM columns per channel half of the weights (192)
+constexpr int kMoAccCol = 2 * kMoWCols;        // first accumulator column (384)
+static_assert(kMoAccCol + 2 * kMoQ == 512, "weights + accumulators fill the tensor memory exactly");
+static_assert(kMoSmem <= 227 * 1024, "shared memory budget");
+static_assert(kMoOffRing % 1024 == 0, "sample tiles must stay 1024-byte aligned (128B swizzle)");
+
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a
+    return r;
+}
+
+struct SampleTileSink {            // one query row of the fp16 operand tile
+    uint32_t row_addr;             // shared address of the row inside atom 0
+    uint32_t row7;                 // row & 7: the swizzle key
+    int kbase;                     // level * 90
+    __device__ __forceinline__ uint32_t addr(int k) const {
+        return row_addr + (uint32_t)(k >> 6) * kMoAtomBytes + ((((uint32_t)(k & 63) >> 3) ^ row7) << 4) + ((uint32_t)(k & 7) << 1);
+    }
+    template <int K>
+    __device__ __forceinline__ void row(int bb, const float (&v)[K]) {
+        static_assert(K == 9, "the fused kernel is written for radius 4");
+        const int k0 = kbase + bb * kMoSlots;          // even: a half2 never straddles a 16-byte chunk
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t h2 = pack_h2_sat(v[2 * i], i < 4 ? v[i < 4 ? 2 * i + 1 : 0] : 0.0f);   // slot 9 of the row: zero
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr(k0 + 2 * i)), "r"(h2) : "memory");
+        }
+    }
+    template <int K>
+    __device__ __forceinline__ void tap(int a, int bb, float v) {
+        const uint32_t h2 = pack_h2_sat(v, 0.0f);
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr(kbase + bb * kMoSlots + a)), "h"((unsigned short)(h2 & 0xffffu)) : "memory");
+    }
+};
+struct SampleTileSinks {
+    uint32_t tile_addr;            // shared address of the operand tile
+    int row0;                      // first row of this unit
+    __device__ __forceinline__ SampleTileSink make(int q, int level) const {
+        const uint32_t r = (uint32_t)(row0 + q);
+        return SampleTileSink{tile_addr + (r >> 3) * 1024u + (r & 7u) * 128u, r & 7u, level * kMoKLevel};
+    }
+};
+
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct ConvC1Params {
+    const uint32_t* wpacked;       // [256][192]: fp16 pairs of W' (ffcorr_pack_convc1_weight)
+    const float* bias;             // [256]
+    float* out;                    // [B, N, 256] (NHWC)
+    int num_tiles;                 // B * tiles_per_batch, tiles of 64 queries
+    uint32_t idesc;
+};
+
+template <bool CUDA_SEM>
+__global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const LookupTiledParams p, const ConvC1Params cp) {
+    constexpr int R = 4;
+    constexpr int S = kMoStages;
+    constexpr int ROWBUF = kTile * RowGeom<float>::PITCH;
+    extern __shared__ __align__(1024) uint8_t smem_mo[];
+    const uint32_t smem_base = smem_u32(smem_mo);
+    if (smem_base & 1023u) __trap();
+    const uint32_t bar_base = smem_base + kMoOffBar;
+    auto vfull = [&](int i) { return bar_base + 8u * i; };
+    auto vempty = [&](int i) { return bar_base + 8u * (2 + i); };
+    const uint32_t accfull = bar_base + 32u, accempty = bar_base + 40u, wready = bar_base + 48u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_mo + kMoOffBar + 56);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(vfull(i), kMoGatherWarps);
+            mbar_init(vempty(i), 1);
+        }
+        mbar_init(accfull, 1);
+        mbar_init(accempty, kMoEpiWarps);
+        mbar_init(wready, kMoEpiWarps);
+        fence_barrier_init();
+    }
+    if (warp == kMoGatherWarps + kMoEpiWarps) tmem_alloc(smem_u32(tmem_slot), 512);
+    // both sample tiles start as zeros: the pad slots (a = 9 of every window row, K' >= 360) are never written with
+    // anything else, and a 0 x NaN from uninitialised shared memory would poison the accumulators
+    for (int i = threadIdx.x; i < 2 * kMoVBytes / 16; i += kMoThreads)
+        reinterpret_cast<uint4*>(smem_mo)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= kMoGatherWarps && warp < kMoGatherWarps + kMoEpiWarps) {
+        // weights -> tensor memory: lane quarter e of TMEM = channels e*32 .. e*32+31 of either half
+        const int e = warp - kMoGatherWarps;                     // == warp % 4: the TMEM lanes this warp may touch
+        const uint32_t t_lane = tmem_base + ((uint32_t)(e * 32) << 16);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t* wrow = cp.wpacked + (size_t)(half * 128 + e * 32 + lane) * kMoWCols;
+#pragma unroll 1
+            for (int j = 0; j < kMoWCols / 32; ++j) {
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + j * 32) + i);
+                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+                }
+                tmem_st_32x32(t_lane + (uint32_t)(half * kMoWCols + j * 32), r);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(wready);          // only the MMA issuer waits for the weights; the gather starts at once
+    }
+
+    const int tiles_per_batch = p.tiles_per_batch;
+    if (warp < kMoGatherWarps) {
+        // ===================== gather warps: one unit of 8 queries per tile =====================
+        float* ring = reinterpret_cast<float*>(smem_mo + kMoOffRing + warp * kMoRingBytes);
+        float* siy = ring + S * ROWBUF;
+        int it = 0;
+        for (int t = blockIdx.x; t < cp.num_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(vempty(buf), (((uint32_t)it >> 1) & 1u) ^ 1u);       // the MMAs that read this tile two rounds ago retired
+            const int b = t / tiles_per_batch;
+            const int n0 = (t - b * tiles_per_batch) * kMoQ + warp * kNhwcQ;
+            if (n0 < p.N)
+                nhwc_lookup_unit<R, CUDA_SEM, S>(p, b, n0, ring, siy, lane, SampleTileSinks{smem_base + (uint32_t)(buf * kMoVBytes), warp * kNhwcQ});
+            fence_proxy_async_smem();                                       // generic writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(vfull(buf));
+        }
+    } else if (warp < kMoGatherWarps + kMoEpiWarps) {
+        // ===================== epilogue warps =====================
+        const int e = warp - kMoGatherWarps;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)kMoAccCol;
+        const float bias0 = __ldg(cp.bias + e * 32 + lane), bias1 = __ldg(cp.bias + 128 + e * 32 + lane);
+        int it = 0;
+        for (int t = blockIdx.x; t < cp.num_tiles; t += gridDim.x, ++it) {
+            const int b = t / tiles_per_batch;
+            const int n_tile = (t - b * tiles_per_batch) * kMoQ;
+            mbar_wait(accfull, (uint32_t)it & 1u);
+            tc_fence_after();
+            float* orow = cp.out + ((size_t)b * p.N + n_tile) * kMoCout + e * 32 + lane;
+            const int nq = min(kMoQ, p.N - n_tile);
+            uint32_t v[64];
+            tmem_ld_32x64(t_lane, v);                  // channels e*32+lane, queries 0..63
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < kMoQ; ++j)
+                if (j < nq) orow[(size_t)j * kMoCout] = fmaxf(__uint_as_float(v[j]) + bias0, 0.0f);
+            tmem_ld_32x64(t_lane + kMoQ, v);           // channels 128+e*32+lane
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accempty);      // the accumulators may be overwritten
+#pragma unroll
+            for (int j = 0; j < kMoQ; ++j)
+                if (j < nq) orow[(size_t)j * kMoCout + 128] = fmaxf(__uint_as_float(v[j]) + bias1, 0.0f);
+        }
+    } else if (lane == 0) {
+        // ===================== MMA issuer =====================
+        int it = 0;
+        mbar_wait(wready, 0);
+        for (int t = blockIdx.x; t < cp.num_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(vfull(buf), ((uint32_t)it >> 1) & 1u);
+            mbar_wait(accempty, ((uint32_t)it & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t vaddr = smem_base + (uint32_t)(buf * kMoVBytes);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(kMoAccCol + half * kMoQ);
+                const uint32_t a_tmem = tmem_base + (uint32_t)(half * kMoWCols);
+#pragma unroll 1
+                for (int ks = 0; ks < kMoKSteps; ++ks) {
+                    // B: atom ks >> 2 of the sample tile, +32 bytes per k-step inside the atom (== +2 in the address field)
+                    const uint64_t bdesc = make_smem_desc(vaddr + (uint32_t)((ks >> 2) * kMoAtomBytes)) + (uint64_t)((ks & 3) * 2);
+                    umma_ts_f16(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, cp.idesc, (uint32_t)(ks != 0));
+                }
+            }
+            umma_commit(vempty(buf));
+            umma_commit(accfull);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMoGatherWarps + kMoEpiWarps) tmem_dealloc(tmem_base, 512);
+}
+
+// W [256][L*81] (convc1.weight, input channel = level*81 + a*9 + bb, corr.py:37-43) -> W' [256][384] fp16 in the K' order of
+// the sample tile (level*90 + bb*10 + a; zero elsewhere), packed two per 32-bit word.
+__global__ void pack_convc1_weight_kernel(const float* __restrict__ w, uint32_t* __restrict__ packed, int cin) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kMoCout * kMoWCols) return;
+    const int row = idx / kMoWCols, j = idx - row * kMoWCols;
+    float v[2];
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        const int k = 2 * j + hlf;
+        const int level = k / kMoKLevel, rem = k - level * kMoKLevel;
+        const int bb = rem / kMoSlots, a = rem - bb * kMoSlots;
+        const int ci = level * 81 + a * 9 + bb;
+        v[hlf] = (a < 9 && ci < cin && level * 81 < cin) ? w[(size_t)row * cin + ci] : 0.0f;
+    }
+    packed[idx] = pack_h2(v[0], v[1]);
 }
 
 template <int R>
@@ -1496,6 +1799,70 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
                                        int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream) {
     return lookup_tiled_impl(lvl, num_levels, coords, out, B, h, w, h * w, (int64_t)h * w, (int64_t)h * w, radius, sampler,
                              out_channels_last, stream, "lookup_tiled");
+}
+
+extern "C" size_t ffcorr_convc1_packed_bytes(void) { return (size_t)kMoCout * kMoWCols * 4; }
+
+extern "C" int ffcorr_pack_convc1_weight(const float* weight, int cout, int cin, void* packed, void* stream) {
+    FFCORR_REQUIRE(weight && packed, FFCORR_EINVAL, "pack_convc1_weight: null pointer");
+    FFCORR_REQUIRE(cout == kMoCout && cin == 4 * 81, FFCORR_EINVAL,
+                   "pack_convc1_weight: the fused kernel is built for convc1 = Conv2d(324, 256, 1) (update.py:82), got %d -> %d", cin, cout);
+    const int total = kMoCout * kMoWCols;
+    pack_convc1_weight_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, reinterpret_cast<uint32_t*>(packed), cin);
+    return check_launch("pack_convc1_weight_kernel");
+}
+
+extern "C" int ffcorr_lookup_convc1_tiled_f32(const float* const* lvl, int num_levels, const float* coords, const void* packed_weight,
+                                              const float* bias, float* out, int B, int h, int w, int radius, int sampler,
+                                              void* stream) {
+    const char* who = "lookup_convc1_tiled";
+    FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "%s: B=%d", who, B);
+    if (B == 0) return FFCORR_OK;
+    FFCORR_REQUIRE(lvl && coords && packed_weight && bias && out, FFCORR_EINVAL, "%s: null pointer", who);
+    FFCORR_REQUIRE(num_levels == 4 && radius == 4, FFCORR_EINVAL,
+                   "%s: built for the reference's 4 levels x radius 4 (324 planes, update.py:82), got %d levels, radius %d", who,
+                   num_levels, radius);
+    if (int rc = check_sampler(sampler, who)) return rc;
+    if (int rc = check_levels(num_levels, h, w, who)) return rc;
+    FFCORR_REQUIRE((int64_t)h * w < (1ll << 24), FFCORR_EINVAL, "%s: h*w = %lld must be below 2^24", who, (long long)h * w);
+    FFCORR_REQUIRE((uintptr_t)packed_weight % 16 == 0 && (uintptr_t)out % 16 == 0, FFCORR_EALIGN, "%s: packed weight / out must be 16-byte aligned", who);
+    LookupTiledParams p{};
+    for (int i = 0; i < num_levels; ++i) {
+        FFCORR_REQUIRE(lvl[i] != nullptr, FFCORR_EINVAL, "%s: lvl[%d] is null", who, i);
+        FFCORR_REQUIRE((uintptr_t)lvl[i] % 16 == 0, FFCORR_EALIGN, "%s: lvl[%d] must be 16-byte aligned", who, i);
+        p.lvl[i] = lvl[i];
+        p.lh[i] = h >> i;
+        p.lw[i] = w >> i;
+        p.th[i] = tiled_th(p.lh[i]);
+        p.tw[i] = tiled_tw(p.lw[i]);
+    }
+    p.coords = coords;
+    p.out = nullptr;
+    p.B = B;
+    p.N = h * w;
+    p.coords_stride = (int64_t)h * w;
+    p.out_stride = (int64_t)h * w;
+    p.num_levels = num_levels;
+    p.tiles_per_batch = ceil_div(p.N, kMoQ);
+    p.blocks_per_batch = p.tiles_per_batch;
+    const int64_t num_tiles = (int64_t)B * p.tiles_per_batch;
+    FFCORR_REQUIRE(num_tiles < (1ll << 31), FFCORR_EINVAL, "%s: too many tiles", who);
+    ConvC1Params cp{};
+    cp.wpacked = reinterpret_cast<const uint32_t*>(packed_weight);
+    cp.bias = bias;
+    cp.out = out;
+    cp.num_tiles = (int)num_tiles;
+    // instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3, M >> 4 (M = 128 channels, N = 64 queries)
+    cp.idesc = (1u << 4) | ((uint32_t)(kMoQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    cudaStream_t s = (cudaStream_t)stream;
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_convc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMoSmem));
+    FFCORR_CUDA(cudaFuncSetAttribute(lookup_convc1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMoSmem));
+    if (sampler == FFCORR_SAMPLER_ATEN_CUDA)
+        lookup_convc1_kernel<true><<<grid, kMoThreads, kMoSmem, s>>>(p, cp);
+    else
+        lookup_convc1_kernel<false><<<grid, kMoThreads, kMoSmem, s>>>(p, cp);
+    return check_launch("lookup_convc1_kernel");
 }
 
 extern "C" int ffcorr_lookup_tiled_f16(const void* const* lvl, int num_levels, const float* coords, float* out,

@@ -205,8 +205,9 @@ class MotionEncoder(nn.Module):
         self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
         self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
 
-    def forward(self, flow, corr):
-        cor = _conv_relu(self.convc2, _conv_relu(self.convc1, corr))
+    def forward(self, flow, corr, cor1=None):
+        # cor1: relu(convc1(corr)) already computed by the fused lookup (CorrBlock.lookup_conv)
+        cor = _conv_relu(self.convc2, _conv_relu(self.convc1, corr) if cor1 is None else cor1)
         flo = _conv_relu(self.convf2, _conv_relu(self.convf1, flow))
         out = _conv_relu(self.conv, torch.cat([cor, flo], dim=1))
         return torch.cat([out, flow], dim=1)
@@ -222,8 +223,8 @@ class UpdateBlock(nn.Module):
         self.flow_head = FlowHead(hidden, 256)
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(256, 64 * 9, 1))
 
-    def forward(self, net, inp, corr, flow, with_mask: bool = True):
-        motion = self.encoder(flow, corr)
+    def forward(self, net, inp, corr, flow, with_mask: bool = True, cor1=None):
+        motion = self.encoder(flow, corr, cor1)
         net = self.gru(net, torch.cat([inp, motion], dim=1))
         delta = self.flow_head(net)
         mask = 0.25 * self.mask[2](_conv_relu(self.mask[0], net)) if with_mask else None  # 0.25: update.py:133-134
@@ -256,6 +257,9 @@ class RAFTBody(nn.Module):
         self.corr_precision: Optional[str] = None
         self.corr_sampler: Optional[str] = None      # None = the package default ("cuda": the reference's GPU run)
         self.corr_storage: Optional[str] = None      # None / "fp32" (default) or "fp16": opt-in half-precision pyramid
+        # opt-in: the lookup and the motion encoder's first layer (convc1 + ReLU, update.py:90) in one kernel
+        # (CorrBlock.lookup_conv); needs update_channels_last, inference only
+        self.fuse_convc1 = False
         # raft.py:63,195-196 `alternate_corr` (config key ALT_CORR): the memory-bounded block that recomputes the
         # pyramid per lookup; inference only, like the reference's alt_cuda_corr
         self.alternate_corr = False
@@ -300,15 +304,22 @@ class RAFTBody(nn.Module):
             inp = inp.contiguous(memory_format=torch.channels_last)
         predictions = []
         flow_up = None
+        convc1 = self.update_block.encoder.convc1
+        fused = bool(self.fuse_convc1 and cl and hasattr(corr_fn, "supports_lookup_conv") and corr_fn.supports_lookup_conv(convc1))
         for it in range(iters):
             coords1 = coords1.detach()  # raft.py:216 -> the lookup never needs d/d coords
-            corr = corr_fn(coords1)
+            corr = cor1 = None
+            if fused:
+                cor1 = corr_fn.lookup_conv(coords1, convc1)
+            else:
+                corr = corr_fn(coords1)
             flow = coords1 - coords0
             if cl:
-                corr = corr.contiguous(memory_format=torch.channels_last)   # a no-op for the B200 block (already NHWC)
+                if corr is not None:
+                    corr = corr.contiguous(memory_format=torch.channels_last)   # a no-op for the B200 block (already NHWC)
                 flow = flow.contiguous(memory_format=torch.channels_last)
             need_up = (not test_mode) or it == iters - 1
-            net, up_mask, delta = self.update_block(net, inp, corr, flow, with_mask=need_up)
+            net, up_mask, delta = self.update_block(net, inp, corr, flow, with_mask=need_up, cor1=cor1)
             coords1 = coords1 + delta
             if need_up:
                 flow_up = convex_upsample(coords1 - coords0, up_mask)

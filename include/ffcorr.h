@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define FFCORR_VERSION 200
+#define FFCORR_VERSION 201
 
 #define FFCORR_OK            0
 #define FFCORR_EINVAL      (-1)   /* bad shape / null pointer / unsupported argument   */
@@ -157,6 +157,22 @@ int ffcorr_build_tiled_f32(const float* fmap1, const float* fmap2, float* const*
                            void* workspace, size_t workspace_bytes, void* stream);
 int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float* coords, float* out,
                             int B, int h, int w, int radius, int sampler, int out_channels_last, void* stream);
+
+/*
+ * The lookup fused with its consumer: out = relu(convc1(lookup(coords))), the first layer of
+ * BasicMotionEncoder (update.py:82-83,90: Conv2d(324, 256, 1) + ReLU on the lookup result).  The 324 samples of a
+ * query are written as fp16 into a tensor-core operand tile in shared memory and never reach global memory; the
+ * weights stay in tensor memory for the whole launch.  out is [B, h, w, 256] fp32 (NHWC: what the next convolution
+ * of the update block reads under channels_last).  Same sample values as ffcorr_lookup_tiled_f32 before the
+ * rounding to fp16 (which has the 11 significant bits of the TF32 convolution the reference runs, common.py:25-27);
+ * fp32 accumulation; samples saturate at +-65504.  Built for the reference's 4 levels x radius 4 only.
+ *   ffcorr_pack_convc1_weight: convc1.weight [256, 324] fp32 (device) -> the kernel's operand order, fp16,
+ *   ffcorr_convc1_packed_bytes() bytes; do it once per set of weights.
+ */
+size_t ffcorr_convc1_packed_bytes(void);
+int ffcorr_pack_convc1_weight(const float* weight, int cout, int cin, void* packed, void* stream);
+int ffcorr_lookup_convc1_tiled_f32(const float* const* lvl, int num_levels, const float* coords, const void* packed_weight,
+                                   const float* bias, float* out, int B, int h, int w, int radius, int sampler, void* stream);
 
 /*
  * Opt-in HALF-PRECISION STORAGE of the pyramid (the Python side: CorrBlock(..., storage="fp16")).  Same geometry as
