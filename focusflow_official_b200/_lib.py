@@ -55,7 +55,7 @@ _PROTOS = {
     "ffcorr_build_tiled_f16": (_i, [_vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, ctypes.c_size_t, _vp]),
     "ffcorr_convc1_packed_bytes": (ctypes.c_size_t, []),
     "ffcorr_pack_convc1_weight": (_i, [_vp, _i, _i, _vp, _vp]),
-    "ffcorr_lookup_convc1_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ffcorr_lookup_convc1_tiled_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_lookup_tiled_f16": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffcorr_untile_f16": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),
     "ffcorr_tile_f16": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, _vp]),

@@ -442,6 +442,7 @@ class CorrBlock:
                  storage: Optional[str] = None):
         self.num_levels = num_levels
         self.radius = radius
+        self._sched, self._sched_used = None, 0
         self.storage = storage or "fp32"
         _storage_dtype(self.storage)
         self.sampler = sampler or _default_sampler
@@ -540,10 +541,16 @@ class CorrBlock:
         packed = _packed_convc1(conv)
         bias = conv.bias.detach().contiguous()
         store = torch.empty((b, h, w, 256), device=coords.device, dtype=torch.float32)
+        # the kernel's tile scheduler wants a zeroed int32 per launch: one memset buys 64 of them
+        if self._sched is None or self._sched_used == self._sched.numel():
+            self._sched = torch.zeros(64, device=coords.device, dtype=torch.int32)
+            self._sched_used = 0
+        counter = self._sched[self._sched_used:self._sched_used + 1]
+        self._sched_used += 1
         with _lib.on_device(coords, self._levels[0], packed, bias) as stream:
             _lib.check(_lib.lib().ffcorr_lookup_convc1_tiled_f32(self._ptrs, 4, coords.data_ptr(), packed.data_ptr(), bias.data_ptr(),
-                                                                 store.data_ptr(), b, h, w, 4, self._sampler, stream),
-                       "ffcorr_lookup_convc1_tiled_f32")
+                                                                 store.data_ptr(), counter.data_ptr(), b, h, w, 4, self._sampler,
+                                                                 stream), "ffcorr_lookup_convc1_tiled_f32")
         return store.permute(0, 3, 1, 2)
 
     @staticmethod

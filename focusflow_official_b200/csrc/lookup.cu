@@ -1169,7 +1169,7 @@ constexpr int kMoStages = FFCORR_MO_STAGES;    // 8 gather warps per SM (the pla
 constexpr int kMoRingBytes = kMoStages * kTile * RowGeom<float>::PITCH * 4 + 9 * kTile * 4;   // ring + siy per gather warp
 constexpr int kMoOffRing = 2 * kMoVBytes;
 constexpr int kMoOffBar = kMoOffRing + kMoGatherWarps * kMoRingBytes;
-constexpr int kMoSmem = kMoOffBar + 64;
+constexpr int kMoSmem = kMoOffBar + 128;
 constexpr int kMoWCols = kMoK / 2;             // TMEM columns per channel half of the weights (192)
 constexpr int kMoAccCol = 2 * kMoWCols;        // first accumulator column (384)
 static_assert(kMoAccCol + 2 * kMoQ == 512, "weights + accumulators fill the tensor memory exactly");
@@ -1239,8 +1239,16 @@ struct ConvC1Params {
     const float* bias;             // [256]
     float* out;                    // [B, N, 256] (NHWC)
     int num_tiles;                 // B * tiles_per_batch, tiles of 64 queries
+    int* tile_counter;             // zero at launch: the tile scheduler's atomic
     uint32_t idesc;
 };
+
+#ifdef FFCORR_MO_TRACE      // development build: per-role clock64() stamps of every CTA (ffcorr_debug_mo_trace reads them)
+__device__ long long g_mo_trace[148 * 128];
+#define MO_TRACE(slot) do { if (lane == 0 && blockIdx.x < 148 && (slot) < 128) g_mo_trace[blockIdx.x * 128 + (slot)] = clock64(); } while (0)
+#else
+#define MO_TRACE(slot) do { } while (0)
+#endif
 
 template <bool CUDA_SEM>
 __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const LookupTiledParams p, const ConvC1Params cp) {
@@ -1251,10 +1259,13 @@ __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const Look
     const uint32_t smem_base = smem_u32(smem_mo);
     if (smem_base & 1023u) __trap();
     const uint32_t bar_base = smem_base + kMoOffBar;
-    auto vfull = [&](int i) { return bar_base + 8u * i; };
-    auto vempty = [&](int i) { return bar_base + 8u * (2 + i); };
-    const uint32_t accfull = bar_base + 32u, accempty = bar_base + 40u, wready = bar_base + 48u;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_mo + kMoOffBar + 56);
+    auto vfull = [&](int i) { return bar_base + 8u * i; };            // sample tile i written (8 gather warps)
+    auto vempty = [&](int i) { return bar_base + 8u * (2 + i); };     // the MMAs that read sample tile i retired
+    auto tready = [&](int i) { return bar_base + 8u * (4 + i); };     // tile_q[i] names the next tile for sample tile i
+    const uint32_t accfull = bar_base + 48u, accempty = bar_base + 56u, wready = bar_base + 64u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_mo + kMoOffBar + 72);
+    volatile int* tile_q = reinterpret_cast<volatile int*>(smem_mo + kMoOffBar + 80);      // [2]
+    volatile int* acc_tile = reinterpret_cast<volatile int*>(smem_mo + kMoOffBar + 88);    // [2]: tile of accumulator use k (k & 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -1263,6 +1274,7 @@ __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const Look
         for (int i = 0; i < 2; ++i) {
             mbar_init(vfull(i), kMoGatherWarps);
             mbar_init(vempty(i), 1);
+            mbar_init(tready(i), 1);
         }
         mbar_init(accfull, 1);
         mbar_init(accempty, kMoEpiWarps);
@@ -1279,59 +1291,70 @@ __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const Look
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) MO_TRACE(0);
 
-    if (warp >= kMoGatherWarps && warp < kMoGatherWarps + kMoEpiWarps) {
-        // weights -> tensor memory: lane quarter e of TMEM = channels e*32 .. e*32+31 of either half
-        const int e = warp - kMoGatherWarps;                     // == warp % 4: the TMEM lanes this warp may touch
-        const uint32_t t_lane = tmem_base + ((uint32_t)(e * 32) << 16);
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const uint32_t* wrow = cp.wpacked + (size_t)(half * 128 + e * 32 + lane) * kMoWCols;
-#pragma unroll 1
-            for (int j = 0; j < kMoWCols / 32; ++j) {
-                uint32_t r[32];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + j * 32) + i);
-                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-                }
-                tmem_st_32x32(t_lane + (uint32_t)(half * kMoWCols + j * 32), r);
-            }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(wready);          // only the MMA issuer waits for the weights; the gather starts at once
-    }
-
+    // Tiles of 64 queries are handed out DYNAMICALLY (one atomicAdd on *cp.tile_counter per tile, by the MMA issuer, two
+    // tiles ahead): a unit that takes the exact per-tap path costs 3x a normal one, and with a static round-robin the CTA
+    // that met it finished 12-17 us after the rest (measured with the trace build).
     const int tiles_per_batch = p.tiles_per_batch;
+
     if (warp < kMoGatherWarps) {
         // ===================== gather warps: one unit of 8 queries per tile =====================
         float* ring = reinterpret_cast<float*>(smem_mo + kMoOffRing + warp * kMoRingBytes);
         float* siy = ring + S * ROWBUF;
-        int it = 0;
-        for (int t = blockIdx.x; t < cp.num_tiles; t += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
             const int buf = it & 1;
-            mbar_wait(vempty(buf), (((uint32_t)it >> 1) & 1u) ^ 1u);       // the MMAs that read this tile two rounds ago retired
+            const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+            mbar_wait(tready(buf), ph);
+            const int t = tile_q[buf];
+            if (t >= cp.num_tiles) break;
+            mbar_wait(vempty(buf), ph ^ 1u);                                // the MMAs that read this sample tile two rounds ago retired
+            if (warp == 0) MO_TRACE(50 + it * 2);
+            if (warp == 7) MO_TRACE(80 + it * 2);
             const int b = t / tiles_per_batch;
             const int n0 = (t - b * tiles_per_batch) * kMoQ + warp * kNhwcQ;
             if (n0 < p.N)
                 nhwc_lookup_unit<R, CUDA_SEM, S>(p, b, n0, ring, siy, lane, SampleTileSinks{smem_base + (uint32_t)(buf * kMoVBytes), warp * kNhwcQ});
+            if (warp == 0) MO_TRACE(51 + it * 2);
+            if (warp == 7) MO_TRACE(81 + it * 2);
             fence_proxy_async_smem();                                       // generic writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(vfull(buf));
         }
     } else if (warp < kMoGatherWarps + kMoEpiWarps) {
-        // ===================== epilogue warps =====================
-        const int e = warp - kMoGatherWarps;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)kMoAccCol;
+        // ===================== epilogue warps (first: the weights -> tensor memory) =====================
+        const int e = warp - kMoGatherWarps;                     // == warp % 4: the TMEM lane quarter this warp may touch
+        const uint32_t t_quarter = tmem_base + ((uint32_t)(e * 32) << 16);
+        constexpr int PIECES = 2 * (kMoWCols / 32);              // 12 pieces of 32 columns; every CTA starts at another one
+#pragma unroll 1                                                 // so that 148 CTAs do not read the same lines at the same time
+        for (int i0 = 0; i0 < PIECES; ++i0) {
+            const int c = (i0 + (int)blockIdx.x) % PIECES;
+            const int half = c / (kMoWCols / 32), j = c - half * (kMoWCols / 32);
+            const uint32_t* wrow = cp.wpacked + (size_t)(half * 128 + e * 32 + lane) * kMoWCols + j * 32;
+            uint32_t rr[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow) + i);
+                rr[4 * i] = v.x; rr[4 * i + 1] = v.y; rr[4 * i + 2] = v.z; rr[4 * i + 3] = v.w;
+            }
+            tmem_st_32x32(t_quarter + (uint32_t)(half * kMoWCols + j * 32), rr);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(wready);          // only the MMA issuer waits for the weights; the gather starts at once
+        if (warp == kMoGatherWarps) MO_TRACE(1);
+
+        const uint32_t t_lane = t_quarter + (uint32_t)kMoAccCol;
         const float bias0 = __ldg(cp.bias + e * 32 + lane), bias1 = __ldg(cp.bias + 128 + e * 32 + lane);
-        int it = 0;
-        for (int t = blockIdx.x; t < cp.num_tiles; t += gridDim.x, ++it) {
+        for (uint32_t k = 0;; ++k) {
+            mbar_wait_relaxed(accfull, k & 1u, 256);
+            const int t = acc_tile[k & 1u];
+            if (t < 0) break;
+            if (e == 0) MO_TRACE(100 + (int)k * 2);
+            tc_fence_after();
             const int b = t / tiles_per_batch;
             const int n_tile = (t - b * tiles_per_batch) * kMoQ;
-            mbar_wait(accfull, (uint32_t)it & 1u);
-            tc_fence_after();
             float* orow = cp.out + ((size_t)b * p.N + n_tile) * kMoCout + e * 32 + lane;
             const int nq = min(kMoQ, p.N - n_tile);
             uint32_t v[64];
@@ -1348,34 +1371,59 @@ __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const Look
 #pragma unroll
             for (int j = 0; j < kMoQ; ++j)
                 if (j < nq) orow[(size_t)j * kMoCout + 128] = fmaxf(__uint_as_float(v[j]) + bias1, 0.0f);
+            if (e == 0) MO_TRACE(101 + (int)k * 2);
         }
     } else if (lane == 0) {
-        // ===================== MMA issuer =====================
-        int it = 0;
+        // ===================== tile scheduler + MMA issuer =====================
+        int cur[2];
+        auto hand_out = [&](int buf) {               // next tile for sample tile `buf` (>= num_tiles: none left)
+            cur[buf] = atomicAdd(cp.tile_counter, 1);
+            tile_q[buf] = cur[buf];
+            mbar_arrive(tready(buf));                // release: the gather warps read tile_q after their acquire
+        };
+        hand_out(0);
+        hand_out(1);
         mbar_wait(wready, 0);
-        for (int t = blockIdx.x; t < cp.num_tiles; t += gridDim.x, ++it) {
+        MO_TRACE(2);
+        uint32_t k = 0;
+        for (int it = 0;; ++it) {
             const int buf = it & 1;
-            mbar_wait(vfull(buf), ((uint32_t)it >> 1) & 1u);
-            mbar_wait(accempty, ((uint32_t)it & 1u) ^ 1u);
+            const int t = cur[buf];
+            if (t >= cp.num_tiles) break;            // tiles come in increasing order: nothing later is valid either
+            mbar_wait_relaxed(vfull(buf), ((uint32_t)it >> 1) & 1u, 128);
+            MO_TRACE(10 + it * 4);
+            hand_out(buf);                           // all gather warps are done reading tile_q[buf]
+            mbar_wait(accempty, (k & 1u) ^ 1u);
+            MO_TRACE(11 + it * 4);
+            acc_tile[k & 1u] = t;
+            __threadfence_block();
+            ++k;
             tc_fence_after();
-            const uint32_t vaddr = smem_base + (uint32_t)(buf * kMoVBytes);
-#pragma unroll 1
+            // B: atom ks >> 2 of the sample tile, +32 bytes per k-step inside the atom; both in units of 16 bytes of the
+            // descriptor's address field (shared addresses stay below 2^18, so the field never overflows)
+            const uint64_t b0 = make_smem_desc(smem_base + (uint32_t)(buf * kMoVBytes));
+#pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(kMoAccCol + half * kMoQ);
                 const uint32_t a_tmem = tmem_base + (uint32_t)(half * kMoWCols);
-#pragma unroll 1
-                for (int ks = 0; ks < kMoKSteps; ++ks) {
-                    // B: atom ks >> 2 of the sample tile, +32 bytes per k-step inside the atom (== +2 in the address field)
-                    const uint64_t bdesc = make_smem_desc(vaddr + (uint32_t)((ks >> 2) * kMoAtomBytes)) + (uint64_t)((ks & 3) * 2);
-                    umma_ts_f16(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc, cp.idesc, (uint32_t)(ks != 0));
-                }
+#pragma unroll
+                for (int ks = 0; ks < kMoKSteps; ++ks)
+                    umma_ts_f16(d_tmem, a_tmem + (uint32_t)(ks * 8), b0 + (uint64_t)((ks >> 2) * (kMoAtomBytes >> 4) + (ks & 3) * 2),
+                                cp.idesc, (uint32_t)(ks != 0));
             }
             umma_commit(vempty(buf));
             umma_commit(accfull);
+            MO_TRACE(12 + it * 4);
         }
+        // tell the epilogue there is nothing more
+        mbar_wait(accempty, (k & 1u) ^ 1u);
+        acc_tile[k & 1u] = -1;
+        __threadfence_block();
+        mbar_arrive(accfull);
     }
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) MO_TRACE(127);
     if (warp == kMoGatherWarps + kMoEpiWarps) tmem_dealloc(tmem_base, 512);
 }
 
@@ -1801,6 +1849,13 @@ extern "C" int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, 
                              out_channels_last, stream, "lookup_tiled");
 }
 
+#ifdef FFCORR_MO_TRACE
+extern "C" int ffcorr_debug_mo_trace(void* dst) {
+    FFCORR_CUDA(cudaMemcpyFromSymbol(dst, g_mo_trace, sizeof(g_mo_trace)));
+    return FFCORR_OK;
+}
+#endif
+
 extern "C" size_t ffcorr_convc1_packed_bytes(void) { return (size_t)kMoCout * kMoWCols * 4; }
 
 extern "C" int ffcorr_pack_convc1_weight(const float* weight, int cout, int cin, void* packed, void* stream) {
@@ -1813,12 +1868,12 @@ extern "C" int ffcorr_pack_convc1_weight(const float* weight, int cout, int cin,
 }
 
 extern "C" int ffcorr_lookup_convc1_tiled_f32(const float* const* lvl, int num_levels, const float* coords, const void* packed_weight,
-                                              const float* bias, float* out, int B, int h, int w, int radius, int sampler,
-                                              void* stream) {
+                                              const float* bias, float* out, int* tile_counter, int B, int h, int w, int radius,
+                                              int sampler, void* stream) {
     const char* who = "lookup_convc1_tiled";
     FFCORR_REQUIRE(B >= 0, FFCORR_EINVAL, "%s: B=%d", who, B);
     if (B == 0) return FFCORR_OK;
-    FFCORR_REQUIRE(lvl && coords && packed_weight && bias && out, FFCORR_EINVAL, "%s: null pointer", who);
+    FFCORR_REQUIRE(lvl && coords && packed_weight && bias && out && tile_counter, FFCORR_EINVAL, "%s: null pointer", who);
     FFCORR_REQUIRE(num_levels == 4 && radius == 4, FFCORR_EINVAL,
                    "%s: built for the reference's 4 levels x radius 4 (324 planes, update.py:82), got %d levels, radius %d", who,
                    num_levels, radius);
@@ -1852,6 +1907,7 @@ extern "C" int ffcorr_lookup_convc1_tiled_f32(const float* const* lvl, int num_l
     cp.bias = bias;
     cp.out = out;
     cp.num_tiles = (int)num_tiles;
+    cp.tile_counter = tile_counter;
     // instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3, M >> 4 (M = 128 channels, N = 64 queries)
     cp.idesc = (1u << 4) | ((uint32_t)(kMoQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());

@@ -40,6 +40,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// The same wait for warps that idle for microseconds next to busy ones (epilogue / MMA roles of lookup_convc1_kernel):
+// back off between polls so the spin does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned sleep_ns) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(sleep_ns);
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -168,11 +168,14 @@ int ffcorr_lookup_tiled_f32(const float* const* lvl, int num_levels, const float
  * fp32 accumulation; samples saturate at +-65504.  Built for the reference's 4 levels x radius 4 only.
  *   ffcorr_pack_convc1_weight: convc1.weight [256, 324] fp32 (device) -> the kernel's operand order, fp16,
  *   ffcorr_convc1_packed_bytes() bytes; do it once per set of weights.
+ *   tile_counter: one device int32 that is ZERO when the launch starts (stream-ordered) and is not shared with another
+ *   launch in flight; the persistent kernel hands its tiles of 64 queries out through it and leaves it non-zero.
  */
 size_t ffcorr_convc1_packed_bytes(void);
 int ffcorr_pack_convc1_weight(const float* weight, int cout, int cin, void* packed, void* stream);
 int ffcorr_lookup_convc1_tiled_f32(const float* const* lvl, int num_levels, const float* coords, const void* packed_weight,
-                                   const float* bias, float* out, int B, int h, int w, int radius, int sampler, void* stream);
+                                   const float* bias, float* out, int* tile_counter, int B, int h, int w, int radius,
+                                   int sampler, void* stream);
 
 /*
  * Opt-in HALF-PRECISION STORAGE of the pyramid (the Python side: CorrBlock(..., storage="fp16")).  Same geometry as

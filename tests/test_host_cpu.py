@@ -113,12 +113,13 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert L.ffcorr_backwarp_f32(None, None, None, None, None, 0, 32, 8, 8, ctypes.c_float(1.0), None) == 0   # empty batch
     # the lookup fused with convc1 (update.py:82-83,90): built for 4 levels x radius 4 and Conv2d(324, 256, 1)
     assert L.ffcorr_convc1_packed_bytes() == 256 * 384 * 2
-    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 3, 1, 1, 1, 1, 1, 16, 16, 4, 1, None) == -1
+    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 3, 1, 1, 1, 1, 1, 1, 16, 16, 4, 1, None) == -1
     assert b"4 levels x radius 4" in L.ffcorr_last_error()
-    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 4, 1, 1, 1, 1, 1, 16, 16, 3, 1, None) == -1
-    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 4, 1, None, 1, 1, 1, 16, 16, 4, 1, None) == -1     # null packed weight
-    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 4, 16, 16, 16, 16, 1, 16, 16, 4, 1, None) == -1    # null level pointers
-    assert L.ffcorr_lookup_convc1_tiled_f32(None, 4, None, None, None, None, 0, 16, 16, 4, 1, None) == 0
+    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 4, 1, 1, 1, 1, 1, 1, 16, 16, 3, 1, None) == -1
+    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 4, 1, None, 1, 1, 1, 1, 16, 16, 4, 1, None) == -1     # null packed weight
+    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 4, 1, 1, 1, 1, None, 1, 16, 16, 4, 1, None) == -1     # null tile counter
+    assert L.ffcorr_lookup_convc1_tiled_f32(ptrs, 4, 16, 16, 16, 16, 16, 1, 16, 16, 4, 1, None) == -1   # null level pointers
+    assert L.ffcorr_lookup_convc1_tiled_f32(None, 4, None, None, None, None, None, 0, 16, 16, 4, 1, None) == 0
     assert L.ffcorr_pack_convc1_weight(1, 128, 324, 1, None) == -1
     assert b"Conv2d(324, 256, 1)" in L.ffcorr_last_error()
     # empty batches are a no-op, even with null pointers

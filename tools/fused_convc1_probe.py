@@ -10,6 +10,10 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import focusflow_official_b200 as ff  # noqa: E402
 
+if os.environ.get("FFCORR_PROBE_LIB"):          # an alternative build of libffcorr.so (kernel variants under test)
+    from focusflow_official_b200 import _lib as _L
+    _L.LIB_PATH = os.path.abspath(os.environ["FFCORR_PROBE_LIB"])
+
 
 def main():
     torch.backends.cudnn.allow_tf32 = False
@@ -80,6 +84,30 @@ def main():
                 print(json.dumps({"lookup_us": t(lambda: blk(coords)),
                                   "lookup_plus_cudnn_conv_relu_us": t(lambda: torch.cudnn_convolution_relu(blk(coords), conv_cl.weight, conv_cl.bias, (1, 1), (0, 0), (1, 1), 1)),
                                   "fused_us": t(lambda: blk.lookup_conv(coords, conv))}), flush=True)
+                dump_trace()
+
+
+def dump_trace():
+    """Development builds with -DFFCORR_MO_TRACE: per-role clock stamps of the last launch, in us since the CTA started."""
+    import ctypes
+
+    import numpy as np
+    from focusflow_official_b200 import _lib
+    L = _lib.lib()
+    if not hasattr(L, "ffcorr_debug_mo_trace"):
+        return
+    buf = np.zeros(148 * 128, dtype=np.int64)
+    L.ffcorr_debug_mo_trace.argtypes = [ctypes.c_void_p]
+    L.ffcorr_debug_mo_trace(buf.ctypes.data)
+    tr = buf.reshape(148, 128)
+    for cta in (0, 31, 32, 100, 147):
+        t0 = tr[cta, 0]
+        us = lambda s: round((tr[cta, s] - t0) / 1965.0, 2) if tr[cta, s] else None
+        print(json.dumps({"cta": cta, "weights_in_tmem": us(1), "mma_sees_weights": us(2), "end": us(127),
+                          "mma[vfull,accempty,issued]": [[us(10 + i * 4), us(11 + i * 4), us(12 + i * 4)] for i in range(7)],
+                          "gather_w0[start,done]": [[us(50 + i * 2), us(51 + i * 2)] for i in range(7)],
+                          "gather_w7[start,done]": [[us(80 + i * 2), us(81 + i * 2)] for i in range(7)],
+                          "epilogue[accfull,stored]": [[us(100 + i * 2), us(101 + i * 2)] for i in range(7)]}), flush=True)
 
 
 if __name__ == "__main__":
