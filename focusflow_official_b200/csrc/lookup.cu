@@ -1269,6 +1269,7 @@ __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const Look
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (warp == 0) MO_TRACE(120);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -1281,11 +1282,15 @@ __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const Look
         mbar_init(wready, kMoEpiWarps);
         fence_barrier_init();
     }
-    if (warp == kMoGatherWarps + kMoEpiWarps) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == kMoGatherWarps + kMoEpiWarps) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        MO_TRACE(121);
+    }
     // both sample tiles start as zeros: the pad slots (a = 9 of every window row, K' >= 360) are never written with
     // anything else, and a 0 x NaN from uninitialised shared memory would poison the accumulators
     for (int i = threadIdx.x; i < 2 * kMoVBytes / 16; i += kMoThreads)
         reinterpret_cast<uint4*>(smem_mo)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) MO_TRACE(122);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -1424,7 +1429,10 @@ __global__ void __launch_bounds__(kMoThreads, 1) lookup_convc1_kernel(const Look
     tc_fence_before();
     __syncthreads();
     if (warp == 0) MO_TRACE(127);
-    if (warp == kMoGatherWarps + kMoEpiWarps) tmem_dealloc(tmem_base, 512);
+    if (warp == kMoGatherWarps + kMoEpiWarps) {
+        tmem_dealloc(tmem_base, 512);
+        MO_TRACE(123);
+    }
 }
 
 // W [256][L*81] (convc1.weight, input channel = level*81 + a*9 + bb, corr.py:37-43) -> W' [256][384] fp16 in the K' order of

@@ -81,7 +81,12 @@ def main():
             torch.backends.cudnn.benchmark = True
             conv_cl = conv.to(memory_format=torch.channels_last)
             with torch.no_grad():
-                print(json.dumps({"lookup_us": t(lambda: blk(coords)),
+                smooth = grid + flow                  # no artificial outliers: every unit takes the fast path
+                print(json.dumps({"coords": "smooth flow only", "lookup_us": t(lambda: blk(smooth)),
+                                  "lookup_plus_cudnn_conv_relu_us": t(lambda: torch.cudnn_convolution_relu(blk(smooth), conv_cl.weight, conv_cl.bias, (1, 1), (0, 0), (1, 1), 1)),
+                                  "fused_us": t(lambda: blk.lookup_conv(smooth, conv))}), flush=True)
+                print(json.dumps({"coords": "with 8 windows at -50 (integer coordinates -> exact per-tap path) and 8 at inf",
+                                  "lookup_us": t(lambda: blk(coords)),
                                   "lookup_plus_cudnn_conv_relu_us": t(lambda: torch.cudnn_convolution_relu(blk(coords), conv_cl.weight, conv_cl.bias, (1, 1), (0, 0), (1, 1), 1)),
                                   "fused_us": t(lambda: blk.lookup_conv(coords, conv))}), flush=True)
                 dump_trace()
@@ -102,8 +107,9 @@ def dump_trace():
     tr = buf.reshape(148, 128)
     for cta in (0, 31, 32, 100, 147):
         t0 = tr[cta, 0]
-        us = lambda s: round((tr[cta, s] - t0) / 1965.0, 2) if tr[cta, s] else None
-        print(json.dumps({"cta": cta, "weights_in_tmem": us(1), "mma_sees_weights": us(2), "end": us(127),
+        us = lambda s: round(float(tr[cta, s] - t0) / 1965.0, 2) if tr[cta, s] else None
+        print(json.dumps({"cta": cta, "entry": us(120), "tmem_allocated": us(121), "smem_zeroed": us(122), "tmem_freed": us(123),
+                          "weights_in_tmem": us(1), "mma_sees_weights": us(2), "end": us(127),
                           "mma[vfull,accempty,issued]": [[us(10 + i * 4), us(11 + i * 4), us(12 + i * 4)] for i in range(7)],
                           "gather_w0[start,done]": [[us(50 + i * 2), us(51 + i * 2)] for i in range(7)],
                           "gather_w7[start,done]": [[us(80 + i * 2), us(81 + i * 2)] for i in range(7)],
