@@ -13,18 +13,27 @@
 // grid_sampler_2d_kernel; scalar division = multiplication by the fp32 reciprocal), so the result agrees with the
 // reference formula run through torch on the same GPU to rounding.
 // Algorithmic bytes: 4 * B*H*W * (2C + 2): read `input` once (taps overlap between neighbours), write the result.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ffcorr {
 namespace {
 
+// Block = TX x (256 / TX) pixels (TX = 64, 32 or 16: the small decoder levels are 32 and 16 pixels wide) x one CHUNK of
+// channels: blockIdx.z = b * chunks + chunk.  Splitting the channels over the grid is what keeps the small levels from
+// being latency-bound (level 5 is 14 x 32 pixels x 128 channels: one thread per pixel looping over all channels was 64
+// blocks of 128 dependent iterations).
+template <int TX>
 __global__ void __launch_bounds__(256) backwarp_kernel(const float* __restrict__ in, const float* __restrict__ flow,
                                                        const float* __restrict__ gx, const float* __restrict__ gy,
                                                        float* __restrict__ out, int C, int H, int W, float flow_scale,
-                                                       float rcp_half_wm1, float rcp_half_hm1) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const int b = blockIdx.z;
+                                                       float rcp_half_wm1, float rcp_half_hm1, int chunks, int chunk_c) {
+    const int x = blockIdx.x * TX + (threadIdx.x % TX);
+    const int y = blockIdx.y * (256 / TX) + (threadIdx.x / TX);
+    const int b = blockIdx.z / chunks;
+    const int c0 = (blockIdx.z - b * chunks) * chunk_c;
+    const int c1 = min(C, c0 + chunk_c);
     if (x >= W || y >= H) return;
     const size_t plane = (size_t)H * W;
     const size_t pix = (size_t)y * W + x;
@@ -61,11 +70,11 @@ __global__ void __launch_bounds__(256) backwarp_kernel(const float* __restrict__
     const float* ip = in + (size_t)b * C * plane;
     float* op = out + (size_t)b * C * plane + pix;
     if (mask == 0.f) {
-        for (int c = 0; c < C; ++c) op[(size_t)c * plane] = 0.f;
+        for (int c = c0; c < c1; ++c) op[(size_t)c * plane] = 0.f;
         return;
     }
 #pragma unroll 4
-    for (int c = 0; c < C; ++c) {
+    for (int c = c0; c < c1; ++c) {
         const float* p = ip + (size_t)c * plane + o00;
         float acc = 0.f;
         if (onw) acc = __fmaf_rn(__ldg(p), wnw, acc);
@@ -87,11 +96,23 @@ extern "C" int ffcorr_backwarp_f32(const float* input, const float* flow, const 
     if (B == 0) return FFCORR_OK;
     FFCORR_REQUIRE(input && flow && grid_x && grid_y && out, FFCORR_EINVAL, "backwarp: null pointer");
     FFCORR_REQUIRE(B <= 65535, FFCORR_EINVAL, "backwarp: B=%d exceeds the grid z extent", B);
-    const dim3 grid((unsigned)ceil_div(W, 64), (unsigned)ceil_div(H, 4), (unsigned)B);
+    const int tx = W > 32 ? 64 : (W > 16 ? 32 : 16);
+    // channel chunks: enough blocks for ~8 per SM, at least 8 channels per block (the per-pixel set-up is repeated per chunk)
+    const int64_t pix_blocks = (int64_t)ceil_div(W, tx) * ceil_div(H, 256 / tx) * B;
+    int chunks = (int)std::min<int64_t>(ceil_div(C, 8), std::max<int64_t>(1, ceil_div64((int64_t)sm_count() * 8, pix_blocks)));
+    const int chunk_c = ceil_div(C, chunks);
+    chunks = ceil_div(C, chunk_c);
+    FFCORR_REQUIRE((int64_t)B * chunks <= 65535, FFCORR_EINVAL, "backwarp: B * channel chunks = %lld exceeds the grid z extent", (long long)B * chunks);
+    const dim3 grid((unsigned)ceil_div(W, tx), (unsigned)ceil_div(H, 256 / tx), (unsigned)(B * chunks));
     // (size - 1.0) / 2.0 is a Python double in the reference; ATen turns "tensor / scalar" into a multiplication by
     // the fp32 reciprocal of the scalar cast to float
     const float rw = 1.0f / (float)((W - 1.0) / 2.0);
     const float rh = 1.0f / (float)((H - 1.0) / 2.0);
-    backwarp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(input, flow, grid_x, grid_y, out, C, H, W, flow_scale, rw, rh);
+    if (tx == 64)
+        backwarp_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(input, flow, grid_x, grid_y, out, C, H, W, flow_scale, rw, rh, chunks, chunk_c);
+    else if (tx == 32)
+        backwarp_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(input, flow, grid_x, grid_y, out, C, H, W, flow_scale, rw, rh, chunks, chunk_c);
+    else
+        backwarp_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(input, flow, grid_x, grid_y, out, C, H, W, flow_scale, rw, rh, chunks, chunk_c);
     return check_launch("backwarp_kernel");
 }

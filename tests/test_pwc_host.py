@@ -55,7 +55,8 @@ def test_cpu_is_refused():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,scale", [((2, 32, 28, 64), 5.0), ((1, 96, 14, 32), 1.25), ((2, 20, 11, 14), 0.625), ((1, 128, 7, 16), 2.5)])
+@pytest.mark.parametrize("shape,scale", [((2, 32, 28, 64), 5.0), ((1, 96, 14, 32), 1.25), ((2, 20, 11, 14), 0.625), ((1, 128, 7, 16), 2.5),
+                                         ((4, 32, 112, 256), 2.5), ((1, 196, 9, 20), 1.0), ((3, 7, 5, 70), 1.0)])
 def test_backwarp_kernel_vs_the_reference_formula(shape, scale):
     """ffcorr_backwarp_f32 == ff_pwcnet.py:27-46 run through torch's CUDA kernels: flows that stay inside, leave the
     image (validity mask), land exactly on pixel centres, and are non-finite."""

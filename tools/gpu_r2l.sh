@@ -1,15 +1,10 @@
 #!/bin/bash
-# A/B/A/B of the whole model with and without the fused lookup + convc1, 30 timed steps each
 cd /root/repo
 OUT=gpurun_out/r2l; mkdir -p $OUT
-for i in 1 2; do for tag in plain fused; do
-  FLAG=""; [ $tag = fused ] && FLAG="--fuse-convc1"
-  timeout 200 python bench.py --steps 30 --warmup 5 --no-stock --no-pwc --no-cpu-baseline $FLAG > $OUT/ab_${tag}_$i.json 2> $OUT/ab.err || tail -3 $OUT/ab.err
-done; done
+timeout 300 python -m pytest tests/test_pwc_host.py -q -m gpu > $OUT/pytest_pwc_host.log 2>&1; echo "pwc host tests exit=$?"; tail -3 $OUT/pytest_pwc_host.log | cut -c1-300
+timeout 300 python bench.py --config 3 --steps 5 --warmup 3 > $OUT/bench_c3.json 2> $OUT/bench_c3.err; echo "c3 exit=$?"
 python - <<'PY'
 import json
-for i in (1,2):
-    for n in ("plain","fused"):
-        d=json.load(open(f"gpurun_out/r2l/ab_{n}_{i}.json"))
-        print(n, i, "pairs/s", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "lookup launch ms", d["roofline"]["launch_ms"])
+d=json.load(open("gpurun_out/r2l/bench_c3.json"))
+print(d["value"], d["ms_per_step"], d["roofline"]["ms_per_forward"], d["roofline"]["backwarp_ms_per_forward"])
 PY
