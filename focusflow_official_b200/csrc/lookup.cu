@@ -7,8 +7,10 @@
 // [h_i, w_i] correlation map is read once, (2r+1)^2 bilinear samples are written.
 // Algorithmic bytes per query (r = 4, L = 4): 4*100*4 read + 324*4 write + 8 = 2904 B.
 //
-// Three kernels: lookup_kernel (row-major pyramid, described below), lookup_tiled_stream_kernel (tiled pyramid,
-// the inference default, described at its definition) and lookup_bwd_kernel (adjoint w.r.t. the pyramid).
+// Kernels: lookup_kernel (row-major pyramid, described below); on the tiled pyramid lookup_tiled_stream_kernel (NCHW
+// output), lookup_tiled_nhwc_kernel (channels-last output, the host model's default), lookup_tiled_nhwc_h_kernel (fp16
+// storage) and lookup_convc1_kernel (the lookup fused with its consumer convc1 + ReLU on the tensor cores) -- each
+// described at its definition; lookup_bwd_kernel (adjoint w.r.t. the pyramid).
 //
 // Work decomposition
 //   unit   = (level, tile of 32 consecutive queries of one batch item), one warp each;
@@ -1165,7 +1167,7 @@ constexpr int kMoVBytes = (kMoK / 64) * kMoAtomBytes;                 // 48 KB
 #ifndef FFCORR_MO_STAGES
 #define FFCORR_MO_STAGES 4
 #endif
-constexpr int kMoStages = FFCORR_MO_STAGES;    // 8 gather warps per SM (the plain kernel has 10): one more row in flight per warp
+constexpr int kMoStages = FFCORR_MO_STAGES;    // 8 gather warps per SM (the plain kernel has 10); 4, 5 and 6 stages measure the same
 constexpr int kMoRingBytes = kMoStages * kTile * RowGeom<float>::PITCH * 4 + 9 * kTile * 4;   // ring + siy per gather warp
 constexpr int kMoOffRing = 2 * kMoVBytes;
 constexpr int kMoOffBar = kMoOffRing + kMoGatherWarps * kMoRingBytes;
