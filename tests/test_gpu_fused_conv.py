@@ -152,3 +152,20 @@ def test_host_model_with_fused_convc1_gives_the_same_flow():
           f"TF32-vs-fp32 host convs: mean {drift.mean().item():.2e} max {drift.max().item():.2e}")
     assert torch.isfinite(got).all()
     assert epe.max().item() <= max(2.0 * drift.max().item(), 2e-3)
+
+
+def test_packed_weight_layout():
+    """ffcorr_pack_convc1_weight: W[co, level*81 + a*9 + bb] (corr.py:37-43 channel order) lands at W'[co, level*90 + bb*10 + a]
+    as fp16 (RN); every other slot of the 384 is zero."""
+    from focusflow_official_b200.corr import _packed_convc1
+
+    conv = torch.nn.Conv2d(324, 256, 1).to(DEV)
+    packed = _packed_convc1(conv).view(torch.float16).view(256, 384).cpu().numpy()
+    w = conv.weight.detach().reshape(256, 324).cpu().numpy()
+    exp = np.zeros((256, 384), np.float16)
+    for level in range(4):
+        for a in range(9):
+            for bb in range(9):
+                exp[:, level * 90 + bb * 10 + a] = w[:, level * 81 + a * 9 + bb].astype(np.float16)
+    assert np.array_equal(packed, exp)
+    assert _packed_convc1(conv) is _packed_convc1(conv)          # cached until the weights change
