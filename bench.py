@@ -575,6 +575,11 @@ def run_gpu_arm(args, rank, world, local):
     if args.update_cl:
         model.flow_net.update_block.to(memory_format=torch.channels_last)
         model.flow_net.update_channels_last = True
+    if args.cnet_cl:
+        # host plumbing: the context encoder (eval-mode BatchNorm has an NHWC kernel) in channels_last -> no NCHW<->NHWC
+        # transposes around its convolutions (+3.2 % pairs/s).  The feature encoder stays NCHW: F.instance_norm has no
+        # channels_last path, and a var_mean formulation of it gains nothing more (NOTES).
+        model.flow_net.cnet.to(memory_format=torch.channels_last)
     if args.storage:
         model.flow_net.corr_storage = args.storage
     if args.fuse_convc1:
@@ -760,6 +765,7 @@ def run_gpu_arm(args, rank, world, local):
                    "pyramid_storage": storage, "lookup_output": ("none: convc1 + ReLU fused into the lookup kernel" if meter.fused_conv else
                                      "channels_last (NHWC), written by the kernel" if meter.nhwc else "NCHW"),
                    "host_convs": "PyTorch/cuDNN TF32 (reference ALLOW_TF32)", "channels_last": bool(args.channels_last), "update_block_channels_last": bool(args.update_cl),
+                   "context_encoder_channels_last": bool(args.cnet_cl),
                    "l2": "per-step working set (2.3 GB pyramid + activations) >> 126 MB L2, no flush needed",
                    "sharding": "by image pair, no data-path collective",
                    "e2e_pipeline": "copy stream: H2D of batch i+1 and D2H of batch i-1 overlap the compute of batch i"},
@@ -1053,6 +1059,8 @@ def main():
                     help="heuristic cuDNN algorithm choice instead of timing-based autotuning (profiler runs: the "
                          "autotuner mis-times kernels under ncu and picks different engines)")
     ap.add_argument("--channels-last", dest="channels_last", action="store_true", default=False)
+    ap.add_argument("--cnet-nchw", dest="cnet_cl", action="store_false", default=True,
+                    help="keep the context encoder in NCHW instead of channels_last (host plumbing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--update-nchw", dest="update_cl", action="store_false", default=True,
                     help="run the GRU update block in NCHW instead of channels_last (host plumbing)")

@@ -1279,6 +1279,38 @@ def test_channels_last_blocks_and_the_host_model_use_no_layout_copy():
         assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())
 
 
+def test_context_encoder_in_channels_last_gives_the_same_flow():
+    """bench.py runs the context encoder (eval-mode BatchNorm) in channels_last: the same convolutions without layout
+    transposes around them.  Flow must agree with the NCHW run to well inside what TF32 host convolutions move it."""
+    from test_host_model import make_model
+    from weights import synthetic_pair
+
+    model = make_model().to(DEV).eval()
+    model.flow_net.update_block.to(memory_format=torch.channels_last)
+    model.flow_net.update_channels_last = True
+    im1, im2, m1, _ = (x.to(DEV) for x in synthetic_pair(2, 128, 192, seed=5))
+    before = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad():
+            torch.backends.cudnn.allow_tf32 = False
+            exact = model(im1, im2, m1, None, raft_iters=12, test_mode=True)[1]
+            torch.backends.cudnn.allow_tf32 = True                         # the reference's run setting (common.py:25-27)
+            ref = model(im1, im2, m1, None, raft_iters=12, test_mode=True)[1]
+            model.flow_net.cnet.to(memory_format=torch.channels_last)
+            got = model(im1, im2, m1, None, raft_iters=12, test_mode=True)[1]
+            torch.backends.cudnn.allow_tf32 = False
+            got_exact = model(im1, im2, m1, None, raft_iters=12, test_mode=True)[1]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = before
+    drift = (ref - exact).norm(dim=1).max().item()                         # what TF32 alone does to the flow
+    epe = (got - ref).norm(dim=1).max().item()
+    epe_exact = (got_exact - exact).norm(dim=1).max().item()               # fp32 convolutions: only the summation order differs
+    print(f"context encoder NHWC vs NCHW: EPE max {epe:.2e} (TF32), {epe_exact:.2e} (fp32); TF32-vs-fp32 drift {drift:.2e}")
+    assert torch.isfinite(got).all()
+    assert epe <= max(2.0 * drift, 2e-3)
+    assert epe_exact <= 1e-3
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_launches_follow_the_tensors_device_not_the_current_one():
     """with cuda:0 current and the model on cuda:1, kernels, TMA descriptors and the stream must be those of
