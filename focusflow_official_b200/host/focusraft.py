@@ -18,6 +18,7 @@ Only `CorrBlock` differs: it is `focusflow_official_b200.CorrBlock` (sm_100a ker
 """
 from __future__ import annotations
 
+import weakref
 from types import SimpleNamespace
 from typing import Callable, Optional
 
@@ -39,17 +40,43 @@ def _conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     return F.relu(conv(x))
 
 
-def _conv_norm(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    """norm(conv(x)) without the separate broadcast bias add when the norm makes it redundant:
-    InstanceNorm (no affine, per-sample statistics) subtracts the channel mean, so the bias cancels exactly;
-    eval-mode BatchNorm has it folded into the running mean.  Inference only; otherwise the plain composition."""
+_folded_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _folded_bn(conv: nn.Conv2d, norm: nn.BatchNorm2d):
+    """Eval-mode BatchNorm folded into the convolution in front of it: w' = w * g / sqrt(var + eps),
+    b' = (b - mean) * g / sqrt(var + eps) + beta.  Cached until any of the six tensors changes."""
+    ts = (conv.weight, conv.bias, norm.weight, norm.bias, norm.running_mean, norm.running_var)
+    key = tuple((t.data_ptr(), t._version) for t in ts) + (conv.weight.is_contiguous(memory_format=torch.channels_last),)
+    hit = _folded_cache.get(conv)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    scale = norm.weight * torch.rsqrt(norm.running_var + norm.eps)
+    w = conv.weight * scale.view(-1, 1, 1, 1)
+    if key[-1]:
+        w = w.contiguous(memory_format=torch.channels_last)
+    b = (conv.bias - norm.running_mean) * scale + norm.bias
+    _folded_cache[conv] = (key, w, b)
+    return w, b
+
+
+def _conv_norm(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    """[relu(] norm(conv(x)) [)] with fewer kernels at inference on CUDA:
+    InstanceNorm (no affine, per-sample statistics) subtracts the channel mean, so the conv bias cancels exactly and its
+    broadcast add is dropped; eval-mode BatchNorm is an affine map per channel, so it is FOLDED into the convolution's
+    weights and bias (one cuDNN ConvBiasAct call instead of conv + bias add + batch-norm + relu).  Same function as the
+    reference's composition up to fp32 rounding of the folded weights; under autograd the plain composition is used."""
     if x.is_cuda and not torch.is_grad_enabled() and conv.bias is not None and conv.padding_mode == "zeros":
         if isinstance(norm, nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats:
-            return norm(F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups))
-        if isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats:
-            y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
-            return F.batch_norm(y, norm.running_mean - conv.bias, norm.running_var, norm.weight, norm.bias, False, 0.0, norm.eps)
-    return norm(conv(x))
+            y = norm(F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups))
+            return F.relu(y, inplace=True) if relu else y
+        if isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats and norm.affine:
+            w, b = _folded_bn(conv, norm)
+            if relu:
+                return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+            return F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    y = norm(conv(x))
+    return F.relu(y, inplace=True) if relu else y
 
 
 def _norm(kind: str, ch: int) -> nn.Module:
@@ -80,8 +107,8 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride), self.norm3)
 
     def forward(self, x):
-        y = self.relu(_conv_norm(self.conv1, self.norm1, x))
-        y = self.relu(_conv_norm(self.conv2, self.norm2, y))
+        y = _conv_norm(self.conv1, self.norm1, x, relu=True)
+        y = _conv_norm(self.conv2, self.norm2, y, relu=True)
         if self.downsample is not None:
             x = _conv_norm(self.downsample[0], self.downsample[1], x)
         return self.relu(x + y)
@@ -151,8 +178,8 @@ class CCEEncoder(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
     def forward(self, x, mask):
-        mask = self.mask_relu1(_conv_norm(self.mask_conv1, self.mask_norm1, mask))
-        x = self.relu1(_conv_norm(self.conv1, self.norm1, x))
+        mask = _conv_norm(self.mask_conv1, self.mask_norm1, mask, relu=True)
+        x = _conv_norm(self.conv1, self.norm1, x, relu=True)
         mask, x = self.fusion1(mask, x)
         mask, x = self.fusion2(self.mask_layer1(mask), self.layer1(x))
         mask, x = self.fusion3(self.mask_layer2(mask), self.layer2(x))
