@@ -60,6 +60,25 @@ def _folded_bn(conv: nn.Conv2d, norm: nn.BatchNorm2d):
     return w, b
 
 
+_stacked_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _stacked(a: nn.Conv2d, b: nn.Conv2d):
+    """Weights and biases of two convolutions of the same geometry stacked along the output channels (cached until one of
+    the four tensors changes): conv(x, cat(wa, wb)) == cat(conv_a(x), conv_b(x))."""
+    ts = (a.weight, a.bias, b.weight, b.bias)
+    key = tuple((t.data_ptr(), t._version) for t in ts) + (a.weight.is_contiguous(memory_format=torch.channels_last),)
+    hit = _stacked_cache.get(a)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    w = torch.cat([a.weight, b.weight], dim=0)
+    if key[-1]:
+        w = w.contiguous(memory_format=torch.channels_last)
+    bias = torch.cat([a.bias, b.bias], dim=0)
+    _stacked_cache[a] = (key, w, bias)
+    return w, bias
+
+
 def _conv_norm(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
     """[relu(] norm(conv(x)) [)] with fewer kernels at inference on CUDA:
     InstanceNorm (no affine, per-sample statistics) subtracts the channel mean, so the conv bias cancels exactly and its
@@ -210,6 +229,15 @@ class SepConvGRU(nn.Module):
 
     def _step(self, h, x, cz, cr, cq):
         hx = torch.cat([h, x], dim=1)
+        if hx.is_cuda and not torch.is_grad_enabled():
+            # inference plumbing: the z and r gates read the same input through convolutions of the same shape -> ONE
+            # convolution with the two weight sets stacked along the output channels (every output channel is computed
+            # exactly as before), one sigmoid; and the state update as one lerp kernel: h + z (q - h) == (1 - z) h + z q
+            w, b = _stacked(cz, cr)
+            zr = torch.sigmoid(F.conv2d(hx, w, b, cz.stride, cz.padding, cz.dilation, cz.groups))
+            z, r = zr[:, :cz.out_channels], zr[:, cz.out_channels:]
+            q = torch.tanh(cq(torch.cat([r * h, x], dim=1)))
+            return torch.lerp(h, q, z)
         z = torch.sigmoid(cz(hx))
         r = torch.sigmoid(cr(hx))
         q = torch.tanh(cq(torch.cat([r * h, x], dim=1)))
