@@ -260,12 +260,15 @@ class MotionEncoder(nn.Module):
         self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
         self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
 
-    def forward(self, flow, corr, cor1=None):
+    def features(self, flow, corr, cor1=None):
+        """The 126 learned motion channels (update.py:90-96 without the final concatenation with `flow`)."""
         # cor1: relu(convc1(corr)) already computed by the fused lookup (CorrBlock.lookup_conv)
         cor = _conv_relu(self.convc2, _conv_relu(self.convc1, corr) if cor1 is None else cor1)
         flo = _conv_relu(self.convf2, _conv_relu(self.convf1, flow))
-        out = _conv_relu(self.conv, torch.cat([cor, flo], dim=1))
-        return torch.cat([out, flow], dim=1)
+        return _conv_relu(self.conv, torch.cat([cor, flo], dim=1))
+
+    def forward(self, flow, corr, cor1=None):
+        return torch.cat([self.features(flow, corr, cor1), flow], dim=1)
 
 
 class UpdateBlock(nn.Module):
@@ -279,8 +282,8 @@ class UpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(256, 64 * 9, 1))
 
     def forward(self, net, inp, corr, flow, with_mask: bool = True, cor1=None):
-        motion = self.encoder(flow, corr, cor1)
-        net = self.gru(net, torch.cat([inp, motion], dim=1))
+        # cat([inp, cat([out, flow])]) (update.py:97,128-129) as one three-way concatenation: same channel order
+        net = self.gru(net, torch.cat([inp, self.encoder.features(flow, corr, cor1), flow], dim=1))
         delta = self.flow_head(net)
         mask = 0.25 * self.mask[2](_conv_relu(self.mask[0], net)) if with_mask else None  # 0.25: update.py:133-134
         return net, mask, delta
