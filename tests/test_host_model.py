@@ -70,3 +70,39 @@ def test_b200_corrblock_refuses_cpu():
     with pytest.raises(NotImplementedError):
         with torch.no_grad():
             model(im1, im2, m1, m2, raft_iters=1, test_mode=True)
+
+
+def test_inference_plumbing_helpers_are_the_same_functions():
+    """The inference-only shortcuts of host/focusraft.py, checked on CPU through their helpers: eval-mode BatchNorm folded
+    into the convolution in front of it, two same-shape convolutions stacked along the output channels, lerp as the GRU
+    state update; and the caches follow in-place weight updates."""
+    import torch.nn.functional as F
+
+    from focusflow_official_b200.host import focusraft as FR
+
+    torch.manual_seed(0)
+    conv, bn = torch.nn.Conv2d(5, 7, 3, padding=1), torch.nn.BatchNorm2d(7).eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0); bn.weight.normal_(); bn.bias.normal_()
+        x = torch.randn(2, 5, 9, 11)
+        w, b = FR._folded_bn(conv, bn)
+        assert torch.allclose(F.conv2d(x, w, b, padding=1), bn(conv(x)), atol=2e-6)
+        assert FR._folded_bn(conv, bn)[0] is w                       # cached
+        bn.running_mean.add_(1.0)                                    # in-place update -> re-folded
+        w2, b2 = FR._folded_bn(conv, bn)
+        assert w2 is not w and torch.allclose(F.conv2d(x, w2, b2, padding=1), bn(conv(x)), atol=2e-6)
+
+        ca, cb = torch.nn.Conv2d(6, 4, (1, 5), padding=(0, 2)), torch.nn.Conv2d(6, 4, (1, 5), padding=(0, 2))
+        y = torch.randn(2, 6, 8, 10)
+        ws, bs = FR._stacked(ca, cb)
+        both = F.conv2d(y, ws, bs, padding=(0, 2))
+        assert torch.allclose(both[:, :4], ca(y), atol=1e-6) and torch.allclose(both[:, 4:], cb(y), atol=1e-6)
+        ca.weight.mul_(2.0)
+        assert torch.allclose(F.conv2d(y, *FR._stacked(ca, cb), padding=(0, 2))[:, :4], ca(y), atol=1e-6)
+
+        h, q, z = torch.randn(3, 4), torch.randn(3, 4), torch.rand(3, 4)
+        assert torch.allclose(torch.lerp(h, q, z), (1 - z) * h + z * q, atol=1e-6)
+
+        enc = FR.MotionEncoder(4, 4)
+        flow, corr = torch.randn(1, 2, 6, 8), torch.randn(1, 324, 6, 8)
+        assert torch.equal(enc(flow, corr), torch.cat([enc.features(flow, corr), flow], dim=1))
